@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the lightning-pose hot path on B200 (driver contract: see the task statement).
+
+Workload = BASELINE.json configs[1]: ResNet-50 semi-supervised (temporal + PCA losses), synthetic
+384x384 video, 17 keypoints.  One *step* = one pass of the hot path over one batch of synthetic
+backbone features: per clip 16 labeled frames + 32 unlabeled frames ->
+  head (PixelShuffle + 2 deconvs + softmax) on all frames
+  -> labeled: fused Gaussian-target generation + heatmap MSE; soft-argmax decode
+  -> unlabeled: soft-argmax decode -> affine undo + model->frame remap -> temporal + PCA losses
+  -> backward of all of the above into the features and the head parameters (unless --fwd-only).
+`value` is frames/s with the features resident in HBM; `e2e` repeats the same step from pinned host
+buffers through the public API (H2D of the features and D2H of the loss scalars inside the timed region).
+
+`--impl reference` times the CPU oracle (the restated reference path, all host threads) on a bounded
+sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_PTS, IMG, FEAT_C, FEAT_HW, HM = 17, 384, 2048, 12, 96
+B_LABELED, T_UNLABELED = 16, 32  # config_default.yaml: train_batch_size 16, dali.base.train.sequence_length 32
+METRIC = "train frames/sec at 384x384x17kpt (hot path: head+targets+decode+losses)"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_problem(n_clips: int, seed: int, device, head_gain: float):
+    """Seeded synthetic inputs of config 2; features = randn * 0.5."""
+    from lightning_pose_b200.models.heads.heatmap import HeatmapHead
+
+    g = torch.Generator().manual_seed(seed)
+    n_frames = n_clips * (B_LABELED + T_UNLABELED)
+    head = HeatmapHead("resnet50", FEAT_C, K_PTS)
+    with torch.no_grad():
+        for layer in list(head.upsampling_layers)[1:]:
+            fan_in, fan_out = layer.weight.shape[1] * 9, layer.weight.shape[0] * 9
+            bound = head_gain * (6.0 / (fan_in + fan_out)) ** 0.5
+            layer.weight.copy_((torch.rand(layer.weight.shape, generator=g) * 2 - 1) * bound)
+    kp_lab = torch.rand(n_clips * B_LABELED, K_PTS, 2, generator=g) * IMG
+    kp_lab[torch.rand(n_clips * B_LABELED, K_PTS, generator=g) < 0.1] = float("nan")
+    vis = torch.randint(0, 3, (n_clips * B_LABELED, K_PTS), generator=g)
+    ang = np.deg2rad(float(torch.rand(1, generator=g)) * 20 - 10)
+    sc = 0.8 + 0.4 * float(torch.rand(1, generator=g))
+    tf = torch.tensor([[sc * np.cos(ang), -sc * np.sin(ang), 4.0], [sc * np.sin(ang), sc * np.cos(ang), -3.0]], dtype=torch.float32)
+    bbox = torch.tensor([[0.0, 0.0, 406.0, 396.0]]).repeat(n_clips * T_UNLABELED, 1)
+    # PCA parameters: rank-6 latent pose + noise, all 17 keypoints
+    lat = torch.randn(500, 6, generator=g) @ torch.randn(6, 2 * K_PTS, generator=g) * 20 + 200 + torch.randn(500, 2 * K_PTS, generator=g) * 2
+    mean = lat.mean(0)
+    _, _, vt = torch.linalg.svd(lat - mean, full_matrices=False)
+    pca = {"mean": mean, "kept": vt[:6].contiguous(), "eps": 5.0}
+    feats = torch.empty((n_frames, FEAT_C, FEAT_HW, FEAT_HW), dtype=torch.float32)
+    for i in range(0, n_frames, 64):  # bounded temp memory
+        feats[i : i + 64] = torch.randn((min(64, n_frames - i), FEAT_C, FEAT_HW, FEAT_HW), generator=g) * 0.5
+    return {"head": head, "feats": feats, "kp_lab": kp_lab, "vis": vis, "tf": tf, "bbox": bbox, "pca": pca, "n_clips": n_clips}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class HotPath:
+    LAUNCHES_FWD = 3 + 1 + 2 + 1 + 1  # head(2 deconvs + softmax), decode, target+mse (2), remap, unsup
+
+    def __init__(self, prob, device, fwd_only: bool):
+        from lightning_pose_b200 import ops
+
+        self.ops, self.dev, self.fwd_only = ops, device, fwd_only
+        self.n_clips = prob["n_clips"]
+        self.head = prob["head"].to(device)
+        self.kp_lab = prob["kp_lab"].to(device)
+        self.vis = prob["vis"].to(device)
+        self.tf = prob["tf"].to(device)
+        self.bbox = prob["bbox"].to(device)
+        self.sv = ops.PcaParams(np.arange(K_PTS, dtype=np.int32), K_PTS, 0, None, prob["pca"]["mean"], prob["pca"]["kept"], prob["pca"]["eps"], device)
+        self.teps = torch.full((K_PTS,), 20.0, device=device)
+        self.w_unsup = 1.0 / (2.0 * np.exp(5.0))
+
+    def step(self, feats: torch.Tensor):
+        ops, n = self.ops, self.n_clips
+        f = feats if self.fwd_only else feats.requires_grad_(True)
+        with torch.set_grad_enabled(not self.fwd_only):
+            hm = self.head(f)  # (n*48, 17, 96, 96)
+            hm_lab, hm_unl = hm[: n * B_LABELED], hm[n * B_LABELED :]
+            l_sup = ops.heatmap_mse_from_keypoints(self.kp_lab, hm_lab, IMG, IMG, visibility=self.vis) if self.fwd_only else \
+                ops.heatmap_loss(ops.generate_heatmaps(self.kp_lab, IMG, IMG, (HM, HM), visibility=self.vis), hm_lab, "mse")
+            kp, cf = ops.decode_softargmax(hm, 2, 1000.0)
+            kp_unl = ops.remap_keypoints(kp[n * B_LABELED :], self.tf, self.bbox, IMG, IMG)
+            per_clip = ops.unsup_losses(kp_unl.reshape(n, T_UNLABELED, 2 * K_PTS), cf[n * B_LABELED :].reshape(n, T_UNLABELED, K_PTS),
+                                        temporal_eps=self.teps, prob_threshold=0.05, pca_singleview=self.sv)
+            total = 0.5 * l_sup + self.w_unsup * per_clip[:, :2].sum()
+            if not self.fwd_only:
+                total.backward()
+        return torch.stack([total.detach(), l_sup.detach(), per_clip[:, 0].mean().detach(), per_clip[:, 1].mean().detach()])
+
+
+def time_steps(fn, steps, warmup, barrier=None):
+    for _ in range(warmup):
+        fn()
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def kernel_breakdown(hp: "HotPath", feats, reps=5):
+    """Per-stage device time (CUDA events on the launching stream) for the roofline line."""
+    ops, n = hp.ops, hp.n_clips
+    nf = feats.shape[0]
+    with torch.no_grad():
+        hm = hp.head(feats)
+        kp, cf = ops.decode_softargmax(hm, 2, 1000.0)
+        stages = {
+            "head_fwd(convT1+convT2+softmax)": (lambda: hp.head(feats), nf * (FEAT_C * FEAT_HW * FEAT_HW * 4 + K_PTS * HM * HM * 4)),
+            "decode_fwd": (lambda: ops.decode_softargmax(hm, 2, 1000.0), nf * (K_PTS * HM * HM * 4 + K_PTS * 12)),
+            "target+mse_fwd": (lambda: ops.heatmap_mse_from_keypoints(hp.kp_lab, hm[: n * B_LABELED], IMG, IMG, visibility=hp.vis),
+                               n * B_LABELED * (K_PTS * HM * HM * 4 + K_PTS * 12)),
+            "unsup_losses_fwd": (lambda: ops.unsup_losses(kp[n * B_LABELED :].reshape(n, T_UNLABELED, -1), cf[n * B_LABELED :].reshape(n, T_UNLABELED, -1),
+                                                          temporal_eps=hp.teps, prob_threshold=0.05, pca_singleview=hp.sv),
+                                 n * T_UNLABELED * K_PTS * 12),
+        }
+        out = {}
+        for name, (fn, nbytes) in stages.items():
+            ms = time_steps(fn, reps, 2) / reps
+            out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / ms / 1e6}
+    return out
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    import lightning_pose_b200  # noqa: F401  (fails loudly without the CUDA library)
+
+    prob = make_problem(args.clips, seed=1234 + rank, device=dev, head_gain=args.head_gain)
+    hp = HotPath(prob, dev, args.fwd_only)
+    feats_host = prob["feats"].pin_memory()
+    feats = feats_host.to(dev, non_blocking=True)
+    n_frames = feats.shape[0]
+    barrier = (lambda: dist.barrier()) if dist else None
+
+    with ClockSampler(local) as clk:
+        ms = time_steps(lambda: hp.step(feats), args.steps, args.warmup, barrier)
+    t = torch.tensor([ms], device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t)
+    value = world * n_frames * args.steps / (ms_total / 1e3)
+
+    # ---- e2e: pinned host features -> device inside the timed region, loss scalars read back -----
+    dbuf = torch.empty_like(feats)
+    losses_host = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        dbuf.copy_(feats_host, non_blocking=True)
+        out = hp.step(dbuf)
+        losses_host.copy_(out, non_blocking=True)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e = time_steps(e2e_step, e2e_steps, 1, barrier)
+    t = torch.tensor([ms_e2e], device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_frames * e2e_steps / (float(t) / 1e3)
+
+    if rank != 0:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    pk, pk_src = peaks()
+    br = kernel_breakdown(hp, feats)
+    dom = max(br, key=lambda k: br[k]["ms"])
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"BASELINE configs[1] hot path on ResNet-50 features (B,2048,12,12): {args.clips} clips/step/GPU x (16 labeled + 32 unlabeled) frames, "
+                        f"K=17, heatmaps 96x96, decode field 384x384; pass = {'forward' if args.fwd_only else 'forward+backward'}",
+            "frames_per_step_per_gpu": n_frames, "head_init": f"uniform xavier gain {args.head_gain} (peaked, trained-like logits)",
+            "l2_policy": f"inputs larger than L2 ({feats.numel() * 4 / 2**20:.0f} MiB of features per step)", "parallelism": f"dp{world}",
+        },
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": feats.numel() * 4, "d2h_bytes_per_step": 16},
+        "gpu_launches": HotPath.LAUNCHES_FWD * args.steps if args.fwd_only else None,
+        "clocks": clk.summary(),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": br[dom]["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": br[dom]["gbs"] / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src},
+        "stages": {k: {"ms": round(v["ms"], 4), "GBps": round(v["gbs"], 1), "frac_hbm": round(v["gbs"] / pk["hbm_gbs"], 4)} for k, v in br.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference(seed=1234, clips=1, reps=1)
+    print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle (restated reference path) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step(prob):
+    from oracle import lp_oracle as O
+
+    n = prob["n_clips"]
+    deconvs = list(prob["head"].upsampling_layers)[1:]
+    with torch.no_grad():
+        hm = O.head_forward(prob["feats"], [d.weight for d in deconvs], [d.bias for d in deconvs])
+        targ = O.gaussian_targets(prob["kp_lab"], IMG, IMG, (HM, HM), visibility=prob["vis"])
+        l_sup = O.heatmap_mse_loss(targ, hm[: n * B_LABELED])
+        kp, cf = O.decode_softargmax(hm, 2, 1000.0)
+        kp_unl = O.model_to_frame(O.undo_affine(kp[n * B_LABELED :], prob["tf"]), prob["bbox"], IMG, IMG)
+        tot = 0.5 * l_sup
+        for c in range(n):
+            sl = slice(c * T_UNLABELED, (c + 1) * T_UNLABELED)
+            tot = tot + (O.temporal_loss(kp_unl[sl], cf[n * B_LABELED :][sl], 20.0, 0.05)
+                         + O.pca_loss(O.pca_format_singleview(kp_unl[sl]), prob["pca"]["mean"], prob["pca"]["kept"], prob["pca"]["eps"])) / (2.0 * np.exp(5.0))
+    return tot
+
+
+def cpu_reference(seed, clips, reps):
+    torch.set_num_threads(os.cpu_count() or 1)
+    prob = make_problem(clips, seed=seed, device="cpu", head_gain=3.0)
+    cpu_step(prob)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cpu_step(prob)
+    dt = (time.perf_counter() - t0) / reps
+    frames = clips * (B_LABELED + T_UNLABELED)
+    model = "?"
+    try:
+        model = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        pass
+    return {"value": frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{clips} clip(s) = {frames} frames of the same workload, forward pass, torch CPU oracle (oracle/lp_oracle.py), {model}",
+            "seconds_per_sample": dt}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    clips = 1
+    prob = make_problem(clips, seed=1234, device="cpu", head_gain=args.head_gain)
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(prob)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(prob)
+    dt = time.perf_counter() - t0
+    frames = clips * (B_LABELED + T_UNLABELED)
+    value = frames * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1] hot path, bounded sample: {clips} clip/step x (16 labeled + 32 unlabeled) frames, forward pass, CPU"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{frames} frames/step, torch CPU restatement of the reference path (oracle/lp_oracle.py)"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=16, help="clips per step per GPU (48 frames each)")
+    ap.add_argument("--head-gain", type=float, default=3.0)
+    ap.add_argument("--fwd-only", action="store_true", default=True)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,175 @@
+/* lpb200 - C-ABI of the B200-native lightning-pose hot path (liblpb200.so, sm_100a only).
+ *
+ * Boundary contract
+ *   - plain C: device pointers + sizes + a CUDA stream handle (cudaStream_t passed as void*);
+ *     no torch / C++ types cross this boundary.
+ *   - all tensor pointers are DEVICE pointers owned by the caller, contiguous, row-major, in the
+ *     reference's own layouts (NCHW heatmaps / features, (N, 2K) keypoints [x0,y0,x1,y1,...]).
+ *   - every call only enqueues work on `stream` (no host sync, CUDA-graph capturable once the
+ *     per-shape tables exist: see lpb_decode_prepare); inputs are borrowed, nothing is retained.
+ *   - return value: 0 = ok, <0 = error (LPB_ERR_*); lpb_last_error() gives the message for the
+ *     calling thread.  There is NO CPU fallback anywhere behind this interface.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * paninski-lab/lightning-pose tree, commit f54c477).
+ */
+#ifndef LPB200_H_
+#define LPB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPB_OK 0
+#define LPB_ERR_INVALID (-1)
+#define LPB_ERR_CUDA (-2)
+#define LPB_ERR_UNSUPPORTED (-3)
+
+/* heatmap loss kinds for lpb_heatmap_loss_* (lightning_pose/losses/losses.py:293-423) */
+#define LPB_HM_MSE 0
+#define LPB_HM_KL 1
+#define LPB_HM_JS 2
+
+/* library / build info -------------------------------------------------------------------- */
+int lpb_version(void);                /* e.g. 100 = 0.1.0 */
+const char* lpb_last_error(void);     /* message of the last failing call on this thread */
+const char* lpb_build_arch(void);     /* "sm_100a" */
+
+/* ---- soft-argmax decode ---------------------------------------------------------------------
+ * replaces run_subpixelmaxima / HeatmapHead.run_subpixelmaxima
+ *   lightning_pose/models/heads/heatmap.py:103-144, :214-227
+ * (upsample x ds [:86-100] -> spatial_softmax2d(T) -> spatial_expectation2d ->
+ *  evaluate_heatmaps_at_location [lightning_pose/data/heatmaps.py:90-142] -> offset fix).
+ *
+ * heatmaps  [n_planes, h, w] fp32 (n_planes = batch * num_keypoints)
+ * xy        [n_planes, 2]  (x, y) in model-pixel units, offset {0.5,1.5,2.5} already removed
+ * conf      [n_planes]
+ * stats     [n_planes, 8] or NULL: {shift M, sum S, xhat, yhat (field coords), A0, A1, B0, B1
+ *           (evaluated coarse region)} - the residual lpb_decode_bwd needs.
+ * ds in {1,2,3}.  Evaluation is exact up to a dropped softmax mass < 1e-12.
+ */
+int lpb_decode_prepare(int h, int w, int ds);
+int lpb_decode_fwd(const float* heatmaps, int64_t n_planes, int h, int w, int ds, float temperature,
+                   float* xy, float* conf, float* stats, void* stream);
+/* d loss / d heatmaps given d loss / d xy (confidence carries no gradient: it only feeds `<`
+ * comparisons, lightning_pose/losses/losses.py:636). grad_heatmaps [n_planes,h,w] is overwritten. */
+int lpb_decode_bwd(const float* heatmaps, const float* stats, const float* grad_xy, int64_t n_planes,
+                   int h, int w, int ds, float temperature, float* grad_heatmaps, void* stream);
+
+/* one materialised upsampling stage: drop-in for `upsample`
+ *   lightning_pose/models/heads/heatmap.py:86-100 ; in [n_planes,h,w] -> out [n_planes,2h,2w] */
+int lpb_upsample2x(const float* in, int64_t n_planes, int h, int w, float* out, void* stream);
+
+/* ---- Gaussian target generation --------------------------------------------------------------
+ * replaces generate_heatmaps  lightning_pose/data/heatmaps.py:11-87
+ * keypoints [n_planes, 2] fp32 image pixels; visibility [n_planes] int32 {0,1,2} or NULL.
+ * out [n_planes, oh, ow] fp32.
+ */
+int lpb_generate_heatmaps(const float* keypoints, const int32_t* visibility, int64_t n_planes,
+                          float img_height, float img_width, int oh, int ow, float sigma, float* out,
+                          void* stream);
+
+/* gradient of lpb_generate_heatmaps wrt keypoints (keep_gradients=True, data/heatmaps.py:37-40);
+ * grad_out [n_planes,oh,ow] -> grad_keypoints [n_planes,2] */
+int lpb_generate_heatmaps_bwd(const float* keypoints, const int32_t* visibility, const float* grad_out,
+                              int64_t n_planes, float img_height, float img_width, int oh, int ow, float sigma,
+                              float* grad_keypoints, void* stream);
+
+/* replaces evaluate_heatmaps_at_location  lightning_pose/data/heatmaps.py:90-142
+ * heatmaps [n_planes,h,w], locs [n_planes,2] (x,y) -> out [n_planes]; radius = floor(sigma*num_stds) */
+int lpb_evaluate_heatmaps_at_location(const float* heatmaps, const float* locs, int64_t n_planes, int h,
+                                      int w, int radius, float* out, void* stream);
+
+/* ---- heatmap head ----------------------------------------------------------------------------
+ * replaces HeatmapHead.forward  lightning_pose/models/heads/heatmap.py:203-212
+ * (PixelShuffle(2) -> ConvTranspose2d(k3,s2,p1,op1) x n_layers [:20-71] -> spatial_softmax2d(T=1)).
+ *
+ * features  [B, C, H, W]   fp32 (lpb_head_fwd_f32) or bf16 (lpb_head_fwd_bf16), NCHW contiguous
+ * w1 [C/4, c1, 3, 3], b1 [c1]   first deconv (ConvTranspose2d layout, fp32 or bf16 to match)
+ * w2 [c1, c2, 3, 3],  b2 [c2]   second deconv, or NULL/NULL for a one-layer head (then c2 = 0)
+ * out [B, K, Ho, Wo] fp32 with K = c2 ? c2 : c1, Ho = 4H*(n_layers==2?2:1) ...
+ * workspace: lpb_head_workspace_bytes() bytes of scratch (device), may be NULL if that is 0.
+ */
+int lpb_head_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes);
+int lpb_head_fwd_f32(const float* features, int B, int C, int H, int W, const float* w1, const float* b1,
+                     int c1, const float* w2, const float* b2, int c2, int final_softmax, float* out,
+                     void* workspace, void* stream);
+
+/* ---- coordinate remap -------------------------------------------------------------------------
+ * replaces undo_affine_transform_batch + model_to_frame_batch
+ *   lightning_pose/data/utils.py:142-234, lightning_pose/data/bboxes.py:74-105,222-288
+ * keypoints_in [n, 2K]; transforms: NULL (identity) | [2,3] (per_frame=0) | [n,2,3] (per_frame=1)
+ * | [V,2,3] with num_views=V>1 (per_frame=0, view-sliced); bbox [n_bbox, 4V] (x,y,h,w per view),
+ * n_bbox == n or n + 4 (context batches use rows 2..n_bbox-3).  keypoints_out [n, 2K] (may alias in).
+ */
+int lpb_remap_keypoints(const float* keypoints_in, int64_t n, int K, const float* transforms,
+                        int per_frame, int num_views, const float* bbox, int64_t n_bbox,
+                        float model_height, float model_width, float* keypoints_out, void* stream);
+
+/* ---- heatmap losses ---------------------------------------------------------------------------
+ * replaces HeatmapMSELoss / HeatmapKLLoss / HeatmapJSLoss (remove_nans + compute_loss + mean)
+ *   lightning_pose/losses/losses.py:229-289, :314-335, :360-378, :404-423
+ * targets/preds [n_planes, hw]; planes whose target is all-zero are dropped on device (no
+ * boolean gather, no host sync).  out[0] = scalar loss, out[1] = number of kept planes.
+ * workspace: n_planes * 2 floats {plane sum, kept flag}; the backward pass reads it again.
+ */
+int lpb_heatmap_loss_fwd(const float* targets, const float* preds, int64_t n_planes, int h, int w, int kind,
+                         float* out, float* workspace, void* stream);
+/* d loss/d preds (targets get no gradient); grad_out is the upstream scalar gradient (device ptr). */
+int lpb_heatmap_loss_bwd(const float* targets, const float* preds, int64_t n_planes, int h, int w, int kind,
+                         const float* workspace, const float* fwd_out, const float* grad_out, float* grad_preds,
+                         void* stream);
+/* fused target generation + MSE: targets never touch HBM. */
+int lpb_heatmap_mse_from_keypoints_fwd(const float* keypoints, const int32_t* visibility, const float* preds,
+                                       int64_t n_planes, float img_height, float img_width, int oh, int ow,
+                                       float sigma, float* out, float* workspace, void* stream);
+
+/* replaces TemporalHeatmapLoss.__call__  lightning_pose/losses/losses.py:793-854
+ * heatmaps [T,K,h,w], confidences [T,K], eps [K]; kind LPB_HM_MSE | LPB_HM_KL; out[0] = scalar loss;
+ * workspace (T-1)*K floats. */
+int lpb_temporal_heatmap_loss_fwd(const float* heatmaps, const float* confidences, int64_t T, int K, int h, int w,
+                                  int kind, const float* eps, float prob_threshold, float* out, float* workspace,
+                                  void* stream);
+
+/* ---- unsupervised losses on the (T, K, 2) keypoint tensor -------------------------------------
+ * replaces TemporalLoss.__call__ and PCALoss.__call__ (+ KeypointPCA._format_data / reproject /
+ * compute_reprojection_error)
+ *   lightning_pose/losses/losses.py:548-573, :608-703; lightning_pose/utils/pca.py:97-190,266-309
+ *
+ * One launch evaluates every clip: keypoints [n_clips, T, 2K], confidences [n_clips, T, K] or NULL.
+ * temporal: eps_k [K] (per-keypoint epsilon), prob_threshold.
+ * pca (optional, may be NULL-disabled by n_obs_dims = 0):
+ *   columns [D/2 ... ] see lpb_pca_desc.
+ * out [n_clips, LPB_UNSUP_NOUT] = {temporal, pca_singleview, pca_multiview, 0}
+ */
+#define LPB_UNSUP_NOUT 4
+typedef struct lpb_pca_desc {
+  /* singleview: kp_index[i] for i < n_sel = selected keypoint ids; D = 2*n_sel.
+   * multiview:  kp_index[v*n_sel + j] = keypoint id of body part j in view v; D = 2*n_views. */
+  const int32_t* kp_index; /* device */
+  int32_t n_sel;
+  int32_t n_views;     /* 0 = singleview */
+  int32_t centering;   /* singleview only: 0 none, 1 mean, 2 median (quantile 0.5) */
+  int32_t n_components;
+  const float* mean;   /* [D] device */
+  const float* kept;   /* [n_components, D] device, rows = kept eigenvectors */
+  float epsilon;
+} lpb_pca_desc;
+
+int lpb_unsup_losses_fwd(const float* keypoints, const float* confidences, int64_t n_clips, int T, int K,
+                         const float* temporal_eps, float prob_threshold, int temporal_enabled,
+                         const lpb_pca_desc* pca_singleview, const lpb_pca_desc* pca_multiview, float* out,
+                         void* stream);
+/* gradient wrt keypoints; grad_out [n_clips, LPB_UNSUP_NOUT] upstream per-loss gradients. */
+int lpb_unsup_losses_bwd(const float* keypoints, const float* confidences, int64_t n_clips, int T, int K,
+                         const float* temporal_eps, float prob_threshold, int temporal_enabled,
+                         const lpb_pca_desc* pca_singleview, const lpb_pca_desc* pca_multiview,
+                         const float* grad_out, float* grad_keypoints, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPB200_H_ */

@@ -1,0 +1,671 @@
+// Soft-argmax decode: heatmaps (n_planes, h, w) -> (x, y, confidence) per plane.
+//
+// Reference semantics (lightning_pose/models/heads/heatmap.py:103-144, data/heatmaps.py:90-142):
+//   field = upsample^ds(h)  (each stage: 2x bicubic + zero-padded 5x5 binomial blur, :86-100)
+//   p = softmax(T * field) over the whole (h*2^ds, w*2^ds) field
+//   (x, y) = sum p * (col, row);  conf = sum of the 5x5 window of p around (trunc y, trunc x)
+//   (x, y) -= {0.5, 1.5, 2.5}
+//
+// B200 design (DESIGN.md "K2"): one CTA per plane; the plane is staged ONCE into shared memory by
+// the TMA engine (cp.async.bulk, one copy per row into a zero-padded tile); the 4x-upsampled field
+// is never materialised: field = U_H h U_W^T is evaluated separably in registers (horizontal pass
+// from smem, vertical pass on a sliding register window with the phase-periodic interior weights
+// in the constant bank) and only inside the coarse bounding box that can hold softmax mass
+// > exp(-40) relative to the peak (rigorous bound |field| <= lip * max|h| over the tap footprint).
+// Flat (fresh-init) planes fall through to the same code with the box = whole plane.
+#include <cstdint>
+
+#include "../../include/lpb200.h"
+#include "lpb_common.cuh"
+#include "upsample_tables.cuh"
+
+namespace lpb {
+
+constexpr int DEC_THREADS = 256;
+constexpr int DEC_WARPS = DEC_THREADS / 32;
+constexpr float DEC_CUT = 40.0f;  // dropped pixels have weight < exp(-40) = 4e-18 of the peak pixel
+constexpr int DEC_CONF_R = 2;     // floor(1.25 * 2), lightning_pose/data/heatmaps.py:111
+
+template <int DS>
+struct DecodeParams {
+  static constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  const float* heat;
+  const float* tabH;  // [h*F][W] vertical-axis window weights
+  const float* tabW;  // [w*F][W] horizontal-axis window weights
+  float* xy;
+  float* conf;
+  float* stats;
+  int h, w, pitch, padl, bulk;
+  float T, lip, offset;
+  float phase[F][W];  // interior rows (constant bank operands)
+};
+
+__host__ __device__ inline int dec_padl(int R) { return (R + 3) & ~3; }
+__host__ __device__ inline int dec_pitch(int w, int R) { return (dec_padl(R) + w + R + 3) & ~3; }
+
+template <int W>
+__device__ __forceinline__ float dot_w(const float* __restrict__ p, const float (&wc)[W]) {
+  float r = 0.f;
+#pragma unroll
+  for (int t = 0; t < W; ++t) r = fmaf(wc[t], p[t], r);
+  return r;
+}
+
+// exact field value at fine pixel (i, j) (W*W taps); used for the lower bound and the confidence
+template <int DS>
+__device__ float eval_point(const float* tile, int pitch, int padl, const float* __restrict__ tabH,
+                            const float* __restrict__ tabW, int i, int j) {
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  const float* base = tile + (i / F) * pitch + padl + (j / F - R);  // row index (a - R) + R = a
+  float acc = 0.f;
+#pragma unroll 1
+  for (int t = 0; t < W; ++t) {
+    const float* row = base + t * pitch;
+    float r = 0.f;
+#pragma unroll
+    for (int u = 0; u < W; ++u) r = fmaf(__ldg(tabW + j * W + u), row[u], r);
+    acc = fmaf(__ldg(tabH + i * W + t), r, acc);
+  }
+  return acc;
+}
+
+template <int DS>
+__global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_constant__ DecodeParams<DS> P) {
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int h = P.h, w = P.w, pitch = P.pitch, padl = P.padl;
+  float* tile = reinterpret_cast<float*>(smem_raw);  // (h + 2R) x pitch; logical (a,b) at [(a+R)*pitch + padl + b]
+  float* red = tile + (h + 2 * R) * pitch;           // 64 floats of reduction scratch
+  int* redi = reinterpret_cast<int*>(red + 64);      // 48 ints
+  uint64_t* bar = reinterpret_cast<uint64_t*>(redi + 48);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t plane = blockIdx.x;
+  const float* __restrict__ src = P.heat + plane * (size_t)h * w;
+
+  // ---- stage the plane: TMA bulk row copies into the zero-padded tile -------------------------
+  if (P.bulk) {
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)(h * w * 4));
+      __syncwarp();
+      for (int a = lane; a < h; a += 32)
+        bulk_g2s(tile + (a + R) * pitch + padl, src + (size_t)a * w, (uint32_t)(w * 4), bar);
+    }
+  }
+  for (int r = warp; r < h + 2 * R; r += DEC_WARPS) {
+    float* row = tile + r * pitch;
+    if (r < R || r >= h + R) {
+      for (int b = lane; b < pitch; b += 32) row[b] = 0.f;
+    } else {
+      for (int b = lane; b < padl; b += 32) row[b] = 0.f;
+      for (int b = padl + w + lane; b < pitch; b += 32) row[b] = 0.f;
+      if (!P.bulk) {
+        const float* g = src + (size_t)(r - R) * w;
+        for (int b = lane; b < w; b += 32) row[padl + b] = __ldg(g + b);
+      }
+    }
+  }
+  if (P.bulk) mbar_wait(bar, 0);
+  __syncthreads();
+
+  // ---- scan 1: coarse arg max of |h| ------------------------------------------------------------
+  float best = -1.f;
+  int besta = 0, bestb = 0;
+  for (int a = warp; a < h; a += DEC_WARPS) {
+    const float* row = tile + (a + R) * pitch + padl;
+    for (int b = lane; b < w; b += 32) {
+      const float v = fabsf(row[b]);
+      if (v > best) {
+        best = v;
+        besta = a;
+        bestb = b;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, besta, o);
+    const int obb = __shfl_xor_sync(0xffffffffu, bestb, o);
+    if (ob > best) {
+      best = ob;
+      besta = oa;
+      bestb = obb;
+    }
+  }
+  if (lane == 0) {
+    red[warp] = best;
+    redi[2 * warp] = besta;
+    redi[2 * warp + 1] = bestb;
+  }
+  __syncthreads();
+  {
+    best = red[0];
+    besta = redi[0];
+    bestb = redi[1];
+#pragma unroll
+    for (int k = 1; k < DEC_WARPS; ++k)
+      if (red[k] > best) {
+        best = red[k];
+        besta = redi[2 * k];
+        bestb = redi[2 * k + 1];
+      }
+  }
+
+  // ---- lower bound on the field maximum: exact values in the F x F block of the coarse arg max --
+  float lb = -3.0e38f;
+  if (tid < F * F) lb = eval_point<DS>(tile, pitch, padl, P.tabH, P.tabW, besta * F + tid / F, bestb * F + tid % F);
+  lb = warp_max(lb);
+  if (lane == 0) red[8 + warp] = lb;
+  __syncthreads();
+  float mlb = red[8];
+#pragma unroll
+  for (int k = 1; k < DEC_WARPS; ++k) mlb = fmaxf(mlb, red[8 + k]);
+
+  // ---- scan 2: bounding box of coarse pixels that can reach (mlb - CUT/T) ------------------------
+  const float theta = (P.T > 0.f) ? (mlb - DEC_CUT / P.T) / P.lip : -1.f;
+  int amin = h, amax = -1, bmin = w, bmax = -1;
+  for (int a = warp; a < h; a += DEC_WARPS) {
+    const float* row = tile + (a + R) * pitch + padl;
+    bool any = false;
+    for (int b = lane; b < w; b += 32) {
+      if (fabsf(row[b]) >= theta) {
+        any = true;
+        bmin = min(bmin, b);
+        bmax = max(bmax, b);
+      }
+    }
+    if (any) {
+      amin = min(amin, a);
+      amax = max(amax, a);
+    }
+  }
+  amin = warp_min_i(amin);
+  amax = warp_max_i(amax);
+  bmin = warp_min_i(bmin);
+  bmax = warp_max_i(bmax);
+  if (lane == 0) {
+    redi[16 + 4 * warp + 0] = amin;
+    redi[16 + 4 * warp + 1] = amax;
+    redi[16 + 4 * warp + 2] = bmin;
+    redi[16 + 4 * warp + 3] = bmax;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < DEC_WARPS; ++k) {
+    amin = min(amin, redi[16 + 4 * k + 0]);
+    amax = max(amax, redi[16 + 4 * k + 1]);
+    bmin = min(bmin, redi[16 + 4 * k + 2]);
+    bmax = max(bmax, redi[16 + 4 * k + 3]);
+  }
+  if (amax < 0) {  // only reachable with NaN input: evaluate everything
+    amin = 0;
+    amax = h - 1;
+    bmin = 0;
+    bmax = w - 1;
+  }
+  const int A0 = max(amin - R, 0), A1 = min(amax + R, h - 1);
+  const int B0 = max(bmin - R, 0), B1 = min(bmax + R, w - 1);
+
+  // ---- work items: 32-fine-column strips x row groups, round-robin over the 8 warps --------------
+  const int J0 = B0 * F, J1 = (B1 + 1) * F;
+  const int nstrips = (J1 - J0 + 31) >> 5;
+  const int nrows = A1 - A0 + 1;
+  int G = 1, seg = nrows;
+  {
+    int bestcost = 0x7fffffff;
+    for (int g = 1; g <= 8; ++g) {
+      const int sg = (nrows + g - 1) / g;
+      const int cost = ((nstrips * g + DEC_WARPS - 1) / DEC_WARPS) * (sg + 2 * R);
+      if (cost < bestcost) {
+        bestcost = cost;
+        G = g;
+        seg = sg;
+      }
+    }
+  }
+  const int nitems = nstrips * G;
+  const float c = P.T * 1.4426950408889634f;
+  float m = mlb, s = 0.f, sx = 0.f, sy = 0.f;
+
+  for (int item = warp; item < nitems; item += DEC_WARPS) {
+    const int sidx = item % nstrips, g = item / nstrips;
+    const int r0 = A0 + g * seg, r1 = min(r0 + seg, A1 + 1);
+    if (r0 >= r1) continue;
+    const int jf = J0 + sidx * 32 + lane;
+    const bool ok = jf < J1;
+    const int jc = ok ? jf : (J1 - 1);
+    float wc[W];
+#pragma unroll
+    for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
+    const float* colbase = tile + padl + (jc / F - R);  // add (a + R) * pitch for coarse row a
+    float tmp[W];
+#pragma unroll
+    for (int t = 0; t < W; ++t) tmp[t] = dot_w<W>(colbase + (r0 + t) * pitch, wc);  // rows r0-R .. r0+R
+    const float xf = (float)jf;
+    for (int a = r0; a < r1; ++a) {
+      float v[F];
+      if (a >= R && a <= h - 1 - R) {
+#pragma unroll
+        for (int p = 0; p < F; ++p) {
+          float r = 0.f;
+#pragma unroll
+          for (int t = 0; t < W; ++t) r = fmaf(P.phase[p][t], tmp[t], r);
+          v[p] = r;
+        }
+      } else {
+        const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
+#pragma unroll
+        for (int p = 0; p < F; ++p) {
+          float r = 0.f;
+#pragma unroll
+          for (int t = 0; t < W; ++t) r = fmaf(__ldg(tr + p * W + t), tmp[t], r);
+          v[p] = r;
+        }
+      }
+      if (ok) {
+        float vm = v[0];
+#pragma unroll
+        for (int p = 1; p < F; ++p) vm = fmaxf(vm, v[p]);
+        if (vm > m) {
+          const float sc = fast_exp2((m - vm) * c);
+          s *= sc;
+          sx *= sc;
+          sy *= sc;
+          m = vm;
+        }
+#pragma unroll
+        for (int p = 0; p < F; ++p) {
+          const float wgt = fast_exp2((v[p] - m) * c);
+          s += wgt;
+          sx = fmaf(wgt, xf, sx);
+          sy = fmaf(wgt, (float)(a * F + p), sy);
+        }
+      }
+      if (a + 1 < r1) {
+#pragma unroll
+        for (int t = 0; t < W - 1; ++t) tmp[t] = tmp[t + 1];
+        tmp[W - 1] = dot_w<W>(colbase + (a + 1 + 2 * R) * pitch, wc);  // coarse row a+1+R
+      }
+    }
+  }
+
+  // ---- merge the per-lane online-softmax states ----------------------------------------------------
+  {
+    const float M = warp_max(m);
+    const float sc = fast_exp2((m - M) * c);
+    s = warp_sum(s * sc);
+    sx = warp_sum(sx * sc);
+    sy = warp_sum(sy * sc);
+    if (lane == 0) {
+      red[16 + 4 * warp + 0] = M;
+      red[16 + 4 * warp + 1] = s;
+      red[16 + 4 * warp + 2] = sx;
+      red[16 + 4 * warp + 3] = sy;
+    }
+  }
+  __syncthreads();
+  float M = red[16];
+#pragma unroll
+  for (int k = 1; k < DEC_WARPS; ++k) M = fmaxf(M, red[16 + 4 * k]);
+  float S = 0.f, SX = 0.f, SY = 0.f;
+#pragma unroll
+  for (int k = 0; k < DEC_WARPS; ++k) {
+    const float sc = fast_exp2((red[16 + 4 * k] - M) * c);
+    S = fmaf(red[16 + 4 * k + 1], sc, S);
+    SX = fmaf(red[16 + 4 * k + 2], sc, SX);
+    SY = fmaf(red[16 + 4 * k + 3], sc, SY);
+  }
+  const float xhat = SX / S, yhat = SY / S;
+
+  // ---- confidence: softmax mass of the (2r+1)^2 window around (trunc y, trunc x) -----------------
+  constexpr int CW = 2 * DEC_CONF_R + 1;
+  float cw = 0.f;
+  if (tid < CW * CW) {
+    const int i = (int)yhat + tid / CW - DEC_CONF_R;
+    const int j = (int)xhat + tid % CW - DEC_CONF_R;
+    if (i >= 0 && i < h * F && j >= 0 && j < w * F) {
+      const float v = eval_point<DS>(tile, pitch, padl, P.tabH, P.tabW, i, j);
+      cw = fast_exp2((v - M) * c) / S;
+    }
+  }
+  cw = warp_sum(cw);  // CW*CW = 25 <= 32: all in warp 0
+  if (tid == 0) {
+    P.xy[2 * plane + 0] = xhat - P.offset;
+    P.xy[2 * plane + 1] = yhat - P.offset;
+    P.conf[plane] = cw;
+    if (P.stats) {
+      float* st = P.stats + 8 * plane;
+      st[0] = M;
+      st[1] = S;
+      st[2] = xhat;
+      st[3] = yhat;
+      st[4] = (float)A0;
+      st[5] = (float)A1;
+      st[6] = (float)B0;
+      st[7] = (float)B1;
+    }
+  }
+}
+
+// d loss / d h = U_H^T G U_W with G[i,j] = T * p[i,j] * ((j - xhat) gx + (i - yhat) gy), p the
+// temperature softmax.  G is non-negligible only inside the box saved by the forward pass; each warp
+// recomputes the field on its strip exactly as the forward does and scatters G through the same taps
+// into a zero-initialised smem gradient plane, which is then written out with coalesced stores.
+template <int DS>
+struct DecodeBwdParams {
+  static constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  const float* heat;
+  const float* stats;
+  const float* gxy;
+  const float* tabH;
+  const float* tabW;
+  float* gheat;
+  int h, w, pitch, padl, bulk;
+  float T;
+  float phase[F][W];
+};
+
+template <int DS>
+__global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_constant__ DecodeBwdParams<DS> P) {
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int h = P.h, w = P.w, pitch = P.pitch, padl = P.padl;
+  const int tile_floats = (h + 2 * R) * pitch;
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  float* gtile = tile + tile_floats;  // same padded geometry, accumulates U_H^T G U_W
+  uint64_t* bar = reinterpret_cast<uint64_t*>(gtile + tile_floats);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t plane = blockIdx.x;
+  const float* __restrict__ src = P.heat + plane * (size_t)h * w;
+
+  if (P.bulk) {
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)(h * w * 4));
+      __syncwarp();
+      for (int a = lane; a < h; a += 32)
+        bulk_g2s(tile + (a + R) * pitch + padl, src + (size_t)a * w, (uint32_t)(w * 4), bar);
+    }
+  }
+  for (int i = tid; i < tile_floats; i += DEC_THREADS) gtile[i] = 0.f;
+  for (int r = warp; r < h + 2 * R; r += DEC_WARPS) {
+    float* row = tile + r * pitch;
+    if (r < R || r >= h + R) {
+      for (int b = lane; b < pitch; b += 32) row[b] = 0.f;
+    } else {
+      for (int b = lane; b < padl; b += 32) row[b] = 0.f;
+      for (int b = padl + w + lane; b < pitch; b += 32) row[b] = 0.f;
+      if (!P.bulk) {
+        const float* g = src + (size_t)(r - R) * w;
+        for (int b = lane; b < w; b += 32) row[padl + b] = __ldg(g + b);
+      }
+    }
+  }
+  if (P.bulk) mbar_wait(bar, 0);
+  __syncthreads();
+
+  const float* st = P.stats + 8 * plane;
+  const float M = st[0], S = st[1], xhat = st[2], yhat = st[3];
+  const int A0 = (int)st[4], A1 = (int)st[5], B0 = (int)st[6], B1 = (int)st[7];
+  const float gx = P.gxy[2 * plane], gy = P.gxy[2 * plane + 1];
+  const float c = P.T * 1.4426950408889634f;
+  const float kscale = P.T / S;
+
+  if (gx != 0.f || gy != 0.f) {
+    const int J0 = B0 * F, J1 = (B1 + 1) * F;
+    const int nstrips = (J1 - J0 + 31) >> 5;
+    const int nrows = A1 - A0 + 1;
+    int G = 1, seg = nrows;
+    {
+      int bestcost = 0x7fffffff;
+      for (int g = 1; g <= 8; ++g) {
+        const int sg = (nrows + g - 1) / g;
+        const int cost = ((nstrips * g + DEC_WARPS - 1) / DEC_WARPS) * (sg + 2 * R);
+        if (cost < bestcost) {
+          bestcost = cost;
+          G = g;
+          seg = sg;
+        }
+      }
+    }
+    const int nitems = nstrips * G;
+    for (int item = warp; item < nitems; item += DEC_WARPS) {
+      const int sidx = item % nstrips, g = item / nstrips;
+      const int r0 = A0 + g * seg, r1 = min(r0 + seg, A1 + 1);
+      if (r0 >= r1) continue;
+      const int jf = J0 + sidx * 32 + lane;
+      const bool ok = jf < J1;
+      const int jc = ok ? jf : (J1 - 1);
+      float wc[W];
+#pragma unroll
+      for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
+      const int cb = padl + (jc / F - R);
+      const float* colbase = tile + cb;
+      float tmp[W];   // horizontal pass of h, rows a-R .. a+R
+      float gacc[W];  // vertical-transpose accumulators: sum_i wr[i][t] * G[i][j] for coarse row a-R+t
+#pragma unroll
+      for (int t = 0; t < W; ++t) {
+        tmp[t] = dot_w<W>(colbase + (r0 + t) * pitch, wc);
+        gacc[t] = 0.f;
+      }
+      const float dx = (float)jf - xhat;
+      for (int a = r0; a < r1; ++a) {
+        const bool interior = (a >= R && a <= h - 1 - R);
+        const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
+#pragma unroll
+        for (int p = 0; p < F; ++p) {
+          float wr[W];
+#pragma unroll
+          for (int t = 0; t < W; ++t) wr[t] = interior ? P.phase[p][t] : __ldg(tr + p * W + t);
+          float v = 0.f;
+#pragma unroll
+          for (int t = 0; t < W; ++t) v = fmaf(wr[t], tmp[t], v);
+          const float pr = fast_exp2((v - M) * c);
+          const float gval = ok ? kscale * pr * fmaf(dx, gx, ((float)(a * F + p) - yhat) * gy) : 0.f;
+#pragma unroll
+          for (int t = 0; t < W; ++t) gacc[t] = fmaf(wr[t], gval, gacc[t]);
+        }
+        // coarse row a-R is complete for this lane's column: scatter through the horizontal taps
+        {
+          float* grow = gtile + a * pitch + cb;  // padded row (a-R)+R; lanes of one coarse column pre-reduce
+#pragma unroll
+          for (int u = 0; u < W; ++u) {
+            float val = gacc[0] * wc[u];
+#pragma unroll
+            for (int o = 1; o < F; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            if ((lane & (F - 1)) == 0 && val != 0.f) atomicAdd(grow + u, val);
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < W - 1; ++t) {
+          gacc[t] = gacc[t + 1];
+          tmp[t] = tmp[t + 1];
+        }
+        gacc[W - 1] = 0.f;
+        tmp[W - 1] = (a + 1 < r1) ? dot_w<W>(colbase + (a + 1 + 2 * R) * pitch, wc) : 0.f;
+      }
+      // flush the remaining W-1 partial rows (coarse rows r1-R .. r1+R-1)
+#pragma unroll
+      for (int t = 0; t < W - 1; ++t) {
+        float* grow = gtile + (r1 + t) * pitch + cb;
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+          float val = gacc[t] * wc[u];
+#pragma unroll
+          for (int o = 1; o < F; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+          if ((lane & (F - 1)) == 0 && val != 0.f) atomicAdd(grow + u, val);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* __restrict__ dst = P.gheat + plane * (size_t)h * w;
+  for (int a = warp; a < h; a += DEC_WARPS) {
+    const float* row = gtile + (a + R) * pitch + padl;
+    for (int b = lane; b < w; b += 32) dst[(size_t)a * w + b] = row[b];
+  }
+}
+
+
+// One materialised upsampling stage (drop-in for `upsample`, lightning_pose/models/heads/heatmap.py:86-100).
+// Not on the fused path (the decode never materialises the field); kept for API completeness.
+__global__ void __launch_bounds__(DEC_THREADS) upsample2x_kernel(const float* __restrict__ in, int h, int w, int pitch,
+                                                                 int padl, const float* __restrict__ tabH,
+                                                                 const float* __restrict__ tabW, float* __restrict__ out) {
+  constexpr int R = 3;
+  extern __shared__ __align__(16) float ups_tile[];
+  const size_t plane = blockIdx.x;
+  const float* __restrict__ src = in + plane * (size_t)h * w;
+  for (int i = threadIdx.x; i < (h + 2 * R) * pitch; i += DEC_THREADS) {
+    const int r = i / pitch - R, c = i % pitch - padl;
+    ups_tile[i] = (r >= 0 && r < h && c >= 0 && c < w) ? __ldg(src + (size_t)r * w + c) : 0.f;
+  }
+  __syncthreads();
+  float* __restrict__ dst = out + plane * (size_t)(4 * h * w);
+  for (int o = threadIdx.x; o < 4 * h * w; o += DEC_THREADS) {
+    const int i = o / (2 * w), j = o - i * (2 * w);
+    dst[o] = eval_point<1>(ups_tile, pitch, padl, tabH, tabW, i, j);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int DS>
+static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, float T, float* xy, float* conf,
+                             float* stats, cudaStream_t stream) {
+  using G = UpsampleGeom<DS>;
+  const DeviceTable* th = get_device_table(h, DS);
+  const DeviceTable* tw = get_device_table(w, DS);
+  if (!th || !tw) return LPB_ERR_INVALID;
+  DecodeParams<DS> P;
+  P.heat = heat;
+  P.tabH = th->win;
+  P.tabW = tw->win;
+  P.xy = xy;
+  P.conf = conf;
+  P.stats = stats;
+  P.h = h;
+  P.w = w;
+  P.padl = dec_padl(G::R);
+  P.pitch = dec_pitch(w, G::R);
+  P.bulk = ((w % 4) == 0 && (reinterpret_cast<uintptr_t>(heat) % 16) == 0) ? 1 : 0;
+  P.T = T;
+  P.lip = th->host.lip * tw->host.lip;
+  P.offset = (DS == 1) ? 0.5f : (DS == 2 ? 1.5f : 2.5f);  // lightning_pose/models/heads/heatmap.py:131-136
+  for (int p = 0; p < G::F; ++p)
+    for (int t = 0; t < G::W; ++t) P.phase[p][t] = th->host.phase[(size_t)p * G::W + t];
+  const size_t smem = ((size_t)(h + 2 * G::R) * P.pitch + 64 + 48) * sizeof(float) + 16;
+  int dev = 0, max_smem = 0;
+  LPB_CUDA(cudaGetDevice(&dev));
+  LPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if ((int64_t)smem > max_smem) {
+    set_error("decode: plane %dx%d needs %zu B shared memory (> %d)", h, w, smem, max_smem);
+    return LPB_ERR_UNSUPPORTED;
+  }
+  LPB_CUDA(cudaFuncSetAttribute(decode_fwd_kernel<DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  decode_fwd_kernel<DS><<<(unsigned)n_planes, DEC_THREADS, smem, stream>>>(P);
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}
+
+template <int DS>
+static int launch_decode_bwd(const float* heat, const float* stats, const float* gxy, int64_t n_planes, int h, int w,
+                             float T, float* gheat, cudaStream_t stream) {
+  using G = UpsampleGeom<DS>;
+  const DeviceTable* th = get_device_table(h, DS);
+  const DeviceTable* tw = get_device_table(w, DS);
+  if (!th || !tw) return LPB_ERR_INVALID;
+  DecodeBwdParams<DS> P;
+  P.heat = heat;
+  P.stats = stats;
+  P.gxy = gxy;
+  P.tabH = th->win;
+  P.tabW = tw->win;
+  P.gheat = gheat;
+  P.h = h;
+  P.w = w;
+  P.padl = dec_padl(G::R);
+  P.pitch = dec_pitch(w, G::R);
+  P.bulk = ((w % 4) == 0 && (reinterpret_cast<uintptr_t>(heat) % 16) == 0) ? 1 : 0;
+  P.T = T;
+  for (int p = 0; p < G::F; ++p)
+    for (int t = 0; t < G::W; ++t) P.phase[p][t] = th->host.phase[(size_t)p * G::W + t];
+  const size_t smem = ((size_t)2 * (h + 2 * G::R) * P.pitch) * sizeof(float) + 16;
+  int dev = 0, max_smem = 0;
+  LPB_CUDA(cudaGetDevice(&dev));
+  LPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if ((int64_t)smem > max_smem) {
+    set_error("decode_bwd: plane %dx%d needs %zu B shared memory (> %d)", h, w, smem, max_smem);
+    return LPB_ERR_UNSUPPORTED;
+  }
+  LPB_CUDA(cudaFuncSetAttribute(decode_bwd_kernel<DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  decode_bwd_kernel<DS><<<(unsigned)n_planes, DEC_THREADS, smem, stream>>>(P);
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}
+
+}  // namespace lpb
+
+extern "C" int lpb_decode_prepare(int h, int w, int ds) {
+  using namespace lpb;
+  LPB_REQUIRE(h >= 1 && w >= 1 && ds >= 1 && ds <= 3, "decode_prepare: bad shape h=%d w=%d ds=%d", h, w, ds);
+  if (!get_device_table(h, ds) || !get_device_table(w, ds)) return LPB_ERR_INVALID;
+  return LPB_OK;
+}
+
+extern "C" int lpb_decode_fwd(const float* heatmaps, int64_t n_planes, int h, int w, int ds, float temperature,
+                              float* xy, float* conf, float* stats, void* stream) {
+  using namespace lpb;
+  LPB_REQUIRE(heatmaps && xy && conf, "decode_fwd: null pointer");
+  LPB_REQUIRE(h >= 1 && w >= 1 && ds >= 1 && ds <= 3, "decode_fwd: bad shape h=%d w=%d ds=%d", h, w, ds);
+  LPB_REQUIRE(n_planes >= 0 && n_planes < (1ll << 31), "decode_fwd: bad n_planes");
+  if (n_planes == 0) return LPB_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (ds) {
+    case 1: return launch_decode_fwd<1>(heatmaps, n_planes, h, w, temperature, xy, conf, stats, s);
+    case 2: return launch_decode_fwd<2>(heatmaps, n_planes, h, w, temperature, xy, conf, stats, s);
+    default: return launch_decode_fwd<3>(heatmaps, n_planes, h, w, temperature, xy, conf, stats, s);
+  }
+}
+
+extern "C" int lpb_decode_bwd(const float* heatmaps, const float* stats, const float* grad_xy, int64_t n_planes, int h,
+                              int w, int ds, float temperature, float* grad_heatmaps, void* stream) {
+  using namespace lpb;
+  LPB_REQUIRE(heatmaps && stats && grad_xy && grad_heatmaps, "decode_bwd: null pointer");
+  LPB_REQUIRE(h >= 1 && w >= 1 && ds >= 1 && ds <= 3, "decode_bwd: bad shape h=%d w=%d ds=%d", h, w, ds);
+  LPB_REQUIRE(n_planes >= 0 && n_planes < (1ll << 31), "decode_bwd: bad n_planes");
+  if (n_planes == 0) return LPB_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (ds) {
+    case 1: return launch_decode_bwd<1>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, grad_heatmaps, s);
+    case 2: return launch_decode_bwd<2>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, grad_heatmaps, s);
+    default: return launch_decode_bwd<3>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, grad_heatmaps, s);
+  }
+}
+
+extern "C" int lpb_upsample2x(const float* in, int64_t n_planes, int h, int w, float* out, void* stream) {
+  using namespace lpb;
+  LPB_REQUIRE(in && out, "upsample2x: null pointer");
+  LPB_REQUIRE(h >= 1 && w >= 1 && n_planes >= 0 && n_planes < (1ll << 31), "upsample2x: bad shape");
+  if (n_planes == 0) return LPB_OK;
+  const DeviceTable* th = get_device_table(h, 1);
+  const DeviceTable* tw = get_device_table(w, 1);
+  if (!th || !tw) return LPB_ERR_INVALID;
+  const int padl = dec_padl(3), pitch = dec_pitch(w, 3);
+  const size_t smem = (size_t)(h + 6) * pitch * sizeof(float);
+  LPB_REQUIRE(smem <= 200 * 1024, "upsample2x: plane %dx%d too large", h, w);
+  if (smem > 48 * 1024)
+    LPB_CUDA(cudaFuncSetAttribute(upsample2x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  upsample2x_kernel<<<(unsigned)n_planes, DEC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(in, h, w, pitch, padl,
+                                                                                                 th->win, tw->win, out);
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}

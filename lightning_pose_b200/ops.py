@@ -1,0 +1,357 @@
+"""torch-facing wrappers of the lpb200 C-ABI: custom ops (``torch.library``) + autograd.
+
+PyTorch is plumbing here (device memory, the current CUDA stream, autograd bookkeeping); every
+numerical operation below runs in ``liblpb200.so``.  All wrappers refuse non-CUDA tensors: there is
+no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import PcaDesc, check, lib
+
+__all__ = [
+    "decode_softargmax",
+    "upsample2x",
+    "generate_heatmaps",
+    "evaluate_heatmaps_at_location",
+    "head_forward",
+    "remap_keypoints",
+    "heatmap_loss",
+    "heatmap_mse_from_keypoints",
+    "temporal_heatmap_loss",
+    "unsup_losses",
+    "PcaParams",
+]
+
+_KIND = {"mse": 0, "kl": 1, "js": 2}
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"lpb200: `{name}` must be a CUDA tensor (this package has no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# =====================================================================================
+# soft-argmax decode
+# =====================================================================================
+@torch.library.custom_op("lpb200::decode_fwd", mutates_args=())
+def _decode_fwd(heatmaps: torch.Tensor, ds: int, temperature: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    b, k, h, w = heatmaps.shape
+    xy = torch.empty((b, k, 2), device=heatmaps.device, dtype=torch.float32)
+    conf = torch.empty((b, k), device=heatmaps.device, dtype=torch.float32)
+    stats = torch.empty((b, k, 8), device=heatmaps.device, dtype=torch.float32)
+    with torch.cuda.device(heatmaps.device):
+        check(lib.lpb_decode_fwd(_ptr(heatmaps), b * k, h, w, ds, temperature, _ptr(xy), _ptr(conf), _ptr(stats), _stream()))
+    return xy, conf, stats
+
+
+@_decode_fwd.register_fake
+def _(heatmaps, ds, temperature):
+    b, k, _, _ = heatmaps.shape
+    return heatmaps.new_empty((b, k, 2)), heatmaps.new_empty((b, k)), heatmaps.new_empty((b, k, 8))
+
+
+@torch.library.custom_op("lpb200::decode_bwd", mutates_args=())
+def _decode_bwd(heatmaps: torch.Tensor, stats: torch.Tensor, grad_xy: torch.Tensor, ds: int, temperature: float) -> torch.Tensor:
+    b, k, h, w = heatmaps.shape
+    g = torch.empty_like(heatmaps)
+    with torch.cuda.device(heatmaps.device):
+        check(lib.lpb_decode_bwd(_ptr(heatmaps), _ptr(stats), _ptr(grad_xy), b * k, h, w, ds, temperature, _ptr(g), _stream()))
+    return g
+
+
+@_decode_bwd.register_fake
+def _(heatmaps, stats, grad_xy, ds, temperature):
+    return torch.empty_like(heatmaps)
+
+
+def _decode_setup(ctx, inputs, output):
+    heatmaps, ds, temperature = inputs
+    ctx.save_for_backward(heatmaps, output[2])
+    ctx.ds, ctx.temperature = ds, temperature
+
+
+def _decode_backward(ctx, g_xy, g_conf, g_stats):
+    heatmaps, stats = ctx.saved_tensors
+    if g_xy is None:
+        return None, None, None
+    return _decode_bwd(heatmaps, stats, g_xy.contiguous().float(), ctx.ds, ctx.temperature), None, None
+
+
+_decode_fwd.register_autograd(_decode_backward, setup_context=_decode_setup)
+
+
+def decode_softargmax(heatmaps: torch.Tensor, downsample_factor: int, temperature: float = 1000.0):
+    """(B,K,h,w) heatmaps -> (preds (B,2K), confidences (B,K)); differentiable wrt heatmaps (via preds)."""
+    hm = _cuda_f32(heatmaps, "heatmaps")
+    if hm.dim() != 4:
+        raise ValueError(f"heatmaps must be (batch, keypoints, h, w); got {tuple(hm.shape)}")
+    if downsample_factor not in (1, 2, 3):
+        raise ValueError(f"downsample_factor must be 1, 2 or 3; got {downsample_factor}")
+    xy, conf, _ = _decode_fwd(hm, int(downsample_factor), float(temperature))
+    return xy.reshape(-1, hm.shape[1] * 2), conf
+
+
+def upsample2x(inputs: torch.Tensor) -> torch.Tensor:
+    x = _cuda_f32(inputs, "inputs")
+    b, k, h, w = x.shape
+    out = torch.empty((b, k, 2 * h, 2 * w), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(lib.lpb_upsample2x(_ptr(x), b * k, h, w, _ptr(out), _stream()))
+    return out
+
+
+# =====================================================================================
+# Gaussian targets / windowed evaluation
+# =====================================================================================
+class _GenerateHeatmaps(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, keypoints, visibility, height, width, oh, ow, sigma):
+        kp = keypoints.contiguous().float()
+        b, k, _ = kp.shape
+        out = torch.empty((b, k, oh, ow), device=kp.device, dtype=torch.float32)
+        with torch.cuda.device(kp.device):
+            check(lib.lpb_generate_heatmaps(_ptr(kp), _ptr(visibility), b * k, float(height), float(width), oh, ow, float(sigma), _ptr(out), _stream()))
+        ctx.save_for_backward(kp, visibility)
+        ctx.meta = (float(height), float(width), oh, ow, float(sigma))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        kp, vis = ctx.saved_tensors
+        height, width, oh, ow, sigma = ctx.meta
+        gk = torch.empty_like(kp)
+        with torch.cuda.device(kp.device):
+            check(lib.lpb_generate_heatmaps_bwd(_ptr(kp), _ptr(vis), _ptr(g.contiguous().float()), kp.shape[0] * kp.shape[1], height, width, oh, ow, sigma, _ptr(gk), _stream()))
+        return gk, None, None, None, None, None, None
+
+
+def generate_heatmaps(keypoints, height, width, output_shape, sigma=1.25, keep_gradients=False, visibility=None):
+    kp = _cuda_f32(keypoints, "keypoints")
+    if kp.dim() != 3 or kp.shape[-1] != 2:
+        raise ValueError(f"keypoints must be (batch, num_keypoints, 2); got {tuple(kp.shape)}")
+    vis = None
+    if visibility is not None:
+        if not visibility.is_cuda:
+            raise RuntimeError("lpb200: `visibility` must be a CUDA tensor")
+        vis = visibility.to(torch.int32).contiguous()
+    if not keep_gradients:
+        kp = kp.detach()
+    return _GenerateHeatmaps.apply(kp, vis, height, width, int(output_shape[0]), int(output_shape[1]), sigma)
+
+
+def evaluate_heatmaps_at_location(heatmaps, locs, radius: int = 2):
+    hm = _cuda_f32(heatmaps, "heatmaps")
+    lc = _cuda_f32(locs, "locs")
+    b, k, h, w = hm.shape
+    out = torch.empty((b, k), device=hm.device, dtype=torch.float32)
+    with torch.cuda.device(hm.device):
+        check(lib.lpb_evaluate_heatmaps_at_location(_ptr(hm), _ptr(lc), b * k, h, w, int(radius), _ptr(out), _stream()))
+    return out
+
+
+# =====================================================================================
+# heatmap head
+# =====================================================================================
+def head_forward(features, weights, biases, final_softmax=True):
+    """PixelShuffle(2) + ConvTranspose2d stack (1 or 2 layers) + spatial softmax; forward only.
+
+    Training uses ``HeatmapHead`` (models/heads/heatmap.py) which pairs this with its backward.
+    """
+    f = _cuda_f32(features, "features")
+    b, c, h, w = f.shape
+    if len(weights) not in (1, 2):
+        raise NotImplementedError(f"head with {len(weights)} deconv layers")
+    w1 = _cuda_f32(weights[0], "w1")
+    b1 = _cuda_f32(biases[0], "b1") if biases[0] is not None else None
+    c1 = w1.shape[1]
+    if len(weights) == 2:
+        w2 = _cuda_f32(weights[1], "w2")
+        b2 = _cuda_f32(biases[1], "b2") if biases[1] is not None else None
+        c2 = w2.shape[1]
+        k, ho, wo = c2, 8 * h, 8 * w
+    else:
+        w2 = b2 = None
+        c2 = 0
+        k, ho, wo = c1, 4 * h, 4 * w
+    out = torch.empty((b, k, ho, wo), device=f.device, dtype=torch.float32)
+    nbytes = C.c_size_t(0)
+    check(lib.lpb_head_workspace_bytes(b, c, h, w, c1, c2, C.byref(nbytes)))
+    ws = torch.empty((max(nbytes.value, 4) // 4,), device=f.device, dtype=torch.float32)
+    with torch.cuda.device(f.device):
+        check(lib.lpb_head_fwd_f32(_ptr(f), b, c, h, w, _ptr(w1), _ptr(b1), c1, _ptr(w2), _ptr(b2), c2, int(bool(final_softmax)), _ptr(out), _ptr(ws), _stream()))
+    return out
+
+
+# =====================================================================================
+# coordinate remap
+# =====================================================================================
+def remap_keypoints(keypoints, transforms, bbox, model_height, model_width, is_multiview=False, num_views=1, out=None):
+    """undo_affine_transform_batch + model_to_frame_batch in one launch (forward; linear map)."""
+    kp = _cuda_f32(keypoints, "keypoints")
+    n, k2 = kp.shape
+    tf = None
+    per_frame = 0
+    if transforms is not None and transforms.shape[-1] == 3:
+        tf = _cuda_f32(transforms, "transforms")
+        if not is_multiview and tf.dim() == 3:
+            per_frame = 1
+            if tf.shape[0] != n:
+                raise ValueError(f"per-frame transforms {tuple(tf.shape)} vs {n} frames")
+    bb = _cuda_f32(bbox, "bbox")
+    res = out if out is not None else torch.empty_like(kp)
+    with torch.cuda.device(kp.device):
+        check(lib.lpb_remap_keypoints(_ptr(kp), n, k2 // 2, _ptr(tf), per_frame, int(num_views), _ptr(bb), bb.shape[0], float(model_height), float(model_width), _ptr(res), _stream()))
+    return res
+
+
+# =====================================================================================
+# heatmap losses
+# =====================================================================================
+class _HeatmapLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, targets, preds, kind):
+        b, k, h, w = preds.shape
+        out = torch.empty((2,), device=preds.device, dtype=torch.float32)
+        ws = torch.empty((b * k * 2,), device=preds.device, dtype=torch.float32)
+        with torch.cuda.device(preds.device):
+            check(lib.lpb_heatmap_loss_fwd(_ptr(targets), _ptr(preds), b * k, h, w, kind, _ptr(out), _ptr(ws), _stream()))
+        ctx.save_for_backward(targets, preds, ws, out)
+        ctx.kind = kind
+        loss, count = out[0].clone(), out[1].clone()
+        ctx.mark_non_differentiable(count)
+        return loss, count
+
+    @staticmethod
+    def backward(ctx, g, _g_count):
+        targets, preds, ws, out = ctx.saved_tensors
+        b, k, h, w = preds.shape
+        gp = torch.empty_like(preds)
+        gg = g.reshape(1).contiguous().float()
+        with torch.cuda.device(preds.device):
+            check(lib.lpb_heatmap_loss_bwd(_ptr(targets), _ptr(preds), b * k, h, w, ctx.kind, _ptr(ws), _ptr(out), _ptr(gg), _ptr(gp), _stream()))
+        return None, gp, None
+
+
+def heatmap_loss(targets, preds, kind: str = "mse", return_count: bool = False):
+    """mean heatmap loss over planes whose target is not all-zero; optionally also that plane count."""
+    t = _cuda_f32(targets, "heatmaps_targ")
+    p = _cuda_f32(preds, "heatmaps_pred")
+    if t.shape != p.shape or t.dim() != 4:
+        raise ValueError(f"heatmap shapes {tuple(t.shape)} vs {tuple(p.shape)}")
+    loss, count = _HeatmapLoss.apply(t.detach(), p, _KIND[kind])
+    return (loss, count) if return_count else loss
+
+
+def heatmap_mse_from_keypoints(keypoints, preds, height, width, sigma=1.25, visibility=None):
+    """Fused target generation + HeatmapMSELoss forward (targets never written to HBM)."""
+    kp = _cuda_f32(keypoints, "keypoints")
+    p = _cuda_f32(preds, "heatmaps_pred")
+    b, k, oh, ow = p.shape
+    vis = visibility.to(torch.int32).contiguous() if visibility is not None else None
+    out = torch.empty((2,), device=p.device, dtype=torch.float32)
+    ws = torch.empty((b * k * 2,), device=p.device, dtype=torch.float32)
+    with torch.cuda.device(p.device):
+        check(lib.lpb_heatmap_mse_from_keypoints_fwd(_ptr(kp), _ptr(vis), _ptr(p), b * k, float(height), float(width), oh, ow, float(sigma), _ptr(out), _ptr(ws), _stream()))
+    return out[0]
+
+
+def temporal_heatmap_loss(heatmaps, confidences, kind: str, epsilon: torch.Tensor, prob_threshold: float):
+    hm = _cuda_f32(heatmaps, "heatmaps_pred")
+    cf = _cuda_f32(confidences, "confidences")
+    t, k, h, w = hm.shape
+    eps = _cuda_f32(epsilon.to(hm.device).reshape(-1).expand(k) if epsilon.numel() in (1, k) else epsilon, "epsilon")
+    out = torch.empty((1,), device=hm.device, dtype=torch.float32)
+    ws = torch.empty((max(t - 1, 1) * k,), device=hm.device, dtype=torch.float32)
+    with torch.cuda.device(hm.device):
+        check(lib.lpb_temporal_heatmap_loss_fwd(_ptr(hm), _ptr(cf), t, k, h, w, _KIND[kind], _ptr(eps), float(prob_threshold), _ptr(out), _ptr(ws), _stream()))
+    return out[0]
+
+
+# =====================================================================================
+# unsupervised losses on (T, K, 2)
+# =====================================================================================
+class PcaParams:
+    """Device-side parameters of one PCA loss (mirror of ``lpb_pca_desc``)."""
+
+    def __init__(self, kp_index, n_sel, n_views, centering, mean, kept, epsilon, device):
+        self.kp_index = torch.as_tensor(kp_index, dtype=torch.int32, device=device).contiguous()
+        self.mean = torch.as_tensor(mean, dtype=torch.float32, device=device).contiguous()
+        self.kept = torch.as_tensor(kept, dtype=torch.float32, device=device).contiguous().reshape(-1, self.mean.numel())
+        self.n_sel, self.n_views = int(n_sel), int(n_views)
+        self.centering = {None: 0, "mean": 1, "median": 2}[centering]
+        self.epsilon = float(epsilon)
+        d = 2 * self.n_views if self.n_views > 0 else 2 * self.n_sel
+        if self.mean.numel() != d or self.kept.shape[1] != d:
+            raise ValueError(f"PCA parameter dimension mismatch: D={d}, mean={self.mean.numel()}, kept={tuple(self.kept.shape)}")
+
+    def desc(self) -> PcaDesc:
+        return PcaDesc(self.kp_index.data_ptr(), self.n_sel, self.n_views, self.centering, self.kept.shape[0],
+                       self.mean.data_ptr(), self.kept.data_ptr(), self.epsilon)
+
+
+class _UnsupLosses(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, keypoints, confidences, temporal_eps, prob_threshold, temporal_on, sv, mv):
+        n_clips, t, k2 = keypoints.shape
+        out = torch.empty((n_clips, 4), device=keypoints.device, dtype=torch.float32)
+        dsv = sv.desc() if sv is not None else None
+        dmv = mv.desc() if mv is not None else None
+        with torch.cuda.device(keypoints.device):
+            check(lib.lpb_unsup_losses_fwd(_ptr(keypoints), _ptr(confidences), n_clips, t, k2 // 2, _ptr(temporal_eps), float(prob_threshold), int(temporal_on),
+                                           C.byref(dsv) if dsv else None, C.byref(dmv) if dmv else None, _ptr(out), _stream()))
+        ctx.save_for_backward(keypoints, confidences, temporal_eps)
+        ctx.meta = (float(prob_threshold), int(temporal_on), sv, mv)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        keypoints, confidences, temporal_eps = ctx.saved_tensors
+        thr, temporal_on, sv, mv = ctx.meta
+        n_clips, t, k2 = keypoints.shape
+        gk = torch.empty_like(keypoints)
+        dsv = sv.desc() if sv is not None else None
+        dmv = mv.desc() if mv is not None else None
+        gg = g.contiguous().float()
+        with torch.cuda.device(keypoints.device):
+            check(lib.lpb_unsup_losses_bwd(_ptr(keypoints), _ptr(confidences), n_clips, t, k2 // 2, _ptr(temporal_eps), thr, temporal_on,
+                                           C.byref(dsv) if dsv else None, C.byref(dmv) if dmv else None, _ptr(gg), _ptr(gk), _stream()))
+        return gk, None, None, None, None, None, None
+
+
+def unsup_losses(keypoints, confidences=None, temporal_eps=None, prob_threshold=0.0, pca_singleview: PcaParams | None = None,
+                 pca_multiview: PcaParams | None = None):
+    """One launch for the unsupervised loss stack.  keypoints (n_clips, T, 2K) or (T, 2K).
+
+    Returns (n_clips, 4) = [temporal, pca_singleview, pca_multiview, 0] per clip (or (4,) for 2-D input).
+    """
+    kp = _cuda_f32(keypoints, "keypoints_pred")
+    squeeze = kp.dim() == 2
+    if squeeze:
+        kp = kp[None]
+    cf = None
+    if confidences is not None:
+        cf = _cuda_f32(confidences, "confidences").reshape(kp.shape[0], kp.shape[1], -1)
+    k = kp.shape[2] // 2
+    te = None
+    if temporal_eps is not None:
+        te = torch.as_tensor(temporal_eps, dtype=torch.float32, device=kp.device).reshape(-1)
+        te = (te.expand(k) if te.numel() == 1 else te).contiguous()
+        if te.numel() != k:
+            raise ValueError(f"temporal epsilon has {te.numel()} entries for {k} keypoints")
+    out = _UnsupLosses.apply(kp, cf, te, prob_threshold, te is not None, pca_singleview, pca_multiview)
+    return out[0] if squeeze else out

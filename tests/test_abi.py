@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library loads, exports exactly what include/lpb200.h declares, validates its
+arguments, and the product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "lpb200.h")
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lpb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_is_plain_c():
+    import subprocess
+
+    subprocess.run(["gcc", "-fsyntax-only", "-x", "c", HEADER], check=True)
+
+
+def test_library_exports_every_declared_symbol():
+    from lightning_pose_b200 import _lib
+
+    syms = header_symbols()
+    assert len(syms) >= 19
+    for s in syms:
+        assert hasattr(_lib.lib, s), f"{s} declared in lpb200.h but not exported by liblpb200.so"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes signature table out of sync with the header"
+    assert _lib.lib.lpb_version() >= 100
+    assert _lib.lib.lpb_build_arch() == b"sm_100a"
+
+
+def test_argument_validation_without_gpu():
+    from lightning_pose_b200 import _lib
+
+    rc = _lib.lib.lpb_decode_fwd(None, 1, 8, 8, 2, 1000.0, None, None, None, None)
+    assert rc == -1 and b"null pointer" in _lib.lib.lpb_last_error()
+    rc = _lib.lib.lpb_decode_prepare(8, 8, 7)
+    assert rc == -1 and b"bad shape" in _lib.lib.lpb_last_error()
+    n = ctypes.c_size_t(0)
+    assert _lib.lib.lpb_head_workspace_bytes(2, 2048, 12, 12, 17, 17, ctypes.byref(n)) == 0
+    assert n.value == 2 * 17 * 48 * 48 * 4
+    with pytest.raises(_lib.LpbError):
+        _lib.check(_lib.lib.lpb_generate_heatmaps(None, None, 1, 1.0, 1.0, 4, 4, 1.25, None, None))
+
+
+def test_no_cpu_fallback():
+    from lightning_pose_b200 import ops
+    from lightning_pose_b200.losses.losses import HeatmapMSELoss, TemporalLoss
+    from lightning_pose_b200.models.heads.heatmap import HeatmapHead, run_subpixelmaxima
+
+    x = torch.rand(1, 2, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.decode_softargmax(x, 2, 1000.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        run_subpixelmaxima(x, 2, torch.tensor(1000.0))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        HeatmapHead("resnet50", 64, 5)(torch.rand(1, 64, 2, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        HeatmapMSELoss()(heatmaps_targ=x, heatmaps_pred=x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        TemporalLoss()(torch.rand(4, 6))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "lightning_pose_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f"{f} references the oracle"

@@ -1,0 +1,389 @@
+"""GPU parity: the CUDA path (through the C-ABI) vs the golden vectors produced by the reference's own
+code and vs the CPU oracle on seeded inputs.  Tolerances follow BASELINE.json's north star:
+1e-4 relative in fp32 for heatmaps, decoded (x, y, confidence) and every loss scalar."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4  # north_star: "within 1e-4 rel fp32"
+T = torch.from_numpy
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "gpu-marked tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def lpb():
+    import lightning_pose_b200  # noqa: F401  (raises if liblpb200.so is missing)
+    from lightning_pose_b200 import ops
+
+    return ops
+
+
+def close(a, b, atol=1e-6, rtol=RTOL):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    np.testing.assert_allclose(a, b, atol=atol, rtol=rtol, equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# decode (a3/a4/a5)
+# ------------------------------------------------------------------------------------------------
+def test_decode_reference_known_answers(lpb, dev, golden):
+    g = golden("decode")
+    for ds in (1, 2, 3):
+        p, c = lpb.decode_softargmax(T(g[f"kat_ds{ds}_in"]).to(dev), ds, 1000.0)
+        close(p, g[f"kat_ds{ds}_out_preds"], atol=2e-5)
+        close(c, g[f"kat_ds{ds}_out_conf"], atol=1e-6)
+    # tests/models/heads/test_heatmap.py:126-156: peaks at (2,2),(4,4) -> (8,8),(16,16), confidence 1
+    p, c = lpb.decode_softargmax(T(g["kat_ds2_in"]).to(dev), 2, 1000.0)
+    close(p[0, :4], [8.0, 8.0, 16.0, 16.0], atol=1e-5)
+    close(c[0, :2], [1.0, 1.0], atol=1e-6)
+    for temp in (1000, 100, 10):
+        p, c = lpb.decode_softargmax(T(g["temp_in"]).to(dev), 2, float(temp))
+        close(p, g[f"temp{temp}_out_preds"], atol=2e-5)
+        close(c, g[f"temp{temp}_out_conf"], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["peaked", "flat", "edge", "multi", "raw"])
+@pytest.mark.parametrize("ds", [1, 2, 3])
+def test_decode_golden_regimes(lpb, dev, golden, name, ds):
+    g = golden("decode")
+    p, c = lpb.decode_softargmax(T(g[f"{name}_in"]).to(dev), ds, 1000.0)
+    # flat planes: the expectation is a mean over ~1e4..1e5 almost-equal weights -> absolute tolerance
+    close(p, g[f"{name}_ds{ds}_out_preds"], atol=5e-4 if name == "flat" else 5e-5)
+    close(c, g[f"{name}_ds{ds}_out_conf"], atol=1e-6)
+
+
+def test_decode_a3_table(lpb, dev, golden):
+    g = golden("decode")
+    t = lpb.generate_heatmaps(T(g["a3_in_keypoints"]).to(dev), 384, 384, (96, 96))
+    close(t.sum((2, 3)), g["a3_out_targets_sum"], atol=2e-6)
+    close(t.amax((2, 3)), g["a3_out_targets_peak"], atol=1e-7)
+    p, c = lpb.decode_softargmax(t, 2, 1000.0)
+    close(p, g["a3_out_preds"], atol=1e-4)
+    close(c, g["a3_out_conf"], atol=2e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 96, 96), (1, 2, 30, 41), (2, 2, 8, 8), (1, 1, 5, 7), (1, 2, 128, 128)])
+@pytest.mark.parametrize("ds", [1, 2, 3])
+def test_decode_vs_oracle_shapes(lpb, dev, shape, ds):
+    """Odd sizes exercise the non-TMA staging path (w % 4 != 0) and all-border planes."""
+    b, k, h, w = shape
+    gen = torch.Generator().manual_seed(100 + h + ds)
+    kp = torch.rand(b, k, 2, generator=gen) * torch.tensor([w * 4.0, h * 4.0])
+    hm = O.gaussian_targets(kp, 4 * h, 4 * w, (h, w)) + 1e-6
+    hm = hm / hm.sum((2, 3), keepdim=True)
+    po, co = O.decode_softargmax(hm, ds, 1000.0)
+    p, c = lpb.decode_softargmax(hm.to(dev), ds, 1000.0)
+    close(p, po, atol=1e-4)
+    close(c, co, atol=2e-6)
+
+
+def test_decode_fullsize_roundtrip_property(lpb, dev):
+    """BASELINE config size (17 kpts, 96x96 -> 384x384), many frames: decode(generate(kp)) ~= kp.
+    Size-independent property (mean error 0.004 px, max 0.09 px away from borders)."""
+    gen = torch.Generator().manual_seed(7)
+    kp = (torch.rand(256, 17, 2, generator=gen) * 368 + 8).to(dev)
+    hm = lpb.generate_heatmaps(kp, 384, 384, (96, 96)) + 1e-6
+    hm = hm / hm.sum((2, 3), keepdim=True)
+    p, c = lpb.decode_softargmax(hm, 2, 1000.0)
+    err = (p.reshape(256, 17, 2) - kp).abs()
+    assert float(err.max()) < 0.12 and float(err.mean()) < 0.01
+    assert float(c.min()) > 0.99
+    # plane-permutation equivariance: a checksum over shuffled planes is unchanged
+    perm = torch.randperm(256 * 17, generator=gen).to(dev)
+    hp = hm.reshape(-1, 1, 96, 96)[perm].reshape(256, 17, 96, 96)
+    p2, c2 = lpb.decode_softargmax(hp, 2, 1000.0)
+    assert torch.equal(p2.reshape(-1, 2), p.reshape(-1, 2)[perm]) and torch.equal(c2.reshape(-1), c.reshape(-1)[perm])
+
+
+def test_decode_backward_vs_autograd(lpb, dev):
+    gen = torch.Generator().manual_seed(11)
+    logits = torch.randn(2, 3, 24 * 32, generator=gen) * 2.5
+    hm = torch.softmax(logits, -1).reshape(2, 3, 24, 32)
+    gxy = torch.randn(2, 6, generator=gen)
+    ref = hm.clone().double().requires_grad_(True)
+    field = ref
+    for _ in range(2):  # float64 oracle of the same algorithm for a clean gradient reference
+        up = torch.nn.functional.interpolate(field, scale_factor=2, mode="bicubic", align_corners=False)
+        k = torch.outer(torch.tensor([1.0, 4, 6, 4, 1]), torch.tensor([1.0, 4, 6, 4, 1])).double() / 256
+        field = torch.nn.functional.conv2d(torch.nn.functional.pad(up, (2, 2, 2, 2)), k.reshape(1, 1, 5, 5).repeat(3, 1, 1, 1), groups=3)
+    p = torch.softmax(field.reshape(2, 3, -1) * 1000.0, -1).reshape(field.shape)
+    ex = (p.sum(2) * torch.arange(p.shape[3], dtype=torch.double)).sum(-1)
+    ey = (p.sum(3) * torch.arange(p.shape[2], dtype=torch.double)).sum(-1)
+    (torch.stack([ex, ey], -1).reshape(2, 6) * gxy.double()).sum().backward()
+    x = hm.to(dev).requires_grad_(True)
+    preds, _ = lpb.decode_softargmax(x, 2, 1000.0)
+    (preds * gxy.to(dev)).sum().backward()
+    g_ref = ref.grad.float()
+    scale = float(g_ref.abs().max())
+    close(x.grad, g_ref, atol=2e-3 * scale, rtol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# targets (a6) and windowed evaluation (a5)
+# ------------------------------------------------------------------------------------------------
+def test_generate_heatmaps_golden(lpb, dev, golden):
+    g = golden("targets")
+    kp, vis = T(g["in_keypoints"]).to(dev), T(g["in_visibility"]).to(dev)
+    close(lpb.generate_heatmaps(kp, 48, 64, (12, 16)), g["out_vis_none"], atol=1e-7)
+    close(lpb.generate_heatmaps(kp, 48, 64, (12, 16), visibility=vis), g["out_vis"], atol=1e-7)
+    close(lpb.generate_heatmaps(kp, 48, 64, (24, 32), sigma=2.0), g["out_sigma2_ds1"], atol=1e-7)
+    close(lpb.evaluate_heatmaps_at_location(T(g["eval_in_heatmaps"]).to(dev), T(g["eval_in_locs"]).to(dev)), g["eval_out"], atol=2e-6)
+
+
+def test_generate_heatmaps_backward(lpb, dev):
+    gen = torch.Generator().manual_seed(5)
+    kp = torch.rand(3, 4, 2, generator=gen) * torch.tensor([64.0, 48.0])
+    kp[0, 1] = torch.tensor([-9.0, 3.0])  # clamped + bad -> zero plane -> zero grad
+    gout = torch.randn(3, 4, 12, 16, generator=gen)
+    ref = kp.clone().double().requires_grad_(True)
+    x = ref[..., 0] * (16 / 64)
+    y = ref[..., 1] * (12 / 48)
+    bad = (x < -1) | (x > 17) | (y < -1) | (y > 13)
+    xc, yc = x.clamp(-1, 17)[..., None, None], y.clamp(-1, 13)[..., None, None]
+    cols = torch.arange(16, dtype=torch.double)[None, None, None, :]
+    rows = torch.arange(12, dtype=torch.double)[None, None, :, None]
+    gmap = torch.exp(-((cols - xc) ** 2 + (rows - yc) ** 2) / (2 * 1.25**2))
+    gmap = gmap / gmap.sum((2, 3), keepdim=True)
+    gmap = torch.where(bad[..., None, None], torch.zeros_like(gmap), gmap)
+    (gmap * gout.double()).sum().backward()
+    k = kp.to(dev).requires_grad_(True)
+    out = lpb.generate_heatmaps(k, 48, 64, (12, 16), keep_gradients=True)
+    (out * gout.to(dev)).sum().backward()
+    close(k.grad, ref.grad.float(), atol=1e-6, rtol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# head (a1/a2)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,nl", [("resnet", 2), ("vit", 1)])
+def test_head_golden(lpb, dev, golden, tag, nl):
+    g = golden("head")
+    ws = [T(g[f"{tag}_w{i}"]).to(dev) for i in range(nl)]
+    bs = [T(g[f"{tag}_b{i}"]).to(dev) for i in range(nl)]
+    f = T(g[f"{tag}_in_features"]).to(dev)
+    close(lpb.head_forward(f, ws, bs, True), g[f"{tag}_out_heatmaps"], atol=1e-8)
+    close(lpb.head_forward(f, ws, bs, False), g[f"{tag}_out_logits"], atol=2e-5)
+
+
+@pytest.mark.parametrize("cfg", [("resnet50", 2048, 17, 12, 12, 2), ("vits_dino", 384, 17, 16, 16, 2), ("resnet50", 512, 17, 4, 6, 3)])
+def test_head_module_vs_oracle(lpb, dev, cfg):
+    """Real channel counts of BASELINE configs 2 and 3 (random weights with a peaked-logit gain)."""
+    from lightning_pose_b200.models.heads.heatmap import HeatmapHead
+
+    arch, cin, k, fh, fw, b = cfg
+    torch.manual_seed(3)
+    head = HeatmapHead(arch, cin, k)
+    for layer in list(head.upsampling_layers)[1:]:
+        torch.nn.init.xavier_uniform_(layer.weight, gain=2.0)
+        torch.nn.init.uniform_(layer.bias, -0.2, 0.2)
+    feats = torch.randn(b, cin, fh, fw) * 0.5
+    deconvs = list(head.upsampling_layers)[1:]
+    ref = O.head_forward(feats, [d.weight.detach() for d in deconvs], [d.bias.detach() for d in deconvs])
+    out = head.to(dev)(feats.to(dev))
+    assert out.shape == ref.shape
+    close(out, ref, atol=1e-9)
+    close(out.sum((2, 3)), torch.ones(b, k), atol=1e-5)  # tests/models/heads/test_heatmap.py:260-273
+    # reference state-dict keys / layouts load unchanged
+    assert set(head.state_dict()) == {f"upsampling_layers.{i}.{n}" for i in range(1, len(deconvs) + 1) for n in ("weight", "bias")}
+
+
+def test_head_backward_matches_oracle_autograd(lpb, dev):
+    from lightning_pose_b200.models.heads.heatmap import HeatmapHead
+
+    torch.manual_seed(4)
+    head = HeatmapHead("resnet50", 64, 5)
+    for layer in list(head.upsampling_layers)[1:]:
+        torch.nn.init.xavier_uniform_(layer.weight, gain=2.0)
+    feats = torch.randn(2, 64, 3, 4)
+    gout = torch.randn(2, 5, 24, 32)
+    deconvs = list(head.upsampling_layers)[1:]
+    f_ref = feats.clone().requires_grad_(True)
+    ws = [d.weight.detach().clone().requires_grad_(True) for d in deconvs]
+    bs = [d.bias.detach().clone().requires_grad_(True) for d in deconvs]
+    (O.head_forward(f_ref, ws, bs) * gout).sum().backward()
+    head = head.to(dev)
+    f = feats.to(dev).requires_grad_(True)
+    (head(f) * gout.to(dev)).sum().backward()
+    close(f.grad, f_ref.grad, atol=1e-7, rtol=1e-3)
+    for d, w_ref in zip(list(head.upsampling_layers)[1:], ws):
+        close(d.weight.grad, w_ref.grad, atol=1e-7, rtol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# remap (a8/a9)
+# ------------------------------------------------------------------------------------------------
+def test_remap_golden(lpb, dev, golden):
+    from lightning_pose_b200.data.bboxes import model_to_frame_batch
+    from lightning_pose_b200.data.utils import undo_affine_transform_batch
+
+    g = golden("remap")
+    kp = T(g["in_keypoints"]).to(dev)
+    close(undo_affine_transform_batch(kp.clone(), T(g["in_transform_shared"]).to(dev)), g["out_affine_shared"], atol=2e-5)
+    close(undo_affine_transform_batch(kp.clone(), T(g["in_transform_perframe"]).to(dev)), g["out_affine_perframe"], atol=2e-5)
+    close(undo_affine_transform_batch(kp.clone(), T(g["in_transform_multiview"]).to(dev), True), g["out_affine_multiview"], atol=2e-5)
+    same = undo_affine_transform_batch(kp, torch.ones(1, device=dev))
+    assert same is kp
+    frames = torch.zeros(6, 3, 128, 256, device=dev)
+    inp = kp.clone()
+    out = model_to_frame_batch({"frames": frames, "bbox": T(g["in_bbox"]).to(dev), "is_multiview": False}, inp)
+    close(out, g["out_frame_single"], atol=2e-5)
+    close(inp, g["out_frame_single"], atol=2e-5)  # in-place through the caller's tensor, like the reference
+    out = model_to_frame_batch({"frames": frames, "bbox": T(g["in_bbox_ctx"]).to(dev), "is_multiview": False}, kp.clone())
+    close(out, g["out_frame_ctx"], atol=2e-5)
+    out = model_to_frame_batch({"frames": frames, "bbox": T(g["in_bbox_mv"]).to(dev), "is_multiview": True}, kp.clone())
+    close(out, g["out_frame_mv"], atol=2e-5)
+    fused = lpb.remap_keypoints(kp, T(g["in_transform_shared"]).to(dev), T(g["in_bbox"]).to(dev), 128, 256)
+    ref = O.model_to_frame(O.undo_affine(T(g["in_keypoints"]), T(g["in_transform_shared"])), T(g["in_bbox"]), 128, 256)
+    close(fused, ref, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# losses (a10-a16)
+# ------------------------------------------------------------------------------------------------
+def test_heatmap_losses_golden(lpb, dev, golden):
+    from lightning_pose_b200.losses.losses import HeatmapJSLoss, HeatmapKLLoss, HeatmapMSELoss
+
+    g = golden("losses")
+    a = O.gaussian_targets(T(g["hm_in_a_kp"]), 384, 384, (96, 96)).to(dev)
+    b = O.gaussian_targets(T(g["hm_in_b_kp"]), 384, 384, (96, 96)).to(dev)
+    targ = O.gaussian_targets(T(g["hmb_in_kp"]), 128, 128, (32, 32), visibility=T(g["hmb_in_vis"])).to(dev)
+    pred = T(g["hmb_in_pred"]).to(dev)
+    for nm, cls in (("mse", HeatmapMSELoss), ("kl", HeatmapKLLoss), ("js", HeatmapJSLoss)):
+        v, logs = cls()(heatmaps_targ=b, heatmaps_pred=a, stage="train")
+        close(v, g[f"hm_{nm}_out_targb_preda"], atol=1e-7)
+        assert logs[0]["name"] == f"train_heatmap_{nm}_loss" and logs[1]["name"] == f"heatmap_{nm}_weight"
+        v, _ = cls()(heatmaps_targ=a, heatmaps_pred=b)
+        close(v, g[f"hm_{nm}_out_targa_predb"], atol=1e-7)
+        v, _ = cls()(heatmaps_targ=targ, heatmaps_pred=pred)
+        close(v, g[f"hmb_{nm}_out"], atol=1e-7)
+    fused = lpb.heatmap_mse_from_keypoints(T(g["hmb_in_kp"]).to(dev), pred, 128, 128, visibility=T(g["hmb_in_vis"]).to(dev))
+    close(fused, g["hmb_mse_out"], atol=1e-7)
+
+
+@pytest.mark.parametrize("kind", ["mse", "kl", "js"])
+def test_heatmap_loss_backward(lpb, dev, golden, kind):
+    g = golden("losses")
+    targ = O.gaussian_targets(T(g["hmb_in_kp"]), 128, 128, (32, 32), visibility=T(g["hmb_in_vis"]))
+    pred = T(g["hmb_in_pred"])
+    fn = {"mse": O.heatmap_mse_loss, "kl": O.heatmap_kl_loss, "js": O.heatmap_js_loss}[kind]
+    pr = pred.clone().requires_grad_(True)
+    (fn(targ, pr) * 1.7).backward()
+    p = pred.to(dev).requires_grad_(True)
+    (lpb.heatmap_loss(targ.to(dev), p, kind) * 1.7).backward()
+    close(p.grad, pr.grad, atol=1e-7, rtol=1e-3)
+
+
+def test_unsup_losses_golden(lpb, dev, golden):
+    from lightning_pose_b200.losses.losses import TemporalLoss
+
+    g = golden("losses")
+    kp, conf = T(g["temporal_in_kp"]).to(dev), T(g["temporal_in_conf"]).to(dev)
+    tl = TemporalLoss(epsilon=[2.0, 20.0], prob_threshold=0.05)
+    v, _ = tl(kp, conf)
+    close(v, 3.8, atol=1e-6)  # SURVEY A.3 / tests/losses/test_losses.py:343-392
+    v, _ = tl(kp)
+    close(v, 5.8, atol=1e-6)
+    v, _ = TemporalLoss(epsilon=20.0, prob_threshold=0.05)(T(g["temporal2_in_kp"]).to(dev), T(g["temporal2_in_conf"]).to(dev))
+    close(v, g["temporal2_out"], atol=1e-6)
+    kseq = T(g["pca_in_kp"]).to(dev)
+    cols = g["pca_sv_cols"].tolist()
+    for centering in (None, "mean", "median"):
+        p = lpb.PcaParams(np.asarray(cols, np.int32), len(cols), 0, centering, g["pca_sv_mean"], g["pca_sv_kept"], 2.5, dev)
+        close(lpb.unsup_losses(kseq, pca_singleview=p)[1], g[f"pca_sv_out_{centering}"], atol=1e-5)
+    mcm = g["pca_mv_mcm"]
+    p = lpb.PcaParams(mcm.reshape(-1).astype(np.int32), mcm.shape[1], mcm.shape[0], None, g["pca_mv_mean"], g["pca_mv_kept"], 0.7, dev)
+    close(lpb.unsup_losses(kseq, pca_multiview=p)[2], g["pca_mv_out"], atol=1e-5)
+    # batched clips: every clip equals the single-clip result
+    out = lpb.unsup_losses(torch.stack([kseq, kseq.flip(0)]), temporal_eps=1.0, pca_multiview=p)
+    close(out[0, 2], g["pca_mv_out"], atol=1e-5)
+    close(out[1, 0], out[0, 0], atol=1e-5)
+
+
+def test_unsup_losses_backward(lpb, dev, golden):
+    g = golden("losses")
+    kseq, conf = T(g["pca_in_kp"]), torch.rand(32, 17, generator=torch.Generator().manual_seed(2))
+    cols = g["pca_sv_cols"].tolist()
+    mcm = g["pca_mv_mcm"]
+    for centering in (None, "mean", "median"):
+        ref = kseq.clone().requires_grad_(True)
+        tot = (
+            1.3 * O.temporal_loss(ref, conf, 3.0, 0.2)
+            + 0.7 * O.pca_loss(O.pca_format_singleview(ref, cols, centering), T(g["pca_sv_mean"]), T(g["pca_sv_kept"]), 2.5)
+            + 2.1 * O.pca_loss(O.pca_format_multiview(ref, mcm.tolist()), T(g["pca_mv_mean"]), T(g["pca_mv_kept"]), 0.7)
+        )
+        tot.backward()
+        x = kseq.to(dev).requires_grad_(True)
+        sv = lpb.PcaParams(np.asarray(cols, np.int32), len(cols), 0, centering, g["pca_sv_mean"], g["pca_sv_kept"], 2.5, dev)
+        mv = lpb.PcaParams(mcm.reshape(-1).astype(np.int32), mcm.shape[1], mcm.shape[0], None, g["pca_mv_mean"], g["pca_mv_kept"], 0.7, dev)
+        out = lpb.unsup_losses(x, conf.to(dev), temporal_eps=3.0, prob_threshold=0.2, pca_singleview=sv, pca_multiview=mv)
+        close(1.3 * out[0] + 0.7 * out[1] + 2.1 * out[2], tot, atol=1e-5)
+        (1.3 * out[0] + 0.7 * out[1] + 2.1 * out[2]).backward()
+        close(x.grad, ref.grad, atol=1e-6, rtol=1e-3)
+
+
+def test_temporal_heatmap_and_reprojection_golden(lpb, dev, golden):
+    from lightning_pose_b200.losses.losses import ReprojectionHeatmapLoss, TemporalHeatmapLoss
+
+    g = golden("losses")
+    hseq, cseq = T(g["thm_in_heatmaps"]).to(dev), T(g["thm_in_conf"]).to(dev)
+    v, _ = TemporalHeatmapLoss("temporal_heatmap_mse", epsilon=1e-5, prob_threshold=0.2)(hseq, cseq)
+    close(v, g["thm_mse_out"], atol=1e-8)
+    v, _ = TemporalHeatmapLoss("temporal_heatmap_kl", epsilon=[0.5, 1.0, 2.0], prob_threshold=0.2)(hseq, cseq)
+    close(v, g["thm_kl_out"], atol=1e-6)
+    targ = O.gaussian_targets(T(g["hmb_in_kp"]), 128, 128, (32, 32), visibility=T(g["hmb_in_vis"])).to(dev)
+    v, _ = ReprojectionHeatmapLoss(128, 128, 32, 32, log_weight=1.0)(heatmaps_targ=targ, keypoints_pred_2d_reprojected=T(g["reproj_in_kp"]).to(dev))
+    close(v, g["reproj_out"], atol=1e-7)
+
+
+def test_loss_factory_golden(lpb, dev, golden):
+    from lightning_pose_b200.losses.factory import LossFactory
+
+    g = golden("losses")
+    targ = O.gaussian_targets(T(g["hmb_in_kp"]), 128, 128, (32, 32), visibility=T(g["hmb_in_vis"])).to(dev)
+    fac = LossFactory({"heatmap_mse": {"log_weight": 0.0}, "temporal": {"log_weight": 5.0, "epsilon": 20.0, "prob_threshold": 0.05}}, None)
+    tot, logs = fac(stage="train", anneal_weight=0.3, heatmaps_targ=targ, heatmaps_pred=T(g["hmb_in_pred"]).to(dev),
+                    keypoints_pred=T(g["temporal2_in_kp"]).to(dev), confidences=T(g["temporal2_in_conf"]).to(dev))
+    close(tot, g["factory_out_total"], atol=1e-7)
+    assert [d["name"] for d in logs] == g["factory_log_names"].tolist()
+    close(torch.stack([torch.as_tensor(d["value"]).float().cpu() for d in logs]), g["factory_log_values"], atol=1e-7)
+
+
+def test_tracker_semisupervised_step_vs_oracle(lpb, dev):
+    """End to end through the mirrored boundary (HeatmapHead -> decode -> remap -> LossFactory)."""
+    from lightning_pose_b200.losses.factory import LossFactory
+    from lightning_pose_b200.models.heads.heatmap import HeatmapHead
+
+    torch.manual_seed(9)
+    head = HeatmapHead("resnet50", 256, 17)
+    for layer in list(head.upsampling_layers)[1:]:
+        torch.nn.init.xavier_uniform_(layer.weight, gain=2.5)
+    feats = torch.randn(8, 256, 4, 4) * 0.5
+    bbox = torch.tensor([[3.0, 5.0, 200.0, 260.0]]).repeat(8, 1)
+    ang = 0.1
+    tf = torch.tensor([[1.05 * np.cos(ang), -1.05 * np.sin(ang), 2.0], [1.05 * np.sin(ang), 1.05 * np.cos(ang), -1.0]], dtype=torch.float32)
+    deconvs = list(head.upsampling_layers)[1:]
+    hm_ref = O.head_forward(feats, [d.weight.detach() for d in deconvs], [d.bias.detach() for d in deconvs])
+    kp_ref, cf_ref = O.decode_softargmax(hm_ref, 2, 1000.0)
+    kp_ref = O.model_to_frame(O.undo_affine(kp_ref, tf), bbox, 128, 128)
+    loss_ref = O.temporal_loss(kp_ref, cf_ref, 2.0, 0.05)
+
+    head = head.to(dev)
+    hm = head(feats.to(dev))
+    kp, cf = head.run_subpixelmaxima(hm)
+    kp = lpb.remap_keypoints(kp, tf.to(dev), bbox.to(dev), 128, 128)
+    fac = LossFactory({"temporal": {"log_weight": 0.0, "epsilon": 2.0, "prob_threshold": 0.05}}, None)
+    tot, _ = fac(stage=None, keypoints_pred=kp, confidences=cf)
+    close(hm, hm_ref, atol=1e-9)
+    close(kp, kp_ref, atol=2e-3, rtol=RTOL)
+    close(cf, cf_ref, atol=1e-5)
+    close(tot, 0.5 * loss_ref, atol=1e-4)

@@ -1,0 +1,79 @@
+"""CPU: the mirrored class / registry surface matches what the reference's introspection relies on
+(lightning_pose/models/factory.py:116-192, tests/models/test_factory.py:126-155,
+tests/models/heads/test_heatmap.py:14-81,293-325, tests/losses/test_factory.py)."""
+import inspect
+
+import pytest
+import torch
+from torch import nn
+
+from lightning_pose_b200.losses import losses as L
+from lightning_pose_b200.losses.factory import LossFactory, get_loss_classes
+from lightning_pose_b200.models.heads.heatmap import HeatmapHead, make_upsampling_layers
+
+
+def required_keys(cls):
+    sig = inspect.signature(cls.__call__)
+    return {n for n, p in sig.parameters.items()
+            if n not in ("self", "stage") and p.kind is p.POSITIONAL_OR_KEYWORD and p.default is p.empty}
+
+
+def test_registry_names():
+    assert sorted(get_loss_classes()) == sorted([
+        "regression", "heatmap_mse", "heatmap_kl", "heatmap_js", "pca_multiview", "pca_singleview", "temporal",
+        "temporal_heatmap_mse", "temporal_heatmap_kl", "supervised_pairwise_projections",
+        "supervised_reprojection_heatmap_mse"])
+    assert L.RegressionRMSELoss.loss_name == "rmse" and "rmse" not in get_loss_classes()
+    assert set(L.__all__) == {"Loss", "HeatmapLoss", "HeatmapMSELoss", "HeatmapKLLoss", "HeatmapJSLoss", "PCALoss",
+                              "TemporalLoss", "TemporalHeatmapLoss", "RegressionMSELoss", "RegressionRMSELoss",
+                              "PairwiseProjectionsLoss", "ReprojectionHeatmapLoss"}
+
+
+def test_call_signatures_are_load_bearing():
+    assert required_keys(L.HeatmapMSELoss) == {"heatmaps_targ", "heatmaps_pred"}
+    assert required_keys(L.TemporalLoss) == {"keypoints_pred"}  # confidences stays optional
+    assert required_keys(L.RegressionMSELoss) == {"keypoints_targ", "keypoints_pred"}
+    assert required_keys(L.PCALoss) == {"keypoints_pred"}
+    assert required_keys(L.TemporalHeatmapLoss) == {"heatmaps_pred", "confidences"}
+    assert required_keys(L.ReprojectionHeatmapLoss) == {"heatmaps_targ", "keypoints_pred_2d_reprojected"}
+
+
+def test_loss_hyperparameters():
+    t = L.TemporalLoss(epsilon=[1.0, 2.0], prob_threshold=0.05, log_weight=11.0)
+    assert torch.allclose(t.weight, 1.0 / (2.0 * torch.exp(torch.tensor(11.0))))
+    assert t.epsilon.tolist() == [1.0, 2.0] and float(t.prob_threshold) == pytest.approx(0.05)
+    with pytest.raises(ValueError):
+        L.TemporalHeatmapLoss(loss_name="nope")
+    with pytest.raises(ValueError):
+        L.PCALoss(loss_name="nope", data_module=object())
+    # staged helpers: the reference's analytic TemporalLoss example (tests/losses/test_losses.py:343-360)
+    kp = torch.tensor([[0.0, 0.0, 0.0, 0.0], [1.0, 1.0, 3.0, 4.0]])
+    assert torch.allclose(t.compute_loss(kp), torch.tensor([[2.0**0.5, 5.0]]))
+    assert torch.allclose(t.rectify_epsilon(torch.tensor([[1.5, 5.0]])), torch.tensor([[0.5, 3.0]]))
+
+
+def test_loss_factory_construction_without_data_module():
+    fac = LossFactory({"heatmap_mse": {"log_weight": 0.0}, "temporal": {"log_weight": 5.0, "epsilon": 3.0}}, None)
+    assert list(fac.loss_instance_dict) == ["heatmap_mse", "temporal"]
+    assert isinstance(fac, nn.Module)
+
+
+@pytest.mark.parametrize("n_layers", [1, 2, 3])
+def test_make_upsampling_layers(n_layers):
+    m = make_upsampling_layers(256, 64, 128, n_layers)
+    assert len(m) == n_layers + 1 and isinstance(m[0], nn.PixelShuffle)
+    assert m[1].in_channels == 64 and m[-1].out_channels == 64
+    if n_layers > 1:
+        assert m[1].out_channels == 128 and m[-1].in_channels == 128
+    for conv in list(m)[1:]:
+        assert isinstance(conv, nn.ConvTranspose2d)
+        assert (conv.kernel_size, conv.stride, conv.padding, conv.output_padding) == ((3, 3), (2, 2), (1, 1), (1, 1))
+
+
+@pytest.mark.parametrize("arch,ds,n", [("resnet50", 1, 3), ("resnet50", 2, 2), ("resnet50", 3, 1), ("vits_dino", 1, 2), ("vits_dino", 2, 1)])
+def test_head_layer_count_rule(arch, ds, n):
+    head = HeatmapHead(arch, 256, 17, downsample_factor=ds)
+    assert len(head.upsampling_layers) == n + 1
+    assert float(head.temperature) == 1000.0 and head.final_softmax is True
+    assert head.upsampling_layers[1].weight.shape[:2] == (64, 17 if n == 1 else 17)
+    assert float(head.upsampling_layers[1].bias.abs().max()) == 0.0
