@@ -176,7 +176,7 @@ def kernel_breakdown(hp: "HotPath", feats, reps=5):
         hm = hp.head(feats)
         kp, cf = ops.decode_softargmax(hm, 2, 1000.0)
         stages = {
-            "head_fwd(convT1+convT2+softmax)": (lambda: hp.head(feats), nf * (FEAT_C * FEAT_HW * FEAT_HW * 4 + K_PTS * HM * HM * 4)),
+            "head_fwd(convT1+convT2+softmax)": (lambda: hp.head(feats), nf * (FEAT_C * FEAT_HW * FEAT_HW * feats.element_size() + K_PTS * HM * HM * 4)),
             "decode_fwd": (lambda: ops.decode_softargmax(hm, 2, 1000.0), nf * (K_PTS * HM * HM * 4 + K_PTS * 12)),
             "target+mse_fwd": (lambda: ops.heatmap_mse_from_keypoints(hp.kp_lab, hm[: n * B_LABELED], IMG, IMG, visibility=hp.vis),
                                n * B_LABELED * (K_PTS * HM * HM * 4 + K_PTS * 12)),
@@ -207,8 +207,10 @@ def run_ours(args):
 
     prob = make_problem(args.clips, seed=1234 + rank, device=dev, head_gain=args.head_gain)
     hp = HotPath(prob, dev, args.fwd_only)
-    feats_host = prob["feats"].pin_memory()
+    tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    feats_host = prob["feats"].to(tdt).pin_memory()
     feats = feats_host.to(dev, non_blocking=True)
+    esz = feats.element_size()
     n_frames = feats.shape[0]
     barrier = (lambda: dist.barrier()) if dist else None
 
@@ -243,24 +245,38 @@ def run_ours(args):
         return
     pk, pk_src = peaks()
     br = kernel_breakdown(hp, feats)
+    flat = None
+    if not args.no_flat:
+        # secondary regime: the reference's own initialiser (xavier gain 0.01) -> flat heatmaps -> the decode
+        # cannot prune and evaluates the whole 384x384 field (SURVEY 7 "hard parts" 1)
+        from lightning_pose_b200.models.heads.heatmap import HeatmapHead
+
+        torch.manual_seed(99)
+        hp.head = HeatmapHead("resnet50", FEAT_C, K_PTS).to(dev)
+        ms_flat = time_steps(lambda: hp.step(feats), max(2, args.steps // 2), 2)
+        flat = {"value": n_frames * max(2, args.steps // 2) / (ms_flat / 1e3), "unit": "frames/s",
+                "head_init": "reference initialiser, xavier gain 0.01 (flat heatmaps, dense decode)",
+                "stages": {k: round(v["ms"], 4) for k, v in kernel_breakdown(hp, feats, reps=3).items()}}
     dom = max(br, key=lambda k: br[k]["ms"])
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": args.dtype, "data": "synthetic",
         "config": {
             "workload": f"BASELINE configs[1] hot path on ResNet-50 features (B,2048,12,12): {args.clips} clips/step/GPU x (16 labeled + 32 unlabeled) frames, "
                         f"K=17, heatmaps 96x96, decode field 384x384; pass = {'forward' if args.fwd_only else 'forward+backward'}",
-            "frames_per_step_per_gpu": n_frames, "head_init": f"uniform xavier gain {args.head_gain} (peaked, trained-like logits)",
-            "l2_policy": f"inputs larger than L2 ({feats.numel() * 4 / 2**20:.0f} MiB of features per step)", "parallelism": f"dp{world}",
+            "frames_per_step_per_gpu": n_frames, "head_init": f"xavier-uniform gain {args.head_gain} (trained-like peaked heatmaps; see flat_regime for the fresh-init case)",
+            "l2_policy": f"inputs larger than L2 ({feats.numel() * esz / 2**20:.0f} MiB of features per step)", "parallelism": f"dp{world}",
         },
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": feats.numel() * 4, "d2h_bytes_per_step": 16},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": feats.numel() * esz, "d2h_bytes_per_step": 16},
         "gpu_launches": HotPath.LAUNCHES_FWD * args.steps if args.fwd_only else None,
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": br[dom]["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": br[dom]["gbs"] / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src},
         "stages": {k: {"ms": round(v["ms"], 4), "GBps": round(v["gbs"], 1), "frac_hbm": round(v["gbs"] / pk["hbm_gbs"], 4)} for k, v in br.items()},
     }
+    if flat is not None:
+        line["flat_regime"] = flat
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference(seed=1234, clips=1, reps=1)
     print(json.dumps(line))
@@ -342,7 +358,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=16, help="clips per step per GPU (48 frames each)")
-    ap.add_argument("--head-gain", type=float, default=3.0)
+    ap.add_argument("--head-gain", type=float, default=5.0, help="xavier gain of the synthetic head weights (5 = trained-like peaks ~0.2)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="feature dtype (bf16 = tcgen05 head)")
+    ap.add_argument("--no-flat", action="store_true", help="skip the secondary flat-heatmap (fresh-init) regime")
     ap.add_argument("--fwd-only", action="store_true", default=True)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -98,6 +98,15 @@ int lpb_head_fwd_f32(const float* features, int B, int C, int H, int W, const fl
                      int c1, const float* w2, const float* b2, int c2, int final_softmax, float* out,
                      void* workspace, void* stream);
 
+/* bf16 tensor-core path (tcgen05 / TMEM), two-deconv heads (ResNet family): features bf16 NCHW, fp32
+ * master weights (rounded to bf16 on device, as autocast does), fp32 accumulate, fp32 heatmaps.
+ * C % 128 == 0, H*W % 8 == 0, c1, c2 <= 20.  Returns LPB_ERR_UNSUPPORTED for shapes outside this
+ * build's tiling (callers then use lpb_head_fwd_f32 on up-cast features). */
+int lpb_head_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes);
+int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int W, const float* w1, const float* b1, int c1,
+                      const float* w2, const float* b2, int c2, int final_softmax, float* out, void* workspace,
+                      void* stream);
+
 /* ---- coordinate remap -------------------------------------------------------------------------
  * replaces undo_affine_transform_batch + model_to_frame_batch
  *   lightning_pose/data/utils.py:142-234, lightning_pose/data/bboxes.py:74-105,222-288

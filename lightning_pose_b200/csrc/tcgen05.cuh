@@ -1,0 +1,85 @@
+// Minimal hand-written tcgen05 / TMEM / UMMA-descriptor helpers (sm_100a inline PTX).
+// Field layouts follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor" tables
+// (cross-checked against cute/arch/mma_sm100_desc.hpp vendored in this image).
+#pragma once
+#include <cstdint>
+
+#include "lpb_common.cuh"
+
+namespace lpb {
+namespace tc {
+
+// ---- TMEM allocation (one warp executes; address lands in shared memory) -------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- shared-memory matrix descriptor: K-major, no swizzle ------------------------------------------
+// canonical layout (16-byte units): ((8, m), 2) : ((1, SBO), LBO)  i.e. a core matrix is 8 rows x 16 B
+// stored contiguously; SBO = byte distance between 8-row groups, LBO = byte distance between the two
+// 8-element K chunks of one K=16 instruction.  With SBO = 128 rows are linear in memory (row r at
+// r*16 B), so a row-shifted view of the same buffer is just a different start address.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);             // [0,14)  start address
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // [16,30) leading-dimension byte offset
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;   // [32,46) stride-dimension byte offset
+  d |= (uint64_t)1 << 46;                              // [46,48) descriptor version 1 (sm_100)
+  return d;                                            // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
+}
+
+// ---- instruction descriptor: kind::f16, BF16 x BF16 -> F32, both operands K-major -------------------
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
+  return (1u << 4)                      // c_format = F32
+         | (1u << 7)                    // a_format = BF16
+         | (1u << 10)                   // b_format = BF16
+         | ((uint32_t)(N >> 3) << 17)   // n_dim
+         | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread on behalf of the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- TMEM -> registers: 32 lanes x 16 consecutive 32-bit columns per warp ---------------------------
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- plain mbarrier arrive ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+}  // namespace tc
+}  // namespace lpb

@@ -167,15 +167,39 @@ def evaluate_heatmaps_at_location(heatmaps, locs, radius: int = 2):
 # =====================================================================================
 # heatmap head
 # =====================================================================================
+def _head_forward_bf16(f, weights, biases, final_softmax):
+    """tcgen05 path; returns None when the shape is outside the tensor-core tiling of this build."""
+    b, c, h, w = f.shape
+    w1, w2 = (_cuda_f32(x, "weight") for x in weights)
+    b1, b2 = (_cuda_f32(x, "bias") for x in biases)
+    c1, c2 = w1.shape[1], w2.shape[1]
+    if c % 128 or (h * w) % 8 or c1 > 20 or c2 > 20 or (2 * h * (2 * w + 1) + 127) // 128 * 80 > 512:
+        return None
+    nbytes = C.c_size_t(0)
+    check(lib.lpb_head_bf16_workspace_bytes(b, c, h, w, c1, c2, C.byref(nbytes)))
+    ws = torch.empty((nbytes.value,), device=f.device, dtype=torch.uint8)
+    out = torch.empty((b, c2, 8 * h, 8 * w), device=f.device, dtype=torch.float32)
+    with torch.cuda.device(f.device):
+        check(lib.lpb_head_fwd_bf16(_ptr(f), b, c, h, w, _ptr(w1), _ptr(b1), c1, _ptr(w2), _ptr(b2), c2, int(bool(final_softmax)), _ptr(out), _ptr(ws), _stream()))
+    return out
+
+
 def head_forward(features, weights, biases, final_softmax=True):
     """PixelShuffle(2) + ConvTranspose2d stack (1 or 2 layers) + spatial softmax; forward only.
 
-    Training uses ``HeatmapHead`` (models/heads/heatmap.py) which pairs this with its backward.
+    bf16 features take the tcgen05 tensor-core kernels (fp32 accumulate, fp32 heatmaps); fp32 features
+    take the full-precision CUDA-core kernels.  Training uses ``HeatmapHead`` which adds the backward.
     """
-    f = _cuda_f32(features, "features")
-    b, c, h, w = f.shape
+    if not isinstance(features, torch.Tensor) or not features.is_cuda:
+        raise RuntimeError("lpb200: `features` must be a CUDA tensor (this package has no CPU fallback)")
     if len(weights) not in (1, 2):
         raise NotImplementedError(f"head with {len(weights)} deconv layers")
+    if features.dtype == torch.bfloat16 and len(weights) == 2 and all(b is not None for b in biases):
+        out = _head_forward_bf16(features.contiguous(), weights, biases, final_softmax)
+        if out is not None:
+            return out
+    f = _cuda_f32(features, "features")
+    b, c, h, w = f.shape
     w1 = _cuda_f32(weights[0], "w1")
     b1 = _cuda_f32(biases[0], "b1") if biases[0] is not None else None
     c1 = w1.shape[1]
