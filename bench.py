@@ -117,7 +117,7 @@ def make_problem(n_clips: int, seed: int, device, head_gain: float):
 # our arm
 # ------------------------------------------------------------------------------------------------
 class HotPath:
-    LAUNCHES_FWD = 3 + 1 + 2 + 1 + 1  # head(2 deconvs + softmax), decode, target+mse (2), remap, unsup
+    LAUNCHES_FWD = 4 + 1 + 2 + 1 + 1  # head(2 weight packs + k1a + k1b), decode, target+mse (2), remap, unsup
 
     def __init__(self, prob, device, fwd_only: bool):
         from lightning_pose_b200 import ops
@@ -359,7 +359,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=16, help="clips per step per GPU (48 frames each)")
     ap.add_argument("--head-gain", type=float, default=5.0, help="xavier gain of the synthetic head weights (5 = trained-like peaks ~0.2)")
-    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="feature dtype (bf16 = tcgen05 head)")
+    ap.add_argument("--dtype", default="bf16", choices=["f32", "bf16"], help="feature dtype (bf16 = tcgen05 head)")
     ap.add_argument("--no-flat", action="store_true", help="skip the secondary flat-heatmap (fresh-init) regime")
     ap.add_argument("--fwd-only", action="store_true", default=True)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -69,15 +69,42 @@ __device__ float eval_point(const float* tile, int pitch, int padl, const float*
   return acc;
 }
 
+// one coarse row of the vertical pass: F fine values from the W-row window `t`
+template <int DS>
+__device__ __forceinline__ void column_pass(const DecodeParams<DS>& P, int a, int h, const float* t, float* v) {
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  if (a >= R && a <= h - 1 - R) {  // interior: phase-periodic weights are constant-bank operands
+#pragma unroll
+    for (int p = 0; p < F; ++p) {
+      float r = 0.f;
+#pragma unroll
+      for (int k = 0; k < W; ++k) r = fmaf(P.phase[p][k], t[k], r);
+      v[p] = r;
+    }
+  } else {  // border rows: per-row table (edge-clamped bicubic taps, zero-padded blur)
+    const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
+#pragma unroll
+    for (int p = 0; p < F; ++p) {
+      float r = 0.f;
+#pragma unroll
+      for (int k = 0; k < W; ++k) r = fmaf(__ldg(tr + p * W + k), t[k], r);
+      v[p] = r;
+    }
+  }
+}
+
 template <int DS>
 __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_constant__ DecodeParams<DS> P) {
   constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  constexpr int CPS = 32 / F;  // coarse columns per 32-fine-column strip
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int h = P.h, w = P.w, pitch = P.pitch, padl = P.padl;
   float* tile = reinterpret_cast<float*>(smem_raw);  // (h + 2R) x pitch; logical (a,b) at [(a+R)*pitch + padl + b]
   float* red = tile + (h + 2 * R) * pitch;           // 64 floats of reduction scratch
-  int* redi = reinterpret_cast<int*>(red + 64);      // 48 ints
-  uint64_t* bar = reinterpret_cast<uint64_t*>(redi + 48);
+  int* redi = reinterpret_cast<int*>(red + 64);      // 112 ints
+  uint64_t* bar = reinterpret_cast<uint64_t*>(redi + 112);
+  int* srmin = redi + 48;  // [32] per-strip first candidate row
+  int* srmax = redi + 80;  // [32] per-strip last candidate row
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t plane = blockIdx.x;
   const float* __restrict__ src = P.heat + plane * (size_t)h * w;
@@ -96,6 +123,10 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
         bulk_g2s(tile + (a + R) * pitch + padl, src + (size_t)a * w, (uint32_t)(w * 4), bar);
     }
   }
+  if (tid < 32) {
+    srmin[tid] = 0x7fffffff;
+    srmax[tid] = -1;
+  }
   for (int r = warp; r < h + 2 * R; r += DEC_WARPS) {
     float* row = tile + r * pitch;
     if (r < R || r >= h + R) {
@@ -112,48 +143,54 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
   if (P.bulk) mbar_wait(bar, 0);
   __syncthreads();
 
-  // ---- scan 1: coarse arg max of |h| ------------------------------------------------------------
+  // ---- scan 1: arg max of |h|; each warp owns a band of rows, lanes read 4-column groups ------------
+  // (rows of the padded tile are 16-byte aligned and followed by >= R zero columns, so the last,
+  //  possibly partial, group is safe to read)
+  const int w4 = (w + 3) >> 2;
+  const int band = (h + DEC_WARPS - 1) / DEC_WARPS;
+  const int ab0 = warp * band, ab1 = min(h, ab0 + band);
   float best = -1.f;
-  int besta = 0, bestb = 0;
-  for (int a = warp; a < h; a += DEC_WARPS) {
-    const float* row = tile + (a + R) * pitch + padl;
-    for (int b = lane; b < w; b += 32) {
-      const float v = fabsf(row[b]);
-      if (v > best) {
-        best = v;
-        besta = a;
-        bestb = b;
+  int bpos = 0;
+  for (int a = ab0; a < ab1; ++a) {
+    const float4* row4 = reinterpret_cast<const float4*>(tile + (a + R) * pitch + padl);
+    for (int b4 = lane; b4 < w4; b4 += 32) {
+      const float4 x = row4[b4];
+      const float m4 = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
+      if (m4 > best) {
+        best = m4;
+        bpos = (a << 16) | b4;
       }
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oa = __shfl_xor_sync(0xffffffffu, besta, o);
-    const int obb = __shfl_xor_sync(0xffffffffu, bestb, o);
+    const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
     if (ob > best) {
       best = ob;
-      besta = oa;
-      bestb = obb;
+      bpos = op;
     }
   }
+  const float bandmax = best;  // warp-uniform: max |h| over this warp's band
   if (lane == 0) {
     red[warp] = best;
-    redi[2 * warp] = besta;
-    redi[2 * warp + 1] = bestb;
+    redi[warp] = bpos;
   }
   __syncthreads();
-  {
-    best = red[0];
-    besta = redi[0];
-    bestb = redi[1];
+  best = red[0];
+  bpos = redi[0];
 #pragma unroll
-    for (int k = 1; k < DEC_WARPS; ++k)
-      if (red[k] > best) {
-        best = red[k];
-        besta = redi[2 * k];
-        bestb = redi[2 * k + 1];
-      }
+  for (int k = 1; k < DEC_WARPS; ++k)
+    if (red[k] > best) {
+      best = red[k];
+      bpos = redi[k];
+    }
+  const int besta = bpos >> 16;
+  int bestb = (bpos & 0xffff) * 4;
+  {
+    const float* g4 = tile + (besta + R) * pitch + padl + bestb;
+    bestb += (fabsf(g4[0]) == best) ? 0 : ((fabsf(g4[1]) == best) ? 1 : ((fabsf(g4[2]) == best) ? 2 : 3));
+    bestb = min(bestb, w - 1);
   }
 
   // ---- lower bound on the field maximum: exact values in the F x F block of the coarse arg max --
@@ -166,29 +203,49 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
 #pragma unroll
   for (int k = 1; k < DEC_WARPS; ++k) mlb = fmaxf(mlb, red[8 + k]);
 
-  // ---- scan 2: bounding box of coarse pixels that can reach (mlb - CUT/T) ------------------------
+  // ---- scan 2: candidates (|h| >= theta) -> per-strip candidate row range + hull ---------------------
+  // a fine pixel can carry weight > exp(-CUT) only if a candidate lies within R coarse samples of it
   const float theta = (P.T > 0.f) ? (mlb - DEC_CUT / P.T) / P.lip : -1.f;
+  const int nstrips = (w * F + 31) >> 5;  // <= 32 (checked on the host)
   int amin = h, amax = -1, bmin = w, bmax = -1;
-  for (int a = warp; a < h; a += DEC_WARPS) {
-    const float* row = tile + (a + R) * pitch + padl;
-    bool any = false;
-    for (int b = lane; b < w; b += 32) {
-      if (fabsf(row[b]) >= theta) {
-        any = true;
-        bmin = min(bmin, b);
-        bmax = max(bmax, b);
+  if (bandmax >= theta) {
+    int rmin = 0x7fffffff, rmax = -1;  // lane s owns strip s
+    const int nit = (w4 + 31) >> 5;
+    unsigned long long gmask = 0;  // 4-column groups that can reach strip `lane`
+    if (lane < nstrips) {
+      const int cs0 = lane * CPS;
+      const int glo = max(cs0 - R, 0) >> 2, ghi = min(cs0 + CPS - 1 + R, w - 1) >> 2;
+      gmask = ((2ull << (ghi - glo)) - 1ull) << glo;
+    }
+    for (int a = ab0; a < ab1; ++a) {
+      const float4* row4 = reinterpret_cast<const float4*>(tile + (a + R) * pitch + padl);
+      unsigned long long cm = 0;
+      for (int it = 0; it < nit; ++it) {  // w4 <= 64: at most two ballots per row
+        const int b4 = lane + 32 * it;
+        bool c = false;
+        if (b4 < w4) {
+          const float4 x = row4[b4];
+          c = (fabsf(x.x) >= theta) || (fabsf(x.y) >= theta) || (fabsf(x.z) >= theta) || (fabsf(x.w) >= theta);
+        }
+        cm |= (unsigned long long)__ballot_sync(0xffffffffu, c) << (32 * it);
+      }
+      if (cm) {
+        amin = min(amin, a);
+        amax = max(amax, a);
+        bmin = min(bmin, 4 * (__ffsll((long long)cm) - 1));
+        bmax = max(bmax, min(4 * (63 - __clzll((long long)cm)) + 3, w - 1));
+        if (cm & gmask) {
+          rmin = min(rmin, a);
+          rmax = max(rmax, a);
+        }
       }
     }
-    if (any) {
-      amin = min(amin, a);
-      amax = max(amax, a);
+    if (rmax >= 0) {
+      atomicMin(&srmin[lane], rmin);
+      atomicMax(&srmax[lane], rmax);
     }
   }
-  amin = warp_min_i(amin);
-  amax = warp_max_i(amax);
-  bmin = warp_min_i(bmin);
-  bmax = warp_max_i(bmax);
-  if (lane == 0) {
+  if (lane == 0) {  // amin..bmax are warp-uniform (derived from ballots)
     redi[16 + 4 * warp + 0] = amin;
     redi[16 + 4 * warp + 1] = amax;
     redi[16 + 4 * warp + 2] = bmin;
@@ -202,117 +259,133 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
     bmin = min(bmin, redi[16 + 4 * k + 2]);
     bmax = max(bmax, redi[16 + 4 * k + 3]);
   }
+  int my_rmin = (lane < nstrips) ? srmin[lane] : 0x7fffffff;
+  int my_rmax = (lane < nstrips) ? srmax[lane] : -1;
   if (amax < 0) {  // only reachable with NaN input: evaluate everything
     amin = 0;
     amax = h - 1;
     bmin = 0;
     bmax = w - 1;
+    if (lane < nstrips) {
+      my_rmin = 0;
+      my_rmax = h - 1;
+    }
   }
   const int A0 = max(amin - R, 0), A1 = min(amax + R, h - 1);
   const int B0 = max(bmin - R, 0), B1 = min(bmax + R, w - 1);
 
-  // ---- work items: 32-fine-column strips x row groups, round-robin over the 8 warps --------------
-  const int J0 = B0 * F, J1 = (B1 + 1) * F;
-  const int nstrips = (J1 - J0 + 31) >> 5;
-  const int nrows = A1 - A0 + 1;
-  int G = 1, seg = nrows;
-  {
-    int bestcost = 0x7fffffff;
-    for (int g = 1; g <= 8; ++g) {
-      const int sg = (nrows + g - 1) / g;
-      const int cost = ((nstrips * g + DEC_WARPS - 1) / DEC_WARPS) * (sg + 2 * R);
-      if (cost < bestcost) {
-        bestcost = cost;
-        G = g;
-        seg = sg;
-      }
-    }
+  // ---- work items: (strip, row segment); lane s describes strip s, items are dealt round-robin ------
+  const bool sact = my_rmax >= 0;
+  const int sr0 = max(my_rmin - R, 0), sr1 = min(my_rmax + R, h - 1) + 1;  // [sr0, sr1)
+  const int nseg = sact ? ((sr1 - sr0) > 40 ? 2 : 1) : 0;
+  int istart = nseg;  // exclusive prefix sum over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, istart, o);
+    if (lane >= o) istart += t;
   }
-  const int nitems = nstrips * G;
+  const int nitems = __shfl_sync(0xffffffffu, istart, 31);
+  istart -= nseg;
+
   const float c = P.T * 1.4426950408889634f;
-  float m = mlb, s = 0.f, sx = 0.f, sy = 0.f;
+  float M = mlb, S = 0.f, SX = 0.f, SY = 0.f;
 
   for (int item = warp; item < nitems; item += DEC_WARPS) {
-    const int sidx = item % nstrips, g = item / nstrips;
-    const int r0 = A0 + g * seg, r1 = min(r0 + seg, A1 + 1);
+    const unsigned own = __ballot_sync(0xffffffffu, item >= istart && item < istart + nseg);
+    const int sl = __ffs(own) - 1;  // strip index
+    const int q0 = __shfl_sync(0xffffffffu, sr0, sl), q1 = __shfl_sync(0xffffffffu, sr1, sl);
+    const int qs = __shfl_sync(0xffffffffu, istart, sl), qn = __shfl_sync(0xffffffffu, nseg, sl);
+    const int half = (q1 - q0 + qn - 1) / qn;
+    const int r0 = q0 + (item - qs) * half, r1 = min(r0 + half, q1);
     if (r0 >= r1) continue;
-    const int jf = J0 + sidx * 32 + lane;
-    const bool ok = jf < J1;
-    const int jc = ok ? jf : (J1 - 1);
+    const int jf = sl * 32 + lane;
+    const bool ok = jf < w * F;
+    const int jc = ok ? jf : (w * F - 1);
     float wc[W];
 #pragma unroll
     for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
     const float* colbase = tile + padl + (jc / F - R);  // add (a + R) * pitch for coarse row a
-    float tmp[W];
+    float tmp[W + 1];  // rows a-R .. a+R+1: two coarse rows are produced per iteration
 #pragma unroll
     for (int t = 0; t < W; ++t) tmp[t] = dot_w<W>(colbase + (r0 + t) * pitch, wc);  // rows r0-R .. r0+R
-    const float xf = (float)jf;
-    for (int a = r0; a < r1; ++a) {
+    float m = M, mc = M * c, s_it = 0.f, sy_it = 0.f;
+    const float kill = ok ? 0.f : -3.0e38f;
+
+    auto accumulate = [&](const float* v, float yrow) {
+      float vm = v[0];
+#pragma unroll
+      for (int p = 1; p < F; ++p) vm = fmaxf(vm, v[p]);
+      vm += kill;
+      if (__any_sync(0xffffffffu, vm > m)) {
+        const float mn = fmaxf(m, vm);
+        const float sc = fast_exp2((m - mn) * c);
+        s_it *= sc;
+        sy_it *= sc;
+        m = mn;
+        mc = mn * c;
+      }
+      float rs = 0.f, pw = 0.f;
+#pragma unroll
+      for (int p = 0; p < F; ++p) {
+        const float e = fast_exp2(fmaf(v[p], c, -mc) + kill);
+        rs += e;
+        if (p > 0) pw = fmaf(e, (float)p, pw);
+      }
+      s_it += rs;
+      sy_it = fmaf(yrow, rs, sy_it) + pw;
+    };
+
+    int a = r0;
+    float yrow = (float)(r0 * F);
+    for (; a + 1 < r1; a += 2, yrow += (float)(2 * F)) {
+      tmp[W] = dot_w<W>(colbase + (a + 1 + 2 * R) * pitch, wc);  // coarse row a+1+R
       float v[F];
-      if (a >= R && a <= h - 1 - R) {
+      column_pass<DS>(P, a, h, tmp, v);
+      accumulate(v, yrow);
+      column_pass<DS>(P, a + 1, h, tmp + 1, v);
+      accumulate(v, yrow + (float)F);
+      if (a + 2 < r1) {
 #pragma unroll
-        for (int p = 0; p < F; ++p) {
-          float r = 0.f;
-#pragma unroll
-          for (int t = 0; t < W; ++t) r = fmaf(P.phase[p][t], tmp[t], r);
-          v[p] = r;
-        }
-      } else {
-        const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
-#pragma unroll
-        for (int p = 0; p < F; ++p) {
-          float r = 0.f;
-#pragma unroll
-          for (int t = 0; t < W; ++t) r = fmaf(__ldg(tr + p * W + t), tmp[t], r);
-          v[p] = r;
-        }
+        for (int t = 0; t < W - 1; ++t) tmp[t] = tmp[t + 2];
+        tmp[W - 1] = dot_w<W>(colbase + (a + 2 + 2 * R) * pitch, wc);  // coarse row a+2+R
       }
-      if (ok) {
-        float vm = v[0];
-#pragma unroll
-        for (int p = 1; p < F; ++p) vm = fmaxf(vm, v[p]);
-        if (vm > m) {
-          const float sc = fast_exp2((m - vm) * c);
-          s *= sc;
-          sx *= sc;
-          sy *= sc;
-          m = vm;
-        }
-#pragma unroll
-        for (int p = 0; p < F; ++p) {
-          const float wgt = fast_exp2((v[p] - m) * c);
-          s += wgt;
-          sx = fmaf(wgt, xf, sx);
-          sy = fmaf(wgt, (float)(a * F + p), sy);
-        }
-      }
-      if (a + 1 < r1) {
-#pragma unroll
-        for (int t = 0; t < W - 1; ++t) tmp[t] = tmp[t + 1];
-        tmp[W - 1] = dot_w<W>(colbase + (a + 1 + 2 * R) * pitch, wc);  // coarse row a+1+R
-      }
+    }
+    if (a < r1) {
+      float v[F];
+      column_pass<DS>(P, a, h, tmp, v);
+      accumulate(v, yrow);
+    }
+    {  // fold the item into the lane's running state
+      const float Mn = fmaxf(M, m);
+      const float a1 = fast_exp2((M - Mn) * c), a2 = fast_exp2((m - Mn) * c);
+      S = fmaf(s_it, a2, S * a1);
+      SX = fmaf((float)jf * s_it, a2, SX * a1);
+      SY = fmaf(sy_it, a2, SY * a1);
+      M = Mn;
     }
   }
 
   // ---- merge the per-lane online-softmax states ----------------------------------------------------
   {
-    const float M = warp_max(m);
-    const float sc = fast_exp2((m - M) * c);
-    s = warp_sum(s * sc);
-    sx = warp_sum(sx * sc);
-    sy = warp_sum(sy * sc);
+    const float Mw = warp_max(M);
+    const float sc = fast_exp2((M - Mw) * c);
+    S = warp_sum(S * sc);
+    SX = warp_sum(SX * sc);
+    SY = warp_sum(SY * sc);
     if (lane == 0) {
-      red[16 + 4 * warp + 0] = M;
-      red[16 + 4 * warp + 1] = s;
-      red[16 + 4 * warp + 2] = sx;
-      red[16 + 4 * warp + 3] = sy;
+      red[16 + 4 * warp + 0] = Mw;
+      red[16 + 4 * warp + 1] = S;
+      red[16 + 4 * warp + 2] = SX;
+      red[16 + 4 * warp + 3] = SY;
     }
   }
   __syncthreads();
-  float M = red[16];
+  M = red[16];
 #pragma unroll
   for (int k = 1; k < DEC_WARPS; ++k) M = fmaxf(M, red[16 + 4 * k]);
-  float S = 0.f, SX = 0.f, SY = 0.f;
+  S = 0.f;
+  SX = 0.f;
+  SY = 0.f;
 #pragma unroll
   for (int k = 0; k < DEC_WARPS; ++k) {
     const float sc = fast_exp2((red[16 + 4 * k] - M) * c);
@@ -562,7 +635,7 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
   P.offset = (DS == 1) ? 0.5f : (DS == 2 ? 1.5f : 2.5f);  // lightning_pose/models/heads/heatmap.py:131-136
   for (int p = 0; p < G::F; ++p)
     for (int t = 0; t < G::W; ++t) P.phase[p][t] = th->host.phase[(size_t)p * G::W + t];
-  const size_t smem = ((size_t)(h + 2 * G::R) * P.pitch + 64 + 48) * sizeof(float) + 16;
+  const size_t smem = ((size_t)(h + 2 * G::R) * P.pitch + 64 + 112) * sizeof(float) + 16;
   int dev = 0, max_smem = 0;
   LPB_CUDA(cudaGetDevice(&dev));
   LPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -627,6 +700,10 @@ extern "C" int lpb_decode_fwd(const float* heatmaps, int64_t n_planes, int h, in
   LPB_REQUIRE(heatmaps && xy && conf, "decode_fwd: null pointer");
   LPB_REQUIRE(h >= 1 && w >= 1 && ds >= 1 && ds <= 3, "decode_fwd: bad shape h=%d w=%d ds=%d", h, w, ds);
   LPB_REQUIRE(n_planes >= 0 && n_planes < (1ll << 31), "decode_fwd: bad n_planes");
+  if (((int64_t)w << ds) > 1024 || w > 256) {
+    lpb::set_error("decode_fwd: heatmap width %d (x%d) exceeds this build's 1024-column field limit", w, 1 << ds);
+    return LPB_ERR_UNSUPPORTED;
+  }
   if (n_planes == 0) return LPB_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (ds) {

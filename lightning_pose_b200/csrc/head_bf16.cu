@@ -90,7 +90,6 @@ struct K1aParams {
   int B, C, HW, W;            // feature geometry (C = 4 * Cin)
   int c1, nstages;
   HeadGeom g;
-  int desc_swap;              // debug: swap LBO/SBO in the descriptors
 };
 
 __global__ void __launch_bounds__(HB_THREADS, 1) k1a_shuffle_convt_kernel(const __grid_constant__ K1aParams P) {
@@ -207,8 +206,8 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k1a_shuffle_convt_kernel(const 
               for (int k16 = 0; k16 < 2; ++k16) {
                 const uint32_t aa = a0 + (2 * k16) * lbo_a + (t * 128 + shift_rows) * 16;
                 const uint32_t bb = b0 + (sh * 4 + 2 * k16) * lbo_b;
-                const uint64_t ad = P.desc_swap ? tc::make_smem_desc(aa, 128, lbo_a) : tc::make_smem_desc(aa, lbo_a, 128);
-                const uint64_t bd = P.desc_swap ? tc::make_smem_desc(bb, 128, lbo_b) : tc::make_smem_desc(bb, lbo_b, 128);
+                const uint64_t ad = tc::make_smem_desc(aa, lbo_a, 128);
+                const uint64_t bd = tc::make_smem_desc(bb, lbo_b, 128);
                 tc::umma_bf16(tmem_base + t * HB_NCOLS, ad, bd, idesc, (st | sh | k16) != 0 ? 1u : 0u);
               }
             }
@@ -281,7 +280,6 @@ struct K1bParams {
   float* out;                // [B][c2][2Hi][2Wi]
   int B, c2, final_softmax;
   HeadGeom g;
-  int desc_swap;
 };
 
 constexpr int K1B_TPB = 3;  // M-tiles per TMEM buffer (3 * 80 = 240 columns; two buffers at 0 and 256)
@@ -371,8 +369,8 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k1b_convt_softmax_kernel(const 
                 for (int k16 = 0; k16 < 2; ++k16) {
                   const uint32_t aa = a0 + (2 * k16) * lbo_a + (t * 128 + shift_rows) * 16;
                   const uint32_t bb = b0 + (sh * 4 + 2 * k16) * lbo_b;
-                  const uint64_t ad = P.desc_swap ? tc::make_smem_desc(aa, 128, lbo_a) : tc::make_smem_desc(aa, lbo_a, 128);
-                  const uint64_t bd = P.desc_swap ? tc::make_smem_desc(bb, 128, lbo_b) : tc::make_smem_desc(bb, lbo_b, 128);
+                  const uint64_t ad = tc::make_smem_desc(aa, lbo_a, 128);
+                  const uint64_t bd = tc::make_smem_desc(bb, lbo_b, 128);
                   tc::umma_bf16(tmem_base + buf * 256 + tt * HB_NCOLS, ad, bd, idesc, (sh | k16) != 0 ? 1u : 0u);
                 }
               }
@@ -526,11 +524,6 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   __nv_bfloat16* mid = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES);
   pack_convt_weights_kernel<<<64, 256, 0, s>>>(w1, C / 4, c1, nst, wp1);
   pack_convt_weights_kernel<<<8, 256, 0, s>>>(w2, c1, c2, 1, wp2);
-  static int desc_swap = -1;
-  if (desc_swap < 0) {
-    const char* e = getenv("LPB_DESC_SWAP");
-    desc_swap = (e && e[0] == '1') ? 1 : 0;
-  }
   K1aParams pa;
   pa.feat = static_cast<const __nv_bfloat16*>(features);
   pa.wpk = wp1;
@@ -543,7 +536,6 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   pa.c1 = c1;
   pa.nstages = nst;
   pa.g = g1;
-  pa.desc_swap = desc_swap;
   LPB_CUDA(cudaFuncSetAttribute(k1a_shuffle_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
   k1a_shuffle_convt_kernel<<<B < sms ? B : sms, HB_THREADS, s1, s>>>(pa);
   K1bParams pb;
@@ -555,7 +547,6 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   pb.c2 = c2;
   pb.final_softmax = final_softmax;
   pb.g = g2;
-  pb.desc_swap = desc_swap;
   LPB_CUDA(cudaFuncSetAttribute(k1b_convt_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   k1b_convt_softmax_kernel<<<B < sms ? B : sms, HB_THREADS, s2, s>>>(pb);
   LPB_CUDA(cudaGetLastError());

@@ -387,3 +387,56 @@ def test_tracker_semisupervised_step_vs_oracle(lpb, dev):
     close(kp, kp_ref, atol=2e-3, rtol=RTOL)
     close(cf, cf_ref, atol=1e-5)
     close(tot, 0.5 * loss_ref, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 tensor-core head (tcgen05): north_star tolerance 1e-2 against the oracle on bf16-rounded tensors
+# ------------------------------------------------------------------------------------------------
+def _bf16_head_oracle(feats_bf16, head):
+    import torch.nn.functional as F
+
+    r = lambda t: t.detach().bfloat16().float()
+    d1, d2 = list(head.upsampling_layers)[1:]
+    x = F.pixel_shuffle(feats_bf16.float(), 2)
+    mid = F.conv_transpose2d(x, r(d1.weight), d1.bias.detach(), stride=2, padding=1, output_padding=1)
+    logits = F.conv_transpose2d(r(mid), r(d2.weight), d2.bias.detach(), stride=2, padding=1, output_padding=1)
+    return logits, O.spatial_softmax2d(logits, 1.0)
+
+
+@pytest.mark.parametrize("shape", [(5, 2048, 12, 12), (3, 512, 8, 8), (2, 1024, 4, 6)])
+def test_head_bf16_tcgen05_vs_oracle(lpb, dev, shape):
+    from lightning_pose_b200.models.heads.heatmap import HeatmapHead
+
+    b, c, fh, fw = shape
+    torch.manual_seed(13)
+    head = HeatmapHead("resnet50", c, 17)
+    for layer in list(head.upsampling_layers)[1:]:
+        torch.nn.init.xavier_uniform_(layer.weight, gain=3.0)
+        torch.nn.init.uniform_(layer.bias, -0.3, 0.3)
+    feats = (torch.randn(b, c, fh, fw) * 0.5).bfloat16()
+    logits_ref, hm_ref = _bf16_head_oracle(feats, head)
+    head = head.to(dev)
+    out = head(feats.to(dev))
+    assert out.dtype == torch.float32 and out.shape == hm_ref.shape
+    close(out, hm_ref, atol=1e-7, rtol=1e-2)
+    close(out.sum((2, 3)), torch.ones(b, 17), atol=1e-5)
+    head.final_softmax = False
+    close(head(feats.to(dev)), logits_ref, atol=1e-2 * float(logits_ref.abs().max()), rtol=1e-2)
+    # decode of the bf16-path heatmaps agrees with the decode of the oracle heatmaps to sub-pixel level
+    kp, cf = lpb.decode_softargmax(out, 2, 1000.0)
+    kp_ref, cf_ref = O.decode_softargmax(hm_ref, 2, 1000.0)
+    conf_ok = cf_ref > 0.5
+    assert float(((kp.cpu() - kp_ref).abs().reshape(b, 17, 2).amax(-1))[conf_ok].max()) < 0.5
+
+
+def test_decode_multimodal_random_fields(lpb, dev):
+    """Random spiky planes (several comparable peaks scattered over the plane) exercise the per-strip
+    candidate row ranges; widths beyond the 1024-column field limit are rejected loudly."""
+    gen = torch.Generator().manual_seed(21)
+    hm = torch.softmax(torch.randn(3, 4, 96 * 96, generator=gen) * 4.0, -1).reshape(3, 4, 96, 96)
+    po, co = O.decode_softargmax(hm, 2, 1000.0)
+    p, c = lpb.decode_softargmax(hm.to(dev), 2, 1000.0)
+    close(p, po, atol=2e-4)
+    close(c, co, atol=2e-6)
+    with pytest.raises(RuntimeError, match="field limit"):
+        lpb.decode_softargmax(torch.rand(1, 1, 4, 300, device=dev), 2, 1000.0)
