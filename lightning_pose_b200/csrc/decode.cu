@@ -103,8 +103,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
   float* red = tile + (h + 2 * R) * pitch;           // 64 floats of reduction scratch
   int* redi = reinterpret_cast<int*>(red + 64);      // 112 ints
   uint64_t* bar = reinterpret_cast<uint64_t*>(redi + 112);
-  int* srmin = redi + 48;  // [32] per-strip first candidate row
-  int* srmax = redi + 80;  // [32] per-strip last candidate row
+  unsigned* smask = reinterpret_cast<unsigned*>(redi + 48);  // [32] per-strip bitmask of active row chunks
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t plane = blockIdx.x;
   const float* __restrict__ src = P.heat + plane * (size_t)h * w;
@@ -123,10 +122,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
         bulk_g2s(tile + (a + R) * pitch + padl, src + (size_t)a * w, (uint32_t)(w * 4), bar);
     }
   }
-  if (tid < 32) {
-    srmin[tid] = 0x7fffffff;
-    srmax[tid] = -1;
-  }
+  if (tid < 32) smask[tid] = 0u;
   for (int r = warp; r < h + 2 * R; r += DEC_WARPS) {
     float* row = tile + r * pitch;
     if (r < R || r >= h + R) {
@@ -208,8 +204,9 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
   const float theta = (P.T > 0.f) ? (mlb - DEC_CUT / P.T) / P.lip : -1.f;
   const int nstrips = (w * F + 31) >> 5;  // <= 32 (checked on the host)
   int amin = h, amax = -1, bmin = w, bmax = -1;
+  const int CH = max(4, (h + 31) >> 5);  // coarse rows per chunk (<= 32 chunks per plane)
   if (bandmax >= theta) {
-    int rmin = 0x7fffffff, rmax = -1;  // lane s owns strip s
+    unsigned cmask = 0u;  // lane s owns strip s: chunks whose rows lie within R of a candidate
     const int nit = (w4 + 31) >> 5;
     unsigned long long gmask = 0;  // 4-column groups that can reach strip `lane`
     if (lane < nstrips) {
@@ -235,15 +232,12 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
         bmin = min(bmin, 4 * (__ffsll((long long)cm) - 1));
         bmax = max(bmax, min(4 * (63 - __clzll((long long)cm)) + 3, w - 1));
         if (cm & gmask) {
-          rmin = min(rmin, a);
-          rmax = max(rmax, a);
+          const int c0 = max(a - R, 0) / CH, c1 = min(a + R, h - 1) / CH;
+          cmask |= ((2u << (c1 - c0)) - 1u) << c0;
         }
       }
     }
-    if (rmax >= 0) {
-      atomicMin(&srmin[lane], rmin);
-      atomicMax(&srmax[lane], rmax);
-    }
+    if (cmask) atomicOr(&smask[lane], cmask);
   }
   if (lane == 0) {  // amin..bmax are warp-uniform (derived from ballots)
     redi[16 + 4 * warp + 0] = amin;
@@ -259,44 +253,65 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
     bmin = min(bmin, redi[16 + 4 * k + 2]);
     bmax = max(bmax, redi[16 + 4 * k + 3]);
   }
-  int my_rmin = (lane < nstrips) ? srmin[lane] : 0x7fffffff;
-  int my_rmax = (lane < nstrips) ? srmax[lane] : -1;
+  unsigned my_mask = (lane < nstrips) ? smask[lane] : 0u;
   if (amax < 0) {  // only reachable with NaN input: evaluate everything
     amin = 0;
     amax = h - 1;
     bmin = 0;
     bmax = w - 1;
-    if (lane < nstrips) {
-      my_rmin = 0;
-      my_rmax = h - 1;
-    }
+    if (lane < nstrips) my_mask = 0xffffffffu >> (32 - (h + CH - 1) / CH);
   }
   const int A0 = max(amin - R, 0), A1 = min(amax + R, h - 1);
   const int B0 = max(bmin - R, 0), B1 = min(bmax + R, w - 1);
 
-  // ---- work items: (strip, row segment); lane s describes strip s, items are dealt round-robin ------
-  const bool sact = my_rmax >= 0;
-  const int sr0 = max(my_rmin - R, 0), sr1 = min(my_rmax + R, h - 1) + 1;  // [sr0, sr1)
-  const int nseg = sact ? ((sr1 - sr0) > 40 ? 2 : 1) : 0;
-  int istart = nseg;  // exclusive prefix sum over lanes
+  // ---- work items: lane s describes strip s; one item per run of active chunks (long runs split in two)
+  auto next_run = [&](unsigned& m, int& q0, int& q1) {  // pops the lowest run of set bits -> rows [q0, q1)
+    const int st = __ffs(m) - 1;
+    const unsigned sh = m >> st;
+    const int len = __ffs(~sh) - 1;  // sh has a zero bit unless all 32 chunks are active
+    q0 = st * CH;
+    q1 = min((st + (len < 0 ? 32 - st : len)) * CH, h);
+    m = (len < 0 || st + len >= 32) ? 0u : (m & ~(((1u << len) - 1u) << st));
+  };
+  int nmine = 0;
+  {
+    unsigned m = my_mask;
+    while (m) {
+      int q0, q1;
+      next_run(m, q0, q1);
+      nmine += (q1 - q0 > 48) ? 2 : 1;
+    }
+  }
+  int istart = nmine;  // exclusive prefix sum over lanes
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int t = __shfl_up_sync(0xffffffffu, istart, o);
     if (lane >= o) istart += t;
   }
   const int nitems = __shfl_sync(0xffffffffu, istart, 31);
-  istart -= nseg;
+  istart -= nmine;
 
   const float c = P.T * 1.4426950408889634f;
   float M = mlb, S = 0.f, SX = 0.f, SY = 0.f;
 
   for (int item = warp; item < nitems; item += DEC_WARPS) {
-    const unsigned own = __ballot_sync(0xffffffffu, item >= istart && item < istart + nseg);
+    const unsigned own = __ballot_sync(0xffffffffu, item >= istart && item < istart + nmine);
     const int sl = __ffs(own) - 1;  // strip index
-    const int q0 = __shfl_sync(0xffffffffu, sr0, sl), q1 = __shfl_sync(0xffffffffu, sr1, sl);
-    const int qs = __shfl_sync(0xffffffffu, istart, sl), qn = __shfl_sync(0xffffffffu, nseg, sl);
-    const int half = (q1 - q0 + qn - 1) / qn;
-    const int r0 = q0 + (item - qs) * half, r1 = min(r0 + half, q1);
+    unsigned rm = __shfl_sync(0xffffffffu, my_mask, sl);
+    int k = item - __shfl_sync(0xffffffffu, istart, sl);
+    int r0 = 0, r1 = 0;
+    while (rm) {
+      int q0, q1;
+      next_run(rm, q0, q1);
+      const int ns = (q1 - q0 > 48) ? 2 : 1;
+      if (k < ns) {
+        const int seglen = (q1 - q0 + ns - 1) / ns;
+        r0 = q0 + k * seglen;
+        r1 = min(r0 + seglen, q1);
+        break;
+      }
+      k -= ns;
+    }
     if (r0 >= r1) continue;
     const int jf = sl * 32 + lane;
     const bool ok = jf < w * F;

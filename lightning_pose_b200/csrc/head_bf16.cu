@@ -27,12 +27,10 @@
 
 namespace lpb {
 
-constexpr int HB_THREADS = 288;      // warps 0-3 producer, warp 4 MMA issuer, warps 5-8 epilogue
 constexpr int HB_NCOLS = 80;         // 4 classes x 20 (>= 17 keypoints), multiple of 16
 constexpr int HB_CLS = 20;
 constexpr int HB_KSTAGE = 32;        // channels per pipeline stage (4 K-chunks of 8)
 constexpr int HB_BSTAGE_BYTES = 4 * 4 * HB_NCOLS * 16;  // [shift][kchunk][80 rows][16 B]
-constexpr int HB_STAGES = 3;
 
 struct HeadGeom {
   int Hi, Wi;       // conv input spatial size (after PixelShuffle for layer 1)
@@ -54,8 +52,11 @@ __host__ inline HeadGeom make_geom(int Hi, int Wi) {
 }
 
 // ---- weight packing: W[Cin][Cout][3][3] (fp32) -> B[stage][shift][kchunk][80][8] bf16 -----------------
-__global__ void pack_convt_weights_kernel(const float* __restrict__ w, int Cin, int Cout, int nstages,
-                                          __nv_bfloat16* __restrict__ out) {
+// bias != nullptr: input channel `Cin` is the constant-one channel and carries the bias (shift (0,0) only,
+// which every output class uses exactly once).  zero/nzero: optional buffer to clear in the same launch.
+__global__ void pack_convt_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias, int Cin, int Cout,
+                                          int nstages, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ zero,
+                                          int nzero) {
   const int total = nstages * 4 * 4 * HB_NCOLS * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 7;
@@ -74,14 +75,22 @@ __global__ void pack_convt_weights_kernel(const float* __restrict__ w, int Cin, 
       const int ky = py == 0 ? 1 : (dm ? 0 : 2);
       const int kx = px == 0 ? 1 : (dn ? 0 : 2);
       v = w[((size_t)c * Cout + o) * 9 + ky * 3 + kx];
+    } else if (bias && c == Cin && o < Cout && sh == 0) {
+      v = bias[o];
     }
     out[i] = __float2bfloat16_rn(v);
   }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x) zero[i] = __float2bfloat16_rn(0.f);
 }
 
 // =====================================================================================================
 // k1a: PixelShuffle + first transposed convolution
 // =====================================================================================================
+// warps 0-3 transposers, warp 4 MMA issuer (+TMEM owner), warps 5-8 epilogue, warp 9 TMA loader
+constexpr int K1A_THREADS = 320;
+constexpr int K1A_ASTAGES = 2;  // K-major operand stages (A + packed weights)
+constexpr int K1A_RSTAGES = 2;  // raw NCHW stages filled by the TMA engine
+
 struct K1aParams {
   const __nv_bfloat16* feat;  // [B][C][H*W]
   const __nv_bfloat16* wpk;   // packed weights [nstages][HB_BSTAGE_BYTES]
@@ -92,27 +101,33 @@ struct K1aParams {
   HeadGeom g;
 };
 
-__global__ void __launch_bounds__(HB_THREADS, 1) k1a_shuffle_convt_kernel(const __grid_constant__ K1aParams P) {
+__global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const __grid_constant__ K1aParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const HeadGeom g = P.g;
   const int a_stage_bytes = 4 * g.rows_alloc * 16;
   const int stage_bytes = a_stage_bytes + HB_BSTAGE_BYTES;
+  const int raw_bytes = 4 * HB_KSTAGE * P.HW * 2;  // 128 source channels of one stage, contiguous in NCHW
   unsigned char* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HB_STAGES * stage_bytes);
-  uint64_t* full = bars;                    // [HB_STAGES]
-  uint64_t* empty = bars + HB_STAGES;       // [HB_STAGES]
-  uint64_t* tmem_full = bars + 2 * HB_STAGES;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  unsigned char* raw_base = smem + K1A_ASTAGES * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + K1A_RSTAGES * raw_bytes);
+  uint64_t* full = bars;                        // [2] operands ready (128 transposer arrivals + weight bytes)
+  uint64_t* empty = bars + 2;                   // [2] MMAs reading the stage have completed
+  uint64_t* raw_full = bars + 4;                // [2] TMA bytes landed
+  uint64_t* raw_empty = bars + 6;               // [2] transposers are done with the raw stage
+  uint64_t* tmem_full = bars + 8;
+  uint64_t* tmem_empty = bars + 9;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // zero the A stages once: halo rows/columns are never written again
-  for (int i = tid; i < HB_STAGES * stage_bytes / 16; i += HB_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  // zero the operand stages once: halo rows/columns are never written again
+  for (int i = tid; i < K1A_ASTAGES * stage_bytes / 16; i += K1A_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    for (int s = 0; s < HB_STAGES; ++s) {
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&full[s], 129);
       mbar_init(&empty[s], 1);
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&raw_empty[s], 128);
     }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 128);
@@ -126,60 +141,73 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k1a_shuffle_convt_kernel(const 
   const uint32_t tmem_base = *tmem_ptr;
 
   const int Wo = 2 * g.Wi, rows_mid = 4 * g.Hi * g.Wi;
+  int nframes = 0;
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x) ++nframes;
+  const int total_it = nframes * P.nstages;
 
-  if (warp < 4) {
-    // ================= producer: NCHW bf16 -> K-major rows, PixelShuffle folded in =================
+  if (warp == 9) {
+    // ================= TMA loader: raw feature slabs run ahead, weights follow the operand slots ====
+    if (lane == 0) {
+      auto issue_raw = [&](int it) {
+        const int r = it % K1A_RSTAGES;
+        mbar_wait(&raw_empty[r], ((it / K1A_RSTAGES) & 1) ^ 1);
+        const int b = blockIdx.x + (it / P.nstages) * gridDim.x, st = it % P.nstages;
+        mbar_expect_tx(&raw_full[r], (uint32_t)raw_bytes);
+        bulk_g2s(raw_base + r * raw_bytes, P.feat + ((size_t)b * P.C + (size_t)st * 4 * HB_KSTAGE) * P.HW, (uint32_t)raw_bytes,
+                 &raw_full[r]);
+      };
+      if (total_it > 0) issue_raw(0);
+      for (int it = 0; it < total_it; ++it) {
+        if (it + 1 < total_it) issue_raw(it + 1);
+        const int s = it % K1A_ASTAGES, st = it % P.nstages;
+        mbar_wait(&empty[s], ((it / K1A_ASTAGES) & 1) ^ 1);
+        mbar_expect_tx(&full[s], HB_BSTAGE_BYTES);
+        bulk_g2s(stage_base + s * stage_bytes + a_stage_bytes,
+                 reinterpret_cast<const unsigned char*>(P.wpk) + (size_t)st * HB_BSTAGE_BYTES, HB_BSTAGE_BYTES, &full[s]);
+      }
+    }
+  } else if (warp < 4) {
+    // ================= transposers: raw NCHW slab (smem) -> K-major rows, PixelShuffle folded in ======
     const int nchunk = P.HW / 8;  // 16-byte chunks of 8 consecutive spatial positions per channel
     const int ntasks = 4 * 4 * nchunk;
-    int it = 0;
-    for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
-      const __nv_bfloat16* fb = P.feat + (size_t)b * P.C * P.HW;
-      for (int st = 0; st < P.nstages; ++st, ++it) {
-        const int s = it % HB_STAGES;
-        const uint32_t ph = (it / HB_STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        unsigned char* As = stage_base + s * stage_bytes;
-        if (tid == 0) {
-          mbar_expect_tx(&full[s], HB_BSTAGE_BYTES);
-          bulk_g2s(As + a_stage_bytes, reinterpret_cast<const unsigned char*>(P.wpk) + (size_t)st * HB_BSTAGE_BYTES,
-                   HB_BSTAGE_BYTES, &full[s]);
-        }
-        for (int task = tid; task < ntasks; task += 128) {
-          const int sc = task % nchunk;
-          const int q = (task / nchunk) & 3;
-          const int kc = task / (4 * nchunk);
-          uint4 v[8];
+    for (int it = 0; it < total_it; ++it) {
+      const int s = it % K1A_ASTAGES, r = it % K1A_RSTAGES;
+      mbar_wait(&raw_full[r], (it / K1A_RSTAGES) & 1);
+      mbar_wait(&empty[s], ((it / K1A_ASTAGES) & 1) ^ 1);
+      unsigned char* As = stage_base + s * stage_bytes;
+      const unsigned char* raw = raw_base + r * raw_bytes;
+      for (int task = tid; task < ntasks; task += 128) {
+        const int sc = task % nchunk;
+        const int q = (task / nchunk) & 3;
+        const int kc = task / (4 * nchunk);
+        uint4 v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int ch = 4 * (st * HB_KSTAGE + kc * 8 + e) + q;
-            v[e] = __ldg(reinterpret_cast<const uint4*>(fb + (size_t)ch * P.HW + sc * 8));
-          }
-          const int di = q >> 1, dj = q & 1;
+        for (int e = 0; e < 8; ++e)
+          v[e] = *reinterpret_cast<const uint4*>(raw + ((size_t)(4 * (kc * 8 + e) + q) * P.HW + sc * 8) * 2);
+        const int di = q >> 1, dj = q & 1;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t w0[8] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x};
-            const uint32_t w1[8] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y};
-            const uint32_t w2[8] = {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z};
-            const uint32_t w3[8] = {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w};
-            const uint32_t* wj = j == 0 ? w0 : (j == 1 ? w1 : (j == 2 ? w2 : w3));
+        for (int j = 0; j < 4; ++j) {
+          uint32_t wj[8];
 #pragma unroll
-            for (int hl = 0; hl < 2; ++hl) {
-              const uint32_t sel = hl ? 0x7632u : 0x5410u;
-              uint4 o;
-              o.x = __byte_perm(wj[0], wj[1], sel);
-              o.y = __byte_perm(wj[2], wj[3], sel);
-              o.z = __byte_perm(wj[4], wj[5], sel);
-              o.w = __byte_perm(wj[6], wj[7], sel);
-              const int sp = sc * 8 + 2 * j + hl;  // spatial index i*W + jcol
-              const int i = sp / P.W, jc = sp - i * P.W;
-              const int row = (2 * i + di) * g.P + (2 * jc + dj);
-              *reinterpret_cast<uint4*>(As + ((size_t)kc * g.rows_alloc + row) * 16) = o;
-            }
+          for (int e = 0; e < 8; ++e) wj[e] = j == 0 ? v[e].x : (j == 1 ? v[e].y : (j == 2 ? v[e].z : v[e].w));
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl) {
+            const uint32_t sel = hl ? 0x7632u : 0x5410u;
+            uint4 o;
+            o.x = __byte_perm(wj[0], wj[1], sel);
+            o.y = __byte_perm(wj[2], wj[3], sel);
+            o.z = __byte_perm(wj[4], wj[5], sel);
+            o.w = __byte_perm(wj[6], wj[7], sel);
+            const int sp = sc * 8 + 2 * j + hl;  // spatial index i*W + jcol
+            const int i = sp / P.W, jc = sp - i * P.W;
+            const int row = (2 * i + di) * g.P + (2 * jc + dj);
+            *reinterpret_cast<uint4*>(As + ((size_t)kc * g.rows_alloc + row) * 16) = o;
           }
         }
-        fence_proxy_async();
-        tc::mbar_arrive(&full[s]);
       }
+      fence_proxy_async();
+      tc::mbar_arrive(&full[s]);
+      tc::mbar_arrive(&raw_empty[r]);
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
@@ -191,9 +219,8 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k1a_shuffle_convt_kernel(const 
       mbar_wait(tmem_empty, fph ^ 1);
       tc::fence_after_sync();
       for (int st = 0; st < P.nstages; ++st, ++it) {
-        const int s = it % HB_STAGES;
-        const uint32_t ph = (it / HB_STAGES) & 1;
-        mbar_wait(&full[s], ph);
+        const int s = it % K1A_ASTAGES;
+        mbar_wait(&full[s], (it / K1A_ASTAGES) & 1);
         tc::fence_after_sync();
         if (lane == 0) {
           const uint32_t a0 = smem_u32(stage_base + s * stage_bytes);
@@ -206,9 +233,8 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k1a_shuffle_convt_kernel(const 
               for (int k16 = 0; k16 < 2; ++k16) {
                 const uint32_t aa = a0 + (2 * k16) * lbo_a + (t * 128 + shift_rows) * 16;
                 const uint32_t bb = b0 + (sh * 4 + 2 * k16) * lbo_b;
-                const uint64_t ad = tc::make_smem_desc(aa, lbo_a, 128);
-                const uint64_t bd = tc::make_smem_desc(bb, lbo_b, 128);
-                tc::umma_bf16(tmem_base + t * HB_NCOLS, ad, bd, idesc, (st | sh | k16) != 0 ? 1u : 0u);
+                tc::umma_bf16(tmem_base + t * HB_NCOLS, tc::make_smem_desc(aa, lbo_a, 128), tc::make_smem_desc(bb, lbo_b, 128),
+                              idesc, (st | sh | k16) != 0 ? 1u : 0u);
               }
             }
           }
@@ -222,6 +248,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k1a_shuffle_convt_kernel(const 
     }
   } else {
     // ================= epilogue: TMEM -> (+bias) -> bf16 -> mid activations (A layout) =================
+    // channel c1 of the mid activations is the constant 1 (lets the next layer fold its bias into the GEMM)
     const int q = warp & 3;
     uint32_t fph = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
@@ -248,10 +275,20 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k1a_shuffle_convt_kernel(const 
               uint32_t pk[4];
 #pragma unroll
               for (int e2 = 0; e2 < 4; ++e2) {
-                const int c0 = kc * 8 + 2 * e2, c1i = c0 + 1;
-                const float f0 = (c0 < P.c1 && c0 < HB_CLS) ? d[cls * HB_CLS + (c0 < HB_CLS ? c0 : 0)] + __ldg(P.bias + c0) : 0.f;
-                const float f1 = (c1i < P.c1 && c1i < HB_CLS) ? d[cls * HB_CLS + (c1i < HB_CLS ? c1i : 0)] + __ldg(P.bias + c1i) : 0.f;
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                float f[2];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const int ch = kc * 8 + 2 * e2 + hh;  // compile-time
+                  float val = 0.f;
+                  if (ch < HB_CLS) {
+                    if (ch < P.c1) val = d[cls * HB_CLS + ch] + __ldg(P.bias + ch);
+                    else if (ch == P.c1) val = 1.0f;
+                  } else if (ch == P.c1) {
+                    val = 1.0f;
+                  }
+                  f[hh] = val;
+                }
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[0], f[1]);
                 pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
               }
               *reinterpret_cast<uint4*>(P.mid + ((((size_t)b * 4 + kc) * rows_mid + row2) * 8)) =
@@ -271,92 +308,98 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k1a_shuffle_convt_kernel(const 
 }
 
 // =====================================================================================================
-// k1b: second transposed convolution + plane softmax
+// k1b: second transposed convolution + plane softmax (two CTAs per SM, half a frame resident at a time)
 // =====================================================================================================
+// warp 0 loader, warp 1 MMA issuer (+TMEM owner), warps 2-9 epilogue: lane quarter q = warp % 4,
+// output-row parity e = (warp - 2) / 4 (classes 2e, 2e+1 = TMEM columns [40e, 40e+40)).
+constexpr int K1B_THREADS = 320;
+constexpr int K1B_TPB = 3;      // M-tiles per batch (3 * 80 = 240 of the CTA's 256 TMEM columns)
+constexpr int K1B_EPI = 256;    // epilogue threads
+
 struct K1bParams {
-  const __nv_bfloat16* mid;  // [B][4][Hi*Wi][8]
-  const __nv_bfloat16* wpk;  // packed weights, one stage (K = 32)
-  const float* bias;         // [c2]
-  float* out;                // [B][c2][2Hi][2Wi]
+  const __nv_bfloat16* mid;   // [B][4][Hi*Wi][8]
+  const __nv_bfloat16* zrow;  // Wi*8 zeros (halo row below the last image row)
+  const __nv_bfloat16* wpk;   // packed weights, one stage (K = 32); bias folded into channel c1
+  float* out;                 // [B][c2][2Hi][2Wi]
   int B, c2, final_softmax;
-  HeadGeom g;
+  int Hh;                     // image rows per half (Hi / 2)
+  HeadGeom g;                 // geometry of one half: Hi = Hh, rows_alloc covers Hh + 1 rows
 };
 
-constexpr int K1B_TPB = 3;  // M-tiles per TMEM buffer (3 * 80 = 240 columns; two buffers at 0 and 256)
-
-__global__ void __launch_bounds__(HB_THREADS, 1) k1b_convt_softmax_kernel(const __grid_constant__ K1bParams P) {
+__global__ void __launch_bounds__(K1B_THREADS, 2) k1b_convt_softmax_kernel(const __grid_constant__ K1bParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const HeadGeom g = P.g;
   const int a_bytes = 4 * g.rows_alloc * 16;
   unsigned char* As = smem;
   unsigned char* Bs = smem + a_bytes;
-  float* stat = reinterpret_cast<float*>(Bs + HB_BSTAGE_BYTES);  // [2][HB_CLS][128] then fin[2][HB_CLS]
-  float* fin = stat + 2 * HB_CLS * 128;
+  float* stat = reinterpret_cast<float*>(Bs + HB_BSTAGE_BYTES);  // [2][HB_CLS][8 warps]
+  float* fin = stat + 2 * HB_CLS * 8;                            // [2][HB_CLS]
   uint64_t* bars = reinterpret_cast<uint64_t*>(fin + 2 * HB_CLS + 8);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + 1;
   uint64_t* b_full = bars + 2;
-  uint64_t* t_full = bars + 3;   // [2]
-  uint64_t* t_empty = bars + 5;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* t_full = bars + 3;
+  uint64_t* t_empty = bars + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < a_bytes / 16; i += HB_THREADS) reinterpret_cast<uint4*>(As)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < a_bytes / 16; i += K1B_THREADS) reinterpret_cast<uint4*>(As)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
     mbar_init(b_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], 128);
-    }
+    mbar_init(t_full, 1);
+    mbar_init(t_empty, K1B_EPI);
     fence_mbar_init();
   }
-  if (warp == 4) tc::tmem_alloc(tmem_ptr, 512);
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, 256);
   fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int Ho = 2 * g.Hi, Wo = 2 * g.Wi;
-  const int npix = g.Hi * g.Wi;
+  const int Hi = 2 * P.Hh, Wi = g.Wi;        // full conv-input image
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  const int npix = Hi * Wi;
   const int nbatch = (g.tiles + K1B_TPB - 1) / K1B_TPB;
   const int npass = P.final_softmax ? 2 : 1;
+  const int nphase = 2 * npass;  // (pass, half)
 
   if (warp == 0) {
-    // ================= loader: weights once, then one frame of mid activations per iteration =======
+    // ================= loader =================
     if (lane == 0) {
       mbar_expect_tx(b_full, HB_BSTAGE_BYTES);
       bulk_g2s(Bs, P.wpk, HB_BSTAGE_BYTES, b_full);
     }
-    uint32_t ph = 0;
+    int ph = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
-      mbar_wait(a_empty, ph ^ 1);
-      if (lane == 0) mbar_expect_tx(a_full, (uint32_t)(4 * npix * 16));
-      __syncwarp();
-      for (int i = lane; i < 4 * g.Hi; i += 32) {
-        const int kc = i / g.Hi, y = i - kc * g.Hi;
-        bulk_g2s(As + ((size_t)kc * g.rows_alloc + (size_t)y * g.P) * 16,
-                 P.mid + (((size_t)b * 4 + kc) * npix + (size_t)y * g.Wi) * 8, (uint32_t)(g.Wi * 16), a_full);
+      for (int phase = 0; phase < nphase; ++phase, ++ph) {
+        const int hf = phase & 1;
+        mbar_wait(a_empty, (ph & 1) ^ 1);
+        if (lane == 0) mbar_expect_tx(a_full, (uint32_t)(4 * (P.Hh + 1) * Wi * 16));
+        __syncwarp();
+        for (int i = lane; i < 4 * (P.Hh + 1); i += 32) {
+          const int kc = i / (P.Hh + 1), yl = i - kc * (P.Hh + 1);
+          const int y = hf * P.Hh + yl;  // image row; y == Hi is the zero halo row
+          const __nv_bfloat16* srcp = (y < Hi) ? P.mid + (((size_t)b * 4 + kc) * npix + (size_t)y * Wi) * 8 : P.zrow;
+          bulk_g2s(As + ((size_t)kc * g.rows_alloc + (size_t)yl * g.P) * 16, srcp, (uint32_t)(Wi * 16), a_full);
+        }
       }
-      ph ^= 1;
     }
-  } else if (warp == 4) {
+  } else if (warp == 1) {
     // ================= MMA issuer =================
     const uint32_t idesc = tc::make_idesc_bf16_f32(128, HB_NCOLS);
     const uint32_t lbo_a = g.rows_alloc * 16, lbo_b = HB_NCOLS * 16;
     const uint32_t a0 = smem_u32(As), b0 = smem_u32(Bs);
     mbar_wait(b_full, 0);
-    uint32_t aph = 0;
-    int nb = 0;  // running batch counter -> buffer + phase
+    int ph = 0, nb = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
-      mbar_wait(a_full, aph);
-      tc::fence_after_sync();
-      for (int pass = 0; pass < npass; ++pass) {
+      for (int phase = 0; phase < nphase; ++phase, ++ph) {
+        mbar_wait(a_full, ph & 1);
+        tc::fence_after_sync();
         for (int bt = 0; bt < nbatch; ++bt, ++nb) {
-          const int buf = nb & 1;
-          mbar_wait(&t_empty[buf], ((nb >> 1) & 1) ^ 1);
+          mbar_wait(t_empty, (nb & 1) ^ 1);
           tc::fence_after_sync();
           if (lane == 0) {
             for (int tt = 0; tt < K1B_TPB; ++tt) {
@@ -369,25 +412,22 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k1b_convt_softmax_kernel(const 
                 for (int k16 = 0; k16 < 2; ++k16) {
                   const uint32_t aa = a0 + (2 * k16) * lbo_a + (t * 128 + shift_rows) * 16;
                   const uint32_t bb = b0 + (sh * 4 + 2 * k16) * lbo_b;
-                  const uint64_t ad = tc::make_smem_desc(aa, lbo_a, 128);
-                  const uint64_t bd = tc::make_smem_desc(bb, lbo_b, 128);
-                  tc::umma_bf16(tmem_base + buf * 256 + tt * HB_NCOLS, ad, bd, idesc, (sh | k16) != 0 ? 1u : 0u);
+                  tc::umma_bf16(tmem_base + tt * HB_NCOLS, tc::make_smem_desc(aa, lbo_a, 128),
+                                tc::make_smem_desc(bb, lbo_b, 128), idesc, (sh | k16) != 0 ? 1u : 0u);
                 }
               }
             }
-            tc::umma_commit(&t_full[buf]);
+            tc::umma_commit(t_full);
+            if (bt == nbatch - 1) tc::umma_commit(a_empty);  // every read of this half has completed
           }
           __syncwarp();
         }
       }
-      if (lane == 0) tc::umma_commit(a_empty);  // all reads of this frame's activations have completed
-      __syncwarp();
-      aph ^= 1;
     }
-  } else if (warp >= 5) {
+  } else {
     // ================= epilogue =================
-    const int q = warp & 3;
-    const int et = (warp - 5) * 32 + lane;  // 0..127
+    const int q = warp & 3, e = (warp - 2) >> 2;
+    const int ew = warp - 2;  // 0..7
     const float L2E = 1.4426950408889634f;
     int nb = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
@@ -397,99 +437,119 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k1b_convt_softmax_kernel(const 
         mx[o] = -3.0e38f;
         sm[o] = 0.f;
       }
-      for (int pass = 0; pass < npass; ++pass) {
-        const bool write = (pass == npass - 1);
+      for (int phase = 0; phase < nphase; ++phase) {
+        const int hf = phase & 1;
+        const bool write = (phase >= nphase - 2);
         for (int bt = 0; bt < nbatch; ++bt, ++nb) {
-          const int buf = nb & 1;
-          mbar_wait(&t_full[buf], (nb >> 1) & 1);
+          mbar_wait(t_full, nb & 1);
           tc::fence_after_sync();
           for (int tt = 0; tt < K1B_TPB; ++tt) {
             const int t = bt * K1B_TPB + tt;
             if (t >= g.tiles) break;
-            float d[HB_NCOLS];
+            // columns [40e, 40e+40) = classes (py = e, px = 0|1); read 48 columns starting at 32e
+            float d[48];
 #pragma unroll
-            for (int cc = 0; cc < HB_NCOLS / 16; ++cc) {
+            for (int cc = 0; cc < 3; ++cc) {
               float v[16];
-              tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + buf * 256 + tt * HB_NCOLS + cc * 16, v);
+              tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + tt * HB_NCOLS + 32 * e + cc * 16, v);
 #pragma unroll
               for (int i = 0; i < 16; ++i) d[cc * 16 + i] = v[i];
             }
             const int row = t * 128 + 32 * q + lane;
-            const int m = row / g.P, n = row - m * g.P;
-            if (m < g.Hi && n < g.Wi) {
+            const int ml = row / g.P, n = row - ml * g.P;
+            const bool valid = (ml < P.Hh) && (n < Wi);
+            const int m = hf * P.Hh + ml;
 #pragma unroll
-              for (int o = 0; o < HB_CLS; ++o) {
-                if (o >= P.c2) break;
-                const float bo = __ldg(P.bias + o);
-                const float l0 = d[o] + bo, l1 = d[HB_CLS + o] + bo, l2 = d[2 * HB_CLS + o] + bo, l3 = d[3 * HB_CLS + o] + bo;
-                if (!write) {
-                  const float mm = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
-                  if (mm > mx[o]) {
-                    sm[o] *= fast_exp2((mx[o] - mm) * L2E);
-                    mx[o] = mm;
-                  }
-                  sm[o] += fast_exp2((l0 - mx[o]) * L2E) + fast_exp2((l1 - mx[o]) * L2E) + fast_exp2((l2 - mx[o]) * L2E) +
-                           fast_exp2((l3 - mx[o]) * L2E);
-                } else {
-                  float p0 = l0, p1 = l1, p2 = l2, p3 = l3;
-                  if (P.final_softmax) {
-                    const float M = fin[o], inv = fin[HB_CLS + o];
-                    p0 = fast_exp2((l0 - M) * L2E) * inv;
-                    p1 = fast_exp2((l1 - M) * L2E) * inv;
-                    p2 = fast_exp2((l2 - M) * L2E) * inv;
-                    p3 = fast_exp2((l3 - M) * L2E) * inv;
-                  }
-                  float* dst = P.out + (((size_t)b * P.c2 + o) * Ho + 2 * m) * Wo + 2 * n;
-                  *reinterpret_cast<float2*>(dst) = make_float2(p0, p1);        // (even row: px = 0, 1)
-                  *reinterpret_cast<float2*>(dst + Wo) = make_float2(p2, p3);   // (odd row)
+            for (int o = 0; o < HB_CLS; ++o) {
+              if (o >= P.c2) break;
+              // class 2e starts at d[8e]; keep the register indices compile-time (select, no local memory)
+              const float l0 = e ? d[8 + o] : d[o], l1 = e ? d[8 + HB_CLS + o] : d[HB_CLS + o];
+              if (!write) {
+                const float mm = valid ? fmaxf(l0, l1) : -3.0e38f;
+                if (__any_sync(0xffffffffu, mm > mx[o])) {
+                  const float mn = fmaxf(mx[o], mm);
+                  sm[o] *= fast_exp2((mx[o] - mn) * L2E);
+                  mx[o] = mn;
                 }
+                if (valid) {
+                  const float mL = mx[o] * L2E;
+                  sm[o] += fast_exp2(fmaf(l0, L2E, -mL)) + fast_exp2(fmaf(l1, L2E, -mL));
+                }
+              } else if (valid) {
+                float p0 = l0, p1 = l1;
+                if (P.final_softmax) {
+                  const float mL = fin[o], inv = fin[HB_CLS + o];
+                  p0 = fast_exp2(fmaf(l0, L2E, -mL)) * inv;
+                  p1 = fast_exp2(fmaf(l1, L2E, -mL)) * inv;
+                }
+                float* dst = P.out + (((size_t)b * P.c2 + o) * Ho + 2 * m + e) * Wo + 2 * n;
+                *reinterpret_cast<float2*>(dst) = make_float2(p0, p1);
               }
             }
           }
           tc::fence_before_sync();
-          tc::mbar_arrive(&t_empty[buf]);
+          tc::mbar_arrive(t_empty);
         }
-        if (!write) {
-          // reduce the per-thread online-softmax states of the 128 epilogue threads, per plane
+        if (P.final_softmax && phase == 1) {
+          // merge the online-softmax states: lanes -> warp (shuffles) -> 8 epilogue warps (smem)
 #pragma unroll
           for (int o = 0; o < HB_CLS; ++o) {
-            stat[o * 128 + et] = mx[o];
-            stat[(HB_CLS + o) * 128 + et] = sm[o];
+            if (o >= P.c2) break;
+            const float M = warp_max(mx[o]);
+            const float S = warp_sum(sm[o] * fast_exp2((mx[o] - M) * L2E));
+            if (lane == 0) {
+              stat[o * 8 + ew] = M;
+              stat[(HB_CLS + o) * 8 + ew] = S;
+            }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (et < P.c2) {
-            float M = -3.0e38f;
-            for (int i = 0; i < 128; ++i) M = fmaxf(M, stat[et * 128 + i]);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (tid - 64 < P.c2) {
+            const int o = tid - 64;
+            float M = stat[o * 8];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) M = fmaxf(M, stat[o * 8 + i]);
             float S = 0.f;
-            for (int i = 0; i < 128; ++i) S += stat[(HB_CLS + et) * 128 + i] * fast_exp2((stat[et * 128 + i] - M) * L2E);
-            fin[et] = M;
-            fin[HB_CLS + et] = 1.0f / S;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) S += stat[(HB_CLS + o) * 8 + i] * fast_exp2((stat[o * 8 + i] - M) * L2E);
+            fin[o] = M * L2E;
+            fin[HB_CLS + o] = 1.0f / S;
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
       }
     }
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
 }
 
-static size_t k1a_smem_bytes(const HeadGeom& g) { return (size_t)HB_STAGES * (4 * g.rows_alloc * 16 + HB_BSTAGE_BYTES) + 128; }
+static size_t k1a_smem_bytes(const HeadGeom& g, int HW) {
+  return (size_t)K1A_ASTAGES * (4 * g.rows_alloc * 16 + HB_BSTAGE_BYTES) + (size_t)K1A_RSTAGES * 4 * HB_KSTAGE * HW * 2 + 128;
+}
 static size_t k1b_smem_bytes(const HeadGeom& g) {
-  return (size_t)4 * g.rows_alloc * 16 + HB_BSTAGE_BYTES + (2 * HB_CLS * 128 + 2 * HB_CLS + 8) * sizeof(float) + 128;
+  return (size_t)4 * g.rows_alloc * 16 + HB_BSTAGE_BYTES + (2 * HB_CLS * 8 + 2 * HB_CLS + 8) * sizeof(float) + 64;
+}
+
+// geometry of one half image (Hh rows + 1 halo row) of the second layer
+__host__ inline HeadGeom make_half_geom(int Hh, int Wi) {
+  HeadGeom g = make_geom(Hh, Wi);
+  g.rows_alloc = (g.tiles * 128 + g.P + 1 + 7) & ~7;
+  if (g.rows_alloc < (Hh + 1) * g.P + 8) g.rows_alloc = ((Hh + 1) * g.P + 8 + 7) & ~7;
+  return g;
 }
 
 }  // namespace lpb
 
-// workspace layout: [packed w1][packed w2][mid activations]
+// workspace layout: [packed w1][packed w2][zero row][mid activations]
 extern "C" int lpb_head_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes) {
   using namespace lpb;
   LPB_REQUIRE(bytes, "head_bf16_workspace_bytes: null pointer");
   LPB_REQUIRE(B >= 0 && C >= 128 && C % 128 == 0 && H >= 1 && W >= 1 && c1 >= 1 && c2 >= 1, "head_bf16_workspace_bytes: bad shape");
   const size_t w1 = (size_t)(C / 4 / HB_KSTAGE) * HB_BSTAGE_BYTES, w2 = HB_BSTAGE_BYTES;
+  const size_t zrow = ((size_t)4 * W * 16 + 255) & ~(size_t)255;
   const size_t mid = (size_t)B * 4 * (16 * H * W) * 16;
-  *bytes = w1 + w2 + mid;
+  *bytes = w1 + w2 + zrow + mid;
   return LPB_OK;
 }
 
@@ -500,9 +560,9 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   LPB_REQUIRE(features && w1 && b1 && w2 && b2 && out && workspace, "head_fwd_bf16: null pointer");
   LPB_REQUIRE(B >= 0 && C >= 128 && C % 128 == 0 && H >= 1 && W >= 1, "head_fwd_bf16: bad feature shape C=%d H=%d W=%d", C, H, W);
   LPB_REQUIRE((H * W) % 8 == 0, "head_fwd_bf16: H*W must be a multiple of 8 (got %d)", H * W);
-  LPB_REQUIRE(c1 >= 1 && c1 <= HB_CLS && c2 >= 1 && c2 <= HB_CLS, "head_fwd_bf16: channel counts %d/%d exceed %d", c1, c2, HB_CLS);
+  LPB_REQUIRE(c1 >= 1 && c1 < HB_CLS && c2 >= 1 && c2 <= HB_CLS, "head_fwd_bf16: channel counts %d/%d exceed %d", c1, c2, HB_CLS);
   if (B == 0) return LPB_OK;
-  const HeadGeom g1 = make_geom(2 * H, 2 * W), g2 = make_geom(4 * H, 4 * W);
+  const HeadGeom g1 = make_geom(2 * H, 2 * W), g2 = make_half_geom(2 * H, 4 * W);  // layer 2: 4H rows in two halves
   if (g1.tiles * HB_NCOLS > 512) {
     set_error("head_fwd_bf16: %d M-tiles of layer 1 exceed TMEM (feature map %dx%d too large for this build)", g1.tiles, H, W);
     return LPB_ERR_UNSUPPORTED;
@@ -511,7 +571,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   LPB_CUDA(cudaGetDevice(&dev));
   LPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t s1 = k1a_smem_bytes(g1), s2 = k1b_smem_bytes(g2);
+  const size_t s1 = k1a_smem_bytes(g1, H * W), s2 = k1b_smem_bytes(g2);
   if ((int64_t)s1 > max_smem || (int64_t)s2 > max_smem) {
     set_error("head_fwd_bf16: needs %zu / %zu B shared memory (> %d)", s1, s2, max_smem);
     return LPB_ERR_UNSUPPORTED;
@@ -519,11 +579,15 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nst = C / 4 / HB_KSTAGE;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
+  const size_t zrow_bytes = ((size_t)4 * W * 16 + 255) & ~(size_t)255;
   __nv_bfloat16* wp1 = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* wp2 = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)nst * HB_BSTAGE_BYTES);
-  __nv_bfloat16* mid = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES);
-  pack_convt_weights_kernel<<<64, 256, 0, s>>>(w1, C / 4, c1, nst, wp1);
-  pack_convt_weights_kernel<<<8, 256, 0, s>>>(w2, c1, c2, 1, wp2);
+  __nv_bfloat16* zrow = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES);
+  __nv_bfloat16* mid = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES + zrow_bytes);
+  pack_convt_weights_kernel<<<64, 256, 0, s>>>(w1, nullptr, C / 4, c1, nst, wp1, nullptr, 0);
+  // layer 2: bias rides on the constant-one channel c1 of the mid activations (only needed without softmax:
+  // a per-plane constant does not change a softmax); the same launch clears the halo row
+  pack_convt_weights_kernel<<<8, 256, 0, s>>>(w2, final_softmax ? nullptr : b2, c1, c2, 1, wp2, zrow, (int)(zrow_bytes / 2));
   K1aParams pa;
   pa.feat = static_cast<const __nv_bfloat16*>(features);
   pa.wpk = wp1;
@@ -537,18 +601,20 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   pa.nstages = nst;
   pa.g = g1;
   LPB_CUDA(cudaFuncSetAttribute(k1a_shuffle_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
-  k1a_shuffle_convt_kernel<<<B < sms ? B : sms, HB_THREADS, s1, s>>>(pa);
+  k1a_shuffle_convt_kernel<<<B < sms ? B : sms, K1A_THREADS, s1, s>>>(pa);
   K1bParams pb;
   pb.mid = mid;
+  pb.zrow = zrow;
   pb.wpk = wp2;
-  pb.bias = b2;
   pb.out = out;
   pb.B = B;
   pb.c2 = c2;
   pb.final_softmax = final_softmax;
+  pb.Hh = 2 * H;
   pb.g = g2;
   LPB_CUDA(cudaFuncSetAttribute(k1b_convt_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-  k1b_convt_softmax_kernel<<<B < sms ? B : sms, HB_THREADS, s2, s>>>(pb);
+  const int grid2 = B < 2 * sms ? B : 2 * sms;
+  k1b_convt_softmax_kernel<<<grid2, K1B_THREADS, s2, s>>>(pb);
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
 }
