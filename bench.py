@@ -83,33 +83,70 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_problem(n_clips: int, seed: int, device, head_gain: float):
-    """Seeded synthetic inputs of config 2; features = randn * 0.5."""
+def _inverse_pixel_shuffle(xs: torch.Tensor) -> torch.Tensor:
+    """(N, C, 2H, 2W) -> (N, 4C, H, W) with out[4c + 2di + dj, i, j] = xs[c, 2i+di, 2j+dj]."""
+    return torch.nn.functional.pixel_unshuffle(xs, 2)
+
+
+def make_problem(n_clips: int, seed: int, device, regime: str = "trained"):
+    """Seeded synthetic inputs of BASELINE configs[1] (no datasets / checkpoints are reachable).
+
+    regime "trained": what the semi-supervised phase of training sees - unimodal, Gaussian-like heatmaps
+      (peak ~0.1, sigma ~1.25 heatmap px, cf. SURVEY 8(d) "peaked").  Built by construction, since the head is
+      linear: the two deconvs carry 2x-bilinear kernels routed per keypoint (+1e-3 noise) and the features carry a
+      planted non-negative response bump per keypoint (+ N(0, 0.1) noise); unlabeled clips follow a random walk.
+    regime "fresh": the reference's own initialiser (xavier-uniform gain 0.01, zero bias) on randn*0.5 features
+      -> flat heatmaps, for which the soft-argmax has to evaluate the whole 384x384 field.
+    """
     from lightning_pose_b200.models.heads.heatmap import HeatmapHead
 
     g = torch.Generator().manual_seed(seed)
-    n_frames = n_clips * (B_LABELED + T_UNLABELED)
-    head = HeatmapHead("resnet50", FEAT_C, K_PTS)
-    with torch.no_grad():
-        for layer in list(head.upsampling_layers)[1:]:
-            fan_in, fan_out = layer.weight.shape[1] * 9, layer.weight.shape[0] * 9
-            bound = head_gain * (6.0 / (fan_in + fan_out)) ** 0.5
-            layer.weight.copy_((torch.rand(layer.weight.shape, generator=g) * 2 - 1) * bound)
-    kp_lab = torch.rand(n_clips * B_LABELED, K_PTS, 2, generator=g) * IMG
-    kp_lab[torch.rand(n_clips * B_LABELED, K_PTS, generator=g) < 0.1] = float("nan")
-    vis = torch.randint(0, 3, (n_clips * B_LABELED, K_PTS), generator=g)
+    n_lab, n_unl = n_clips * B_LABELED, n_clips * T_UNLABELED
+    n_frames = n_lab + n_unl
+    torch.manual_seed(seed)
+    head = HeatmapHead("resnet50", FEAT_C, K_PTS)  # reference initialiser
+    c4, hs = FEAT_C // 4, 2 * FEAT_HW
+    # keypoints in heatmap pixels: labeled uniform, unlabeled = per-clip random walk
+    kp_hm = torch.empty(n_frames, K_PTS, 2)
+    kp_hm[:n_lab] = torch.rand(n_lab, K_PTS, 2, generator=g) * 80 + 8
+    walk = torch.cumsum(torch.randn(n_clips, T_UNLABELED, K_PTS, 2, generator=g) * 0.6, dim=1)
+    kp_hm[n_lab:] = (torch.rand(n_clips, 1, K_PTS, 2, generator=g) * 60 + 18 + walk).clamp(6, 90).reshape(n_unl, K_PTS, 2)
+    feats = torch.empty((n_frames, FEAT_C, FEAT_HW, FEAT_HW), dtype=torch.float32)
+    if regime == "trained":
+        tri = torch.tensor([[0.25, 0.5, 0.25], [0.5, 1.0, 0.5], [0.25, 0.5, 0.25]])
+        group = torch.arange(c4) % K_PTS
+        with torch.no_grad():
+            d1, d2 = list(head.upsampling_layers)[1:]
+            w1 = torch.randn(d1.weight.shape, generator=g) * 1e-3
+            w1[torch.arange(c4), group] += tri / (c4 // K_PTS)
+            w2 = torch.randn(d2.weight.shape, generator=g) * 1e-3
+            w2[torch.arange(K_PTS), torch.arange(K_PTS)] += tri
+            d1.weight.copy_(w1)
+            d2.weight.copy_(w2)
+        centre = torch.arange(hs, dtype=torch.float32) * 4 + 1.5  # heatmap position of a shuffled pixel
+        for i in range(0, n_frames, 64):  # bounded temp memory
+            kp = kp_hm[i : i + 64]
+            dy = (centre[None, None, :, None] - kp[:, :, 1, None, None]) ** 2
+            dx = (centre[None, None, None, :] - kp[:, :, 0, None, None]) ** 2
+            q = torch.exp(-(dy + dx) / (2 * 4.3**2))  # (n, K, 24, 24) planted response: logit bump, sigma_eff ~1.25 px
+            q = q * (13.0 / q.amax(dim=(2, 3), keepdim=True))  # peak logit 13 -> heatmap peak ~0.1-0.25 like a trained net
+            xs = q[:, group] + torch.randn((kp.shape[0], c4, hs, hs), generator=g) * 0.1
+            feats[i : i + 64] = _inverse_pixel_shuffle(xs)
+    else:
+        for i in range(0, n_frames, 64):
+            feats[i : i + 64] = torch.randn((min(64, n_frames - i), FEAT_C, FEAT_HW, FEAT_HW), generator=g) * 0.5
+    kp_lab = kp_hm[:n_lab] * (IMG / HM) + torch.randn(n_lab, K_PTS, 2, generator=g) * 2.0  # labels in image pixels
+    kp_lab[torch.rand(n_lab, K_PTS, generator=g) < 0.1] = float("nan")
+    vis = torch.randint(0, 3, (n_lab, K_PTS), generator=g)
     ang = np.deg2rad(float(torch.rand(1, generator=g)) * 20 - 10)
     sc = 0.8 + 0.4 * float(torch.rand(1, generator=g))
     tf = torch.tensor([[sc * np.cos(ang), -sc * np.sin(ang), 4.0], [sc * np.sin(ang), sc * np.cos(ang), -3.0]], dtype=torch.float32)
-    bbox = torch.tensor([[0.0, 0.0, 406.0, 396.0]]).repeat(n_clips * T_UNLABELED, 1)
+    bbox = torch.tensor([[0.0, 0.0, 406.0, 396.0]]).repeat(n_unl, 1)
     # PCA parameters: rank-6 latent pose + noise (SURVEY 8(d)), all 17 keypoints
     lat = torch.randn(500, 6, generator=g) @ torch.randn(6, 2 * K_PTS, generator=g) * 20 + 200 + torch.randn(500, 2 * K_PTS, generator=g) * 2
     mean = lat.mean(0)
     _, _, vt = torch.linalg.svd(lat - mean, full_matrices=False)
     pca = {"mean": mean, "kept": vt[:6].contiguous(), "eps": 5.0}
-    feats = torch.empty((n_frames, FEAT_C, FEAT_HW, FEAT_HW), dtype=torch.float32)
-    for i in range(0, n_frames, 64):  # bounded temp memory
-        feats[i : i + 64] = torch.randn((min(64, n_frames - i), FEAT_C, FEAT_HW, FEAT_HW), generator=g) * 0.5
     return {"head": head, "feats": feats, "kp_lab": kp_lab, "vis": vis, "tf": tf, "bbox": bbox, "pca": pca, "n_clips": n_clips}
 
 
@@ -205,7 +242,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     import lightning_pose_b200  # noqa: F401  (fails loudly without the CUDA library)
 
-    prob = make_problem(args.clips, seed=1234 + rank, device=dev, head_gain=args.head_gain)
+    prob = make_problem(args.clips, seed=1234 + rank, device=dev, regime=args.regime)
     hp = HotPath(prob, dev, args.fwd_only)
     tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     feats_host = prob["feats"].to(tdt).pin_memory()
@@ -247,16 +284,17 @@ def run_ours(args):
     br = kernel_breakdown(hp, feats)
     flat = None
     if not args.no_flat:
-        # secondary regime: the reference's own initialiser (xavier gain 0.01) -> flat heatmaps -> the decode
-        # cannot prune and evaluates the whole 384x384 field (SURVEY 7 "hard parts" 1)
-        from lightning_pose_b200.models.heads.heatmap import HeatmapHead
-
-        torch.manual_seed(99)
-        hp.head = HeatmapHead("resnet50", FEAT_C, K_PTS).to(dev)
-        ms_flat = time_steps(lambda: hp.step(feats), max(2, args.steps // 2), 2)
-        flat = {"value": n_frames * max(2, args.steps // 2) / (ms_flat / 1e3), "unit": "frames/s",
-                "head_init": "reference initialiser, xavier gain 0.01 (flat heatmaps, dense decode)",
-                "stages": {k: round(v["ms"], 4) for k, v in kernel_breakdown(hp, feats, reps=3).items()}}
+        # secondary regime: the reference's own initialiser (xavier gain 0.01) on randn features -> flat heatmaps ->
+        # the decode cannot prune and evaluates the whole 384x384 field (SURVEY 7 "hard parts" 1)
+        prob_f = make_problem(args.clips, seed=4321 + rank, device=dev, regime="fresh")
+        hp_f = HotPath(prob_f, dev, args.fwd_only)
+        feats_f = prob_f["feats"].to(tdt).to(dev)
+        nst = max(2, args.steps // 2)
+        ms_flat = time_steps(lambda: hp_f.step(feats_f), nst, 2)
+        flat = {"value": n_frames * nst / (ms_flat / 1e3), "unit": "frames/s",
+                "regime": "fresh init: reference initialiser (xavier gain 0.01) on randn*0.5 features; flat heatmaps, dense decode",
+                "stages": {k: round(v["ms"], 4) for k, v in kernel_breakdown(hp_f, feats_f, reps=3).items()}}
+        del hp_f, feats_f, prob_f
     dom = max(br, key=lambda k: br[k]["ms"])
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -265,7 +303,8 @@ def run_ours(args):
         "config": {
             "workload": f"BASELINE configs[1] hot path on ResNet-50 features (B,2048,12,12): {args.clips} clips/step/GPU x (16 labeled + 32 unlabeled) frames, "
                         f"K=17, heatmaps 96x96, decode field 384x384; pass = {'forward' if args.fwd_only else 'forward+backward'}",
-            "frames_per_step_per_gpu": n_frames, "head_init": f"xavier-uniform gain {args.head_gain} (trained-like peaked heatmaps; see flat_regime for the fresh-init case)",
+            "frames_per_step_per_gpu": n_frames, "regime": ("trained-like synthetic response (unimodal Gaussian-like heatmaps; planted features + bilinear per-keypoint deconvs, see bench.make_problem); fresh_init_regime = reference initialiser"
+                                                                                  if args.regime == "trained" else "fresh init (reference initialiser, flat heatmaps)"),
             "l2_policy": f"inputs larger than L2 ({feats.numel() * esz / 2**20:.0f} MiB of features per step)", "parallelism": f"dp{world}",
         },
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": feats.numel() * esz, "d2h_bytes_per_step": 16},
@@ -276,7 +315,7 @@ def run_ours(args):
         "stages": {k: {"ms": round(v["ms"], 4), "GBps": round(v["gbs"], 1), "frac_hbm": round(v["gbs"] / pk["hbm_gbs"], 4)} for k, v in br.items()},
     }
     if flat is not None:
-        line["flat_regime"] = flat
+        line["fresh_init_regime"] = flat
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference(seed=1234, clips=1, reps=1)
     print(json.dumps(line))
@@ -309,7 +348,7 @@ def cpu_step(prob):
 
 def cpu_reference(seed, clips, reps):
     torch.set_num_threads(os.cpu_count() or 1)
-    prob = make_problem(clips, seed=seed, device="cpu", head_gain=3.0)
+    prob = make_problem(clips, seed=seed, device="cpu", regime="trained")
     cpu_step(prob)  # warm-up
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -331,7 +370,7 @@ def run_reference(args):
         return
     torch.set_num_threads(os.cpu_count() or 1)
     clips = 1
-    prob = make_problem(clips, seed=1234, device="cpu", head_gain=args.head_gain)
+    prob = make_problem(clips, seed=1234, device="cpu", regime=args.regime)
     for _ in range(min(args.warmup, 1)):
         cpu_step(prob)
     t0 = time.perf_counter()
@@ -358,9 +397,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=16, help="clips per step per GPU (48 frames each)")
-    ap.add_argument("--head-gain", type=float, default=5.0, help="xavier gain of the synthetic head weights (5 = trained-like peaks ~0.2)")
+    ap.add_argument("--regime", default="trained", choices=["trained", "fresh"], help="synthetic input regime (see make_problem)")
     ap.add_argument("--dtype", default="bf16", choices=["f32", "bf16"], help="feature dtype (bf16 = tcgen05 head)")
-    ap.add_argument("--no-flat", action="store_true", help="skip the secondary flat-heatmap (fresh-init) regime")
+    ap.add_argument("--no-flat", action="store_true", help="skip the secondary fresh-init (flat heatmap) regime")
     ap.add_argument("--fwd-only", action="store_true", default=True)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

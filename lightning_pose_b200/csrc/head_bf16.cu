@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 2) k1b_convt_softmax_kernel(const
     const int q = warp & 3, e = (warp - 2) >> 2;
     const int ew = warp - 2;  // 0..7
     const float L2E = 1.4426950408889634f;
+    const size_t plane_stride = (size_t)Ho * Wo;
     int nb = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
       float mx[HB_CLS], sm[HB_CLS];
@@ -446,24 +447,31 @@ __global__ void __launch_bounds__(K1B_THREADS, 2) k1b_convt_softmax_kernel(const
           for (int tt = 0; tt < K1B_TPB; ++tt) {
             const int t = bt * K1B_TPB + tt;
             if (t >= g.tiles) break;
-            // columns [40e, 40e+40) = classes (py = e, px = 0|1); read 48 columns starting at 32e
-            float d[48];
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
+            // columns [40e, 40e+40) = classes (py = e, px = 0|1) of this tile
+            float d[40];
+            {
+              const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + tt * HB_NCOLS + 40 * e;
               float v[16];
-              tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + tt * HB_NCOLS + 32 * e + cc * 16, v);
+              tc::tmem_ld16(ta, v);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) d[cc * 16 + i] = v[i];
+              for (int i = 0; i < 16; ++i) d[i] = v[i];
+              tc::tmem_ld16(ta + 16, v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) d[16 + i] = v[i];
+              float v8[8];
+              tc::tmem_ld8(ta + 32, v8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) d[32 + i] = v8[i];
             }
             const int row = t * 128 + 32 * q + lane;
             const int ml = row / g.P, n = row - ml * g.P;
             const bool valid = (ml < P.Hh) && (n < Wi);
             const int m = hf * P.Hh + ml;
+            float* dst = P.out + ((size_t)b * P.c2 * Ho + 2 * m + e) * Wo + 2 * n;  // plane o adds o * Ho * Wo
 #pragma unroll
             for (int o = 0; o < HB_CLS; ++o) {
               if (o >= P.c2) break;
-              // class 2e starts at d[8e]; keep the register indices compile-time (select, no local memory)
-              const float l0 = e ? d[8 + o] : d[o], l1 = e ? d[8 + HB_CLS + o] : d[HB_CLS + o];
+              const float l0 = d[o], l1 = d[HB_CLS + o];
               if (!write) {
                 const float mm = valid ? fmaxf(l0, l1) : -3.0e38f;
                 if (__any_sync(0xffffffffu, mm > mx[o])) {
@@ -482,8 +490,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 2) k1b_convt_softmax_kernel(const
                   p0 = fast_exp2(fmaf(l0, L2E, -mL)) * inv;
                   p1 = fast_exp2(fmaf(l1, L2E, -mL)) * inv;
                 }
-                float* dst = P.out + (((size_t)b * P.c2 + o) * Ho + 2 * m + e) * Wo + 2 * n;
-                *reinterpret_cast<float2*>(dst) = make_float2(p0, p1);
+                *reinterpret_cast<float2*>(dst + (size_t)o * plane_stride) = make_float2(p0, p1);
               }
             }
           }

@@ -2,7 +2,7 @@
 # GPU parity + bench + ncu launch list + full captures of the top kernels.
 set -uo pipefail
 mkdir -p gpurun_out
-echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
+echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q --durations=6 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
 echo "== bench bf16"; timeout 900 python bench.py --steps 10 --warmup 3 ${BENCH_ARGS:-} 2>&1 | tail -3 | tee gpurun_out/bench.log
 echo "== bench f32"; timeout 900 python bench.py --steps 5 --warmup 3 --dtype f32 --no-cpu-baseline 2>&1 | tail -3 | tee gpurun_out/bench_f32.log
 echo "== ncu launch list"
