@@ -136,6 +136,11 @@ int lpb_heatmap_mse_from_keypoints_fwd(const float* keypoints, const int32_t* vi
                                        int64_t n_planes, float img_height, float img_width, int oh, int ow,
                                        float sigma, float* out, float* workspace, void* stream);
 
+int lpb_heatmap_mse_from_keypoints_bwd(const float* keypoints, const int32_t* visibility, const float* preds,
+                                       int64_t n_planes, float img_height, float img_width, int oh, int ow,
+                                       float sigma, const float* fwd_out, const float* grad_out, float* grad_preds,
+                                       void* stream);
+
 /* replaces TemporalHeatmapLoss.__call__  lightning_pose/losses/losses.py:793-854
  * heatmaps [T,K,h,w], confidences [T,K], eps [K]; kind LPB_HM_MSE | LPB_HM_KL; out[0] = scalar loss;
  * workspace (T-1)*K floats. */

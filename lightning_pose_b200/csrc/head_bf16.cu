@@ -447,21 +447,15 @@ __global__ void __launch_bounds__(K1B_THREADS, 2) k1b_convt_softmax_kernel(const
           for (int tt = 0; tt < K1B_TPB; ++tt) {
             const int t = bt * K1B_TPB + tt;
             if (t >= g.tiles) break;
-            // columns [40e, 40e+40) = classes (py = e, px = 0|1) of this tile
-            float d[40];
-            {
-              const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + tt * HB_NCOLS + 40 * e;
+            // columns [40e, 40e+40) = classes (py = e, px = 0|1) of this tile; TMEM loads stay 16-column
+            // aligned: read [32e, 32e+48) and pick with compile-time register indices
+            float d[48];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
               float v[16];
-              tc::tmem_ld16(ta, v);
+              tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + tt * HB_NCOLS + 32 * e + cc * 16, v);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) d[i] = v[i];
-              tc::tmem_ld16(ta + 16, v);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) d[16 + i] = v[i];
-              float v8[8];
-              tc::tmem_ld8(ta + 32, v8);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) d[32 + i] = v8[i];
+              for (int i = 0; i < 16; ++i) d[cc * 16 + i] = v[i];
             }
             const int row = t * 128 + 32 * q + lane;
             const int ml = row / g.P, n = row - ml * g.P;
@@ -471,7 +465,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 2) k1b_convt_softmax_kernel(const
 #pragma unroll
             for (int o = 0; o < HB_CLS; ++o) {
               if (o >= P.c2) break;
-              const float l0 = d[o], l1 = d[HB_CLS + o];
+              const float l0 = e ? d[8 + o] : d[o], l1 = e ? d[8 + HB_CLS + o] : d[HB_CLS + o];
               if (!write) {
                 const float mm = valid ? fmaxf(l0, l1) : -3.0e38f;
                 if (__any_sync(0xffffffffu, mm > mx[o])) {

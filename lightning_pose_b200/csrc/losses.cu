@@ -166,6 +166,41 @@ __global__ void __launch_bounds__(HL_THREADS) heatmap_mse_from_kp_kernel(const f
 }
 
 
+// backward of the fused target + MSE: d loss / d pred = 2 (pred - target) / n_kept on kept planes
+__global__ void __launch_bounds__(HL_THREADS) heatmap_mse_from_kp_bwd_kernel(const float* __restrict__ kp,
+                                                                             const int32_t* __restrict__ vis,
+                                                                             const float* __restrict__ pred, float sx,
+                                                                             float sy, int oh, int ow, float two_s2,
+                                                                             const float* __restrict__ fwd_out,
+                                                                             const float* __restrict__ gout,
+                                                                             float* __restrict__ gpred) {
+  extern __shared__ float sm[];  // ex[ow], ey[oh], red[16]
+  float* ex = sm;
+  float* ey = sm + ow;
+  float* red = ey + oh;
+  const size_t plane = blockIdx.x;
+  const int n = oh * ow;
+  const TargetPlane tp = classify_target(kp[2 * plane], kp[2 * plane + 1], vis ? vis[plane] : -1, sx, sy, oh, ow);
+  float* __restrict__ g = gpred + plane * (size_t)n;
+  if (tp.mode == TARGET_ZERO) {
+    for (int i = threadIdx.x; i < n; i += HL_THREADS) g[i] = 0.f;
+    return;
+  }
+  const float scale = 2.f * gout[0] / fwd_out[1];
+  const float* __restrict__ p = pred + plane * (size_t)n;
+  if (tp.mode == TARGET_UNIFORM) {
+    const float u = 1.0f / (float)n;
+    for (int i = threadIdx.x; i < n; i += HL_THREADS) g[i] = (__ldg(p + i) - u) * scale;
+    return;
+  }
+  const float norm = target_axis_factors(tp, oh, ow, two_s2, ex, ey, red, HL_THREADS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < oh; r += HL_THREADS / 32) {
+    const float er = ey[r] * norm;
+    for (int c = lane; c < ow; c += 32) g[(size_t)r * ow + c] = (__ldg(p + (size_t)r * ow + c) - ex[c] * er) * scale;
+  }
+}
+
 // ---- TemporalHeatmapLoss (lightning_pose/losses/losses.py:793-854) ------------------------------------
 // stage 1: one CTA per (t, k) pair of consecutive planes -> ws[t*K+k] = mean-pixel MSE or
 // KL(pred = h[t] + 1e-10, target = h[t+1] + 1e-10)  (argument order of :818-822)
@@ -675,6 +710,23 @@ extern "C" int lpb_temporal_heatmap_loss_fwd(const float* heatmaps, const float*
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   temporal_heatmap_pair_kernel<<<(unsigned)((T - 1) * K), HL_THREADS, 0, s>>>(heatmaps, K, h * w, kind, workspace);
   temporal_heatmap_final_kernel<<<1, HL_THREADS, 0, s>>>(workspace, confidences, (int)T, K, eps, prob_threshold, out);
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}
+
+extern "C" int lpb_heatmap_mse_from_keypoints_bwd(const float* keypoints, const int32_t* visibility, const float* preds,
+                                                  int64_t n_planes, float img_height, float img_width, int oh, int ow,
+                                                  float sigma, const float* fwd_out, const float* grad_out,
+                                                  float* grad_preds, void* stream) {
+  using namespace lpb;
+  LPB_REQUIRE(keypoints && preds && fwd_out && grad_out && grad_preds, "heatmap_mse_from_keypoints_bwd: null pointer");
+  LPB_REQUIRE(oh >= 1 && ow >= 1 && oh + ow < 8000 && sigma > 0.f && img_height > 0.f && img_width > 0.f,
+              "heatmap_mse_from_keypoints_bwd: bad shape");
+  LPB_REQUIRE(n_planes >= 1 && n_planes < (1ll << 31), "heatmap_mse_from_keypoints_bwd: bad n_planes");
+  const size_t smem = (size_t)(oh + ow + 16) * sizeof(float);
+  heatmap_mse_from_kp_bwd_kernel<<<(unsigned)n_planes, HL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      keypoints, visibility, preds, (float)((double)ow / (double)img_width), (float)((double)oh / (double)img_height), oh,
+      ow, (float)(2.0 * (double)sigma * (double)sigma), fwd_out, grad_out, grad_preds);
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
 }

@@ -76,12 +76,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680u)  // suspend-time hint: the waiting warp sleeps in hardware instead of spinning
+      "r"(parity)
       : "memory");
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-B aligned.

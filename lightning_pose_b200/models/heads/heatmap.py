@@ -83,14 +83,15 @@ class _HeadFunction(torch.autograd.Function):
         if ctx.final_softmax:  # d softmax: p * (g - sum(g * p)) per plane
             g = out * (g - (g * out).sum(dim=(2, 3), keepdim=True))
         # interim: transposed-conv dgrad/wgrad through the framework's conv ops ("backward")
+        cdt = torch.bfloat16 if features.dtype == torch.bfloat16 else torch.float32  # same precision as the forward
         with torch.enable_grad():
-            f = features.detach().float().requires_grad_(ctx.needs_input_grad[0])
+            f = features.detach().to(cdt).requires_grad_(ctx.needs_input_grad[0])
             ps = [p.detach().float().requires_grad_(True) for p in params]
             x = torch.nn.functional.pixel_shuffle(f, 2)
             for wt, bs in zip(ps[:n], ps[n:]):
-                x = torch.nn.functional.conv_transpose2d(x, wt, bs, stride=2, padding=1, output_padding=1)
+                x = torch.nn.functional.conv_transpose2d(x, wt.to(cdt), bs.to(cdt), stride=2, padding=1, output_padding=1)
             ins = ([f] if ctx.needs_input_grad[0] else []) + ps
-            grads = torch.autograd.grad(x, ins, g)
+            grads = torch.autograd.grad(x, ins, g.to(cdt))
         gf = grads[0] if ctx.needs_input_grad[0] else None
         gp = grads[1:] if ctx.needs_input_grad[0] else grads
         return (gf, None, *gp)

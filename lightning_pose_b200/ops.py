@@ -281,17 +281,36 @@ def heatmap_loss(targets, preds, kind: str = "mse", return_count: bool = False):
     return (loss, count) if return_count else loss
 
 
+class _HeatmapMseFromKeypoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kp, vis, preds, height, width, sigma):
+        b, k, oh, ow = preds.shape
+        out = torch.empty((2,), device=preds.device, dtype=torch.float32)
+        ws = torch.empty((b * k * 2,), device=preds.device, dtype=torch.float32)
+        with torch.cuda.device(preds.device):
+            check(lib.lpb_heatmap_mse_from_keypoints_fwd(_ptr(kp), _ptr(vis), _ptr(preds), b * k, height, width, oh, ow, sigma, _ptr(out), _ptr(ws), _stream()))
+        ctx.save_for_backward(kp, vis, preds, out)
+        ctx.meta = (height, width, sigma)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        kp, vis, preds, out = ctx.saved_tensors
+        height, width, sigma = ctx.meta
+        b, k, oh, ow = preds.shape
+        gp = torch.empty_like(preds)
+        gg = g.reshape(1).contiguous().float()
+        with torch.cuda.device(preds.device):
+            check(lib.lpb_heatmap_mse_from_keypoints_bwd(_ptr(kp), _ptr(vis), _ptr(preds), b * k, height, width, oh, ow, sigma, _ptr(out), _ptr(gg), _ptr(gp), _stream()))
+        return None, None, gp, None, None, None
+
+
 def heatmap_mse_from_keypoints(keypoints, preds, height, width, sigma=1.25, visibility=None):
-    """Fused target generation + HeatmapMSELoss forward (targets never written to HBM)."""
-    kp = _cuda_f32(keypoints, "keypoints")
+    """Fused target generation + HeatmapMSELoss (targets never written to HBM); differentiable in ``preds``."""
+    kp = _cuda_f32(keypoints, "keypoints").detach()
     p = _cuda_f32(preds, "heatmaps_pred")
-    b, k, oh, ow = p.shape
     vis = visibility.to(torch.int32).contiguous() if visibility is not None else None
-    out = torch.empty((2,), device=p.device, dtype=torch.float32)
-    ws = torch.empty((b * k * 2,), device=p.device, dtype=torch.float32)
-    with torch.cuda.device(p.device):
-        check(lib.lpb_heatmap_mse_from_keypoints_fwd(_ptr(kp), _ptr(vis), _ptr(p), b * k, float(height), float(width), oh, ow, float(sigma), _ptr(out), _ptr(ws), _stream()))
-    return out[0]
+    return _HeatmapMseFromKeypoints.apply(kp, vis, p, float(height), float(width), float(sigma))
 
 
 def temporal_heatmap_loss(heatmaps, confidences, kind: str, epsilon: torch.Tensor, prob_threshold: float):

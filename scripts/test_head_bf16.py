@@ -36,9 +36,10 @@ for softmax in (0, 1):
     check(lib.lpb_head_fwd_bf16(p(args[0]), B, Cf, H, W, p(args[1]), p(args[2]), K, p(args[3]), p(args[4]), K, softmax, p(out), p(ws), None))
     torch.cuda.synchronize()
     nst = Cf // 4 // 32
-    mid = ws[(nst + 1) * 20480 :].view(torch.bfloat16).reshape(B, 4, 48 * 48, 8).permute(0, 1, 3, 2).reshape(B, 32, 48, 48).float().cpu()
+    zrow = (4 * W * 16 + 255) // 256 * 256
+    mid = ws[(nst + 1) * 20480 + zrow :].view(torch.bfloat16).reshape(B, 4, 48 * 48, 8).permute(0, 1, 3, 2).reshape(B, 32, 48, 48).float().cpu()
     e_mid = (mid[:, :K] - mid_ref).abs().max().item()
-    pad = mid[:, K:].abs().max().item()
+    pad = mid[:, K + 1 :].abs().max().item()  # channel K is the constant-one channel
     ref = hm_ref if softmax else logit_ref
     o = out.cpu()
     err = (o - ref).abs().max().item()

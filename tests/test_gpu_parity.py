@@ -444,3 +444,46 @@ def test_decode_multimodal_random_fields(lpb, dev):
     close(c, co, atol=2e-6)
     with pytest.raises(RuntimeError, match="field limit"):
         lpb.decode_softargmax(torch.rand(1, 1, 4, 300, device=dev), 2, 1000.0)
+
+
+def test_semisupervised_tracker_training_step(lpb, dev):
+    """Boundary row a7: the mirrored SemiSupervisedHeatmapTracker (backbone -> head -> decode -> remap -> loss
+    factories) against the oracle evaluated on the same backbone features; gradients reach the backbone."""
+    from lightning_pose_b200.losses.factory import LossFactory
+    from lightning_pose_b200.models.heatmap_tracker import SemiSupervisedHeatmapTracker
+
+    k = 5
+    sup = LossFactory({"heatmap_mse": {"log_weight": 0.0}}, None)
+    unsup = LossFactory({"temporal": {"log_weight": 1.0, "epsilon": 1.0, "prob_threshold": 0.0}}, None)
+    model = SemiSupervisedHeatmapTracker(k, loss_factory=sup, loss_factory_unsupervised=unsup, backbone="resnet18").to(dev)
+    for layer in list(model.head.upsampling_layers)[1:]:
+        torch.nn.init.xavier_uniform_(layer.weight, gain=3.0)
+    model.train(False)  # BN in eval mode: deterministic features
+    gen = torch.Generator().manual_seed(3)
+    imgs = torch.randn(4, 3, 64, 96, generator=gen)
+    frames = torch.randn(6, 3, 64, 96, generator=gen)
+    kps = torch.rand(4, k, 2, generator=gen) * torch.tensor([96.0, 64.0])
+    bbox_l = torch.tensor([[1.0, 2.0, 128.0, 192.0]]).repeat(4, 1)
+    bbox_u = torch.tensor([[0.0, 0.0, 64.0, 96.0]]).repeat(6, 1)
+    targ = O.gaussian_targets(kps, 64, 96, (16, 24))
+    batch = {
+        "labeled": {"images": imgs.to(dev), "keypoints": kps.reshape(4, -1).to(dev), "heatmaps": targ.to(dev), "bbox": bbox_l.to(dev)},
+        "unlabeled": {"frames": frames.to(dev), "transforms": torch.ones(1, device=dev), "bbox": bbox_u.to(dev), "is_multiview": False},
+    }
+    out = model.training_step(batch, 0)
+    out["loss"].backward()
+    assert model.backbone[0].weight.grad is not None and torch.isfinite(model.backbone[0].weight.grad).all()
+    with torch.no_grad():
+        fl = model.backbone(imgs.to(dev)).cpu()
+        fu = model.backbone(frames.to(dev)).cpu()
+    d = list(model.head.upsampling_layers)[1:]
+    ws, bs = [x.weight.detach().cpu() for x in d], [x.bias.detach().cpu() for x in d]
+    hl, hu = O.head_forward(fl, ws, bs), O.head_forward(fu, ws, bs)
+    ku, cu = O.decode_softargmax(hu, 2, 1000.0)
+    ku = O.model_to_frame(ku, bbox_u, 64, 96)
+    ref = 0.5 * O.heatmap_mse_loss(targ, hl) + O.loss_weight(1.0) * O.temporal_loss(ku, cu, 1.0, 0.0)
+    close(out["loss"], ref, atol=1e-5, rtol=2e-4)
+    pk, pc = model.predict_step(batch["unlabeled"], 0)
+    close(pk, ku, atol=2e-3, rtol=RTOL)
+    kl, _ = O.decode_softargmax(hl, 2, 1000.0)
+    close(model.last_rmse, O.model_to_frame(kl, bbox_l, 64, 96).sub(O.model_to_frame(kps.reshape(4, -1), bbox_l, 64, 96)).reshape(-1, 2).pow(2).mean(1).sqrt().mean(), atol=1e-3, rtol=1e-3)

@@ -77,3 +77,20 @@ def test_head_layer_count_rule(arch, ds, n):
     assert float(head.temperature) == 1000.0 and head.final_softmax is True
     assert head.upsampling_layers[1].weight.shape[:2] == (64, 17 if n == 1 else 17)
     assert float(head.upsampling_layers[1].bias.abs().max()) == 0.0
+
+
+def test_tracker_surface():
+    """tests/models/test_factory.py:142-155: tracker output keys are read from the TypedDict annotations."""
+    import typing
+
+    from lightning_pose_b200.models.heatmap_tracker import HeatmapTracker, SemiSupervisedHeatmapTracker
+
+    lab = typing.get_type_hints(HeatmapTracker.get_loss_inputs_labeled)["return"]
+    unl = typing.get_type_hints(SemiSupervisedHeatmapTracker.get_loss_inputs_unlabeled)["return"]
+    assert set(lab.__annotations__) == {"heatmaps_targ", "heatmaps_pred", "keypoints_targ", "keypoints_pred", "confidences"}
+    assert set(unl.__annotations__) == {"heatmaps_pred", "keypoints_pred", "keypoints_pred_augmented", "confidences"}
+    m = SemiSupervisedHeatmapTracker(17, backbone="resnet18")
+    assert [g["name"] for g in m.get_parameters()] == ["backbone", "head"] and m.get_parameters()[0]["lr"] == 0
+    assert m.num_targets == 34 and float(m.total_unsupervised_importance) == 1.0
+    sig = inspect.signature(HeatmapTracker.predict_step)
+    assert list(sig.parameters)[1:] == ["batch_dict", "batch_idx", "return_heatmaps"]
