@@ -36,6 +36,7 @@ struct DecodeParams {
   float* conf;
   float* stats;
   int h, w, pitch, padl, bulk;
+  int64_t n_planes;
   float T, lip, offset;
   float phase[F][W];  // interior rows (constant bank operands)
 };
@@ -105,24 +106,12 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
   uint64_t* bar = reinterpret_cast<uint64_t*>(redi + 112);
   unsigned* smask = reinterpret_cast<unsigned*>(redi + 48);  // [32] per-strip bitmask of active row chunks
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t plane = blockIdx.x;
-  const float* __restrict__ src = P.heat + plane * (size_t)h * w;
 
-  // ---- stage the plane: TMA bulk row copies into the zero-padded tile -------------------------
-  if (P.bulk) {
-    if (tid == 0) {
-      mbar_init(bar, 1);
-      fence_mbar_init();
-    }
-    __syncthreads();
-    if (warp == 0) {
-      if (lane == 0) mbar_expect_tx(bar, (uint32_t)(h * w * 4));
-      __syncwarp();
-      for (int a = lane; a < h; a += 32)
-        bulk_g2s(tile + (a + R) * pitch + padl, src + (size_t)a * w, (uint32_t)(w * 4), bar);
-    }
+  // ---- once per CTA: barrier + zero halo (the CTA is persistent; only the interior is rewritten) ----
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
   }
-  if (tid < 32) smask[tid] = 0u;
   for (int r = warp; r < h + 2 * R; r += DEC_WARPS) {
     float* row = tile + r * pitch;
     if (r < R || r >= h + R) {
@@ -130,13 +119,34 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
     } else {
       for (int b = lane; b < padl; b += 32) row[b] = 0.f;
       for (int b = padl + w + lane; b < pitch; b += 32) row[b] = 0.f;
-      if (!P.bulk) {
-        const float* g = src + (size_t)(r - R) * w;
-        for (int b = lane; b < w; b += 32) row[padl + b] = __ldg(g + b);
-      }
     }
   }
-  if (P.bulk) mbar_wait(bar, 0);
+  __syncthreads();
+
+  uint32_t tma_phase = 0;
+  for (size_t plane = blockIdx.x; plane < (size_t)P.n_planes; plane += gridDim.x) {
+  const float* __restrict__ src = P.heat + plane * (size_t)h * w;
+
+  // ---- stage the plane: TMA bulk row copies into the zero-padded tile -------------------------
+  if (P.bulk) {
+    if (warp == 0) {
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)(h * w * 4));
+      __syncwarp();
+      for (int a = lane; a < h; a += 32)
+        bulk_g2s(tile + (a + R) * pitch + padl, src + (size_t)a * w, (uint32_t)(w * 4), bar);
+    }
+  } else {
+    for (int r = warp; r < h; r += DEC_WARPS) {
+      const float* g = src + (size_t)r * w;
+      float* row = tile + (r + R) * pitch + padl;
+      for (int b = lane; b < w; b += 32) row[b] = __ldg(g + b);
+    }
+  }
+  if (tid < 32) smask[tid] = 0u;
+  if (P.bulk) {
+    mbar_wait(bar, tma_phase);
+    tma_phase ^= 1;
+  }
   __syncthreads();
 
   // ---- scan 1: arg max of |h|; each warp owns a band of rows, lanes read 4-column groups ------------
@@ -147,14 +157,28 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
   const int ab0 = warp * band, ab1 = min(h, ab0 + band);
   float best = -1.f;
   int bpos = 0;
-  for (int a = ab0; a < ab1; ++a) {
-    const float4* row4 = reinterpret_cast<const float4*>(tile + (a + R) * pitch + padl);
-    for (int b4 = lane; b4 < w4; b4 += 32) {
-      const float4 x = row4[b4];
+  if (w4 <= 32) {  // common case: one 16-byte group per lane and row, no inner loop
+    const float4* row4 = reinterpret_cast<const float4*>(tile + (ab0 + R) * pitch + padl) + (lane < w4 ? lane : 0);
+    const int pitch4 = pitch >> 2;
+    for (int a = ab0; a < ab1; ++a, row4 += pitch4) {
+      const float4 x = *row4;
       const float m4 = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
       if (m4 > best) {
         best = m4;
-        bpos = (a << 16) | b4;
+        bpos = a;
+      }
+    }
+    bpos = (bpos << 16) | (lane < w4 ? lane : 0);
+  } else {
+    for (int a = ab0; a < ab1; ++a) {
+      const float4* row4 = reinterpret_cast<const float4*>(tile + (a + R) * pitch + padl);
+      for (int b4 = lane; b4 < w4; b4 += 32) {
+        const float4 x = row4[b4];
+        const float m4 = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
+        if (m4 > best) {
+          best = m4;
+          bpos = (a << 16) | b4;
+        }
       }
     }
   }
@@ -438,6 +462,8 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
       st[7] = (float)B1;
     }
   }
+  __syncthreads();  // every read of the tile / scratch is done before the next plane is staged
+  }  // persistent plane loop
 }
 
 // d loss / d h = U_H^T G U_W with G[i,j] = T * p[i,j] * ((j - xhat) gx + (i - yhat) gy), p the
@@ -645,6 +671,7 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
   P.padl = dec_padl(G::R);
   P.pitch = dec_pitch(w, G::R);
   P.bulk = ((w % 4) == 0 && (reinterpret_cast<uintptr_t>(heat) % 16) == 0) ? 1 : 0;
+  P.n_planes = n_planes;
   P.T = T;
   P.lip = th->host.lip * tw->host.lip;
   P.offset = (DS == 1) ? 0.5f : (DS == 2 ? 1.5f : 2.5f);  // lightning_pose/models/heads/heatmap.py:131-136
@@ -659,7 +686,11 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
     return LPB_ERR_UNSUPPORTED;
   }
   LPB_CUDA(cudaFuncSetAttribute(decode_fwd_kernel<DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  decode_fwd_kernel<DS><<<(unsigned)n_planes, DEC_THREADS, smem, stream>>>(P);
+  int sms = 0, per_sm = 0;
+  LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  LPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_fwd_kernel<DS>, DEC_THREADS, smem));
+  const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);  // persistent CTAs: one wave
+  decode_fwd_kernel<DS><<<(unsigned)(n_planes < resident ? n_planes : resident), DEC_THREADS, smem, stream>>>(P);
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
 }

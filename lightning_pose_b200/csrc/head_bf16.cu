@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "../../include/lpb200.h"
 #include "lpb_common.cuh"
@@ -462,31 +463,36 @@ __global__ void __launch_bounds__(K1B_THREADS, 2) k1b_convt_softmax_kernel(const
             const bool valid = (ml < P.Hh) && (n < Wi);
             const int m = hf * P.Hh + ml;
             float* dst = P.out + ((size_t)b * P.c2 * Ho + 2 * m + e) * Wo + 2 * n;  // plane o adds o * Ho * Wo
+            auto planes = [&](auto ec) {  // compile-time class offset: no per-value selects
+              constexpr int E = decltype(ec)::value;
 #pragma unroll
-            for (int o = 0; o < HB_CLS; ++o) {
-              if (o >= P.c2) break;
-              const float l0 = e ? d[8 + o] : d[o], l1 = e ? d[8 + HB_CLS + o] : d[HB_CLS + o];
-              if (!write) {
-                const float mm = valid ? fmaxf(l0, l1) : -3.0e38f;
-                if (__any_sync(0xffffffffu, mm > mx[o])) {
-                  const float mn = fmaxf(mx[o], mm);
-                  sm[o] *= fast_exp2((mx[o] - mn) * L2E);
-                  mx[o] = mn;
+              for (int o = 0; o < HB_CLS; ++o) {
+                if (o >= P.c2) break;
+                const float l0 = d[8 * E + o], l1 = d[8 * E + HB_CLS + o];
+                if (!write) {
+                  const float mm = valid ? fmaxf(l0, l1) : -3.0e38f;
+                  if (__any_sync(0xffffffffu, mm > mx[o])) {
+                    const float mn = fmaxf(mx[o], mm);
+                    sm[o] *= fast_exp2((mx[o] - mn) * L2E);
+                    mx[o] = mn;
+                  }
+                  if (valid) {
+                    const float mL = mx[o] * L2E;
+                    sm[o] += fast_exp2(fmaf(l0, L2E, -mL)) + fast_exp2(fmaf(l1, L2E, -mL));
+                  }
+                } else if (valid) {
+                  float p0 = l0, p1 = l1;
+                  if (P.final_softmax) {
+                    const float mL = fin[o], inv = fin[HB_CLS + o];
+                    p0 = fast_exp2(fmaf(l0, L2E, -mL)) * inv;
+                    p1 = fast_exp2(fmaf(l1, L2E, -mL)) * inv;
+                  }
+                  *reinterpret_cast<float2*>(dst + (size_t)o * plane_stride) = make_float2(p0, p1);
                 }
-                if (valid) {
-                  const float mL = mx[o] * L2E;
-                  sm[o] += fast_exp2(fmaf(l0, L2E, -mL)) + fast_exp2(fmaf(l1, L2E, -mL));
-                }
-              } else if (valid) {
-                float p0 = l0, p1 = l1;
-                if (P.final_softmax) {
-                  const float mL = fin[o], inv = fin[HB_CLS + o];
-                  p0 = fast_exp2(fmaf(l0, L2E, -mL)) * inv;
-                  p1 = fast_exp2(fmaf(l1, L2E, -mL)) * inv;
-                }
-                *reinterpret_cast<float2*>(dst + (size_t)o * plane_stride) = make_float2(p0, p1);
               }
-            }
+            };
+            if (e == 0) planes(std::integral_constant<int, 0>{});
+            else planes(std::integral_constant<int, 1>{});
           }
           tc::fence_before_sync();
           tc::mbar_arrive(t_empty);

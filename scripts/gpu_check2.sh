@@ -3,6 +3,7 @@
 # Risky kernels first, under short timeouts: a hang costs ~2 minutes, not the whole budget.
 set -uo pipefail
 mkdir -p gpurun_out
+echo "== first-call timings"; timeout 300 python scripts/time_first_calls.py 2>&1 | tail -20 | tee gpurun_out/first_calls.log
 echo "== tcgen05 head bring-up"; HB_B=5 timeout 120 python scripts/test_head_bf16.py 2>&1 | tail -6 | tee gpurun_out/head_bf16.log
 if ! grep -q "RESULT PASS" gpurun_out/head_bf16.log || grep -q "RESULT FAIL" gpurun_out/head_bf16.log; then echo "ABORT: tcgen05 head failed or hung"; exit 1; fi
 echo "== pytest gpu"; timeout 400 python -m pytest tests -m gpu -x -q --durations=6 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
