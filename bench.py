@@ -154,10 +154,13 @@ def make_problem(n_clips: int, seed: int, device, regime: str = "trained"):
 # our arm
 # ------------------------------------------------------------------------------------------------
 class HotPath:
-    LAUNCHES_FWD = 4 + 1 + 2 + 1 + 1  # head(2 weight packs + k1a + k1b), decode, target+mse (2), remap, unsup
+    # our own kernel launches per step (library kernels of torch are not counted)
+    LAUNCHES_FWD = 4 + 1 + 2 + 1 + 1  # head (2 weight packs + k1a + k1b), decode, target+mse (2), remap, unsup losses
+    LAUNCHES_BWD = 1 + 1 + 1 + 1 + 1  # unsup bwd, remap bwd, decode bwd, target+mse bwd, plane-softmax bwd
 
-    def __init__(self, prob, device, fwd_only: bool):
+    def __init__(self, prob, device, fwd_only: bool, world: int = 1):
         from lightning_pose_b200 import ops
+        from lightning_pose_b200.ddp import FlatGradAllReducer
 
         self.ops, self.dev, self.fwd_only = ops, device, fwd_only
         self.n_clips = prob["n_clips"]
@@ -169,23 +172,33 @@ class HotPath:
         self.sv = ops.PcaParams(np.arange(K_PTS, dtype=np.int32), K_PTS, 0, None, prob["pca"]["mean"], prob["pca"]["kept"], prob["pca"]["eps"], device)
         self.teps = torch.full((K_PTS,), 20.0, device=device)
         self.w_unsup = 1.0 / (2.0 * np.exp(5.0))
+        if not fwd_only:
+            self.opt = torch.optim.Adam(self.head.parameters(), lr=1e-5, fused=True)
+            self.reducer = FlatGradAllReducer(self.head.parameters(), n_scalars=4) if world > 1 else None
 
     def step(self, feats: torch.Tensor):
         ops, n = self.ops, self.n_clips
-        f = feats if self.fwd_only else feats.requires_grad_(True)
+        nl = n * B_LABELED
+        if not self.fwd_only:
+            self.opt.zero_grad(set_to_none=True)
+            feats = feats.detach().requires_grad_(True)  # d loss / d features feeds the backbone's backward
         with torch.set_grad_enabled(not self.fwd_only):
-            hm = self.head(f)  # (n*48, 17, 96, 96)
-            hm_lab, hm_unl = hm[: n * B_LABELED], hm[n * B_LABELED :]
-            l_sup = ops.heatmap_mse_from_keypoints(self.kp_lab, hm_lab, IMG, IMG, visibility=self.vis) if self.fwd_only else \
-                ops.heatmap_loss(ops.generate_heatmaps(self.kp_lab, IMG, IMG, (HM, HM), visibility=self.vis), hm_lab, "mse")
+            hm = self.head(feats)  # (n*48, 17, 96, 96)
+            l_sup = ops.heatmap_mse_from_keypoints(self.kp_lab, hm[:nl], IMG, IMG, visibility=self.vis)
             kp, cf = ops.decode_softargmax(hm, 2, 1000.0)
-            kp_unl = ops.remap_keypoints(kp[n * B_LABELED :], self.tf, self.bbox, IMG, IMG)
-            per_clip = ops.unsup_losses(kp_unl.reshape(n, T_UNLABELED, 2 * K_PTS), cf[n * B_LABELED :].reshape(n, T_UNLABELED, K_PTS),
+            kp_unl = ops.remap_keypoints(kp[nl:], self.tf, self.bbox, IMG, IMG)
+            per_clip = ops.unsup_losses(kp_unl.reshape(n, T_UNLABELED, 2 * K_PTS), cf[nl:].reshape(n, T_UNLABELED, K_PTS),
                                         temporal_eps=self.teps, prob_threshold=0.05, pca_singleview=self.sv)
             total = 0.5 * l_sup + self.w_unsup * per_clip[:, :2].sum()
-            if not self.fwd_only:
-                total.backward()
-        return torch.stack([total.detach(), l_sup.detach(), per_clip[:, 0].mean().detach(), per_clip[:, 1].mean().detach()])
+        scalars = [total.detach(), l_sup.detach(), per_clip[:, 0].mean().detach(), per_clip[:, 1].mean().detach()]
+        if not self.fwd_only:
+            total.backward()
+            if self.reducer is not None:
+                return_scalars = self.reducer.step(scalars)  # ONE all-reduce: head gradients + logged scalars
+                self.opt.step()
+                return return_scalars
+            self.opt.step()
+        return torch.stack(scalars)
 
 
 def time_steps(fn, steps, warmup, barrier=None):
@@ -243,7 +256,7 @@ def run_ours(args):
     import lightning_pose_b200  # noqa: F401  (fails loudly without the CUDA library)
 
     prob = make_problem(args.clips, seed=1234 + rank, device=dev, regime=args.regime)
-    hp = HotPath(prob, dev, args.fwd_only)
+    hp = HotPath(prob, dev, args.fwd_only, world)
     tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     feats_host = prob["feats"].to(tdt).pin_memory()
     feats = feats_host.to(dev, non_blocking=True)
@@ -282,6 +295,11 @@ def run_ours(args):
         return
     pk, pk_src = peaks()
     br = kernel_breakdown(hp, feats)
+    fwd_only_value = None
+    if not args.fwd_only:
+        hp_fwd = HotPath(prob, dev, True)
+        ms_f = time_steps(lambda: hp_fwd.step(feats), args.steps, 2)
+        fwd_only_value = {"value": n_frames * args.steps / (ms_f / 1e3), "unit": "frames/s", "ms_per_step": ms_f / args.steps}
     flat = None
     if not args.no_flat:
         # secondary regime: the reference's own initialiser (xavier gain 0.01) on randn features -> flat heatmaps ->
@@ -302,22 +320,25 @@ def run_ours(args):
         "dtype": args.dtype, "data": "synthetic",
         "config": {
             "workload": f"BASELINE configs[1] hot path on ResNet-50 features (B,2048,12,12): {args.clips} clips/step/GPU x (16 labeled + 32 unlabeled) frames, "
-                        f"K=17, heatmaps 96x96, decode field 384x384; pass = {'forward' if args.fwd_only else 'forward+backward'}",
+                        f"K=17, heatmaps 96x96, decode field 384x384; pass = {'forward' if args.fwd_only else 'forward + backward + Adam step on the head (+ one flat all-reduce when N>1)'}",
+            "backward": "native kernels: loss stack, remap, soft-argmax decode, target+mse, plane softmax; torch library (cuDNN): dgrad/wgrad of the two transposed convolutions (interim, DESIGN.md 7)",
             "frames_per_step_per_gpu": n_frames, "regime": ("trained-like synthetic response (unimodal Gaussian-like heatmaps; planted features + bilinear per-keypoint deconvs, see bench.make_problem); fresh_init_regime = reference initialiser"
                                                                                   if args.regime == "trained" else "fresh init (reference initialiser, flat heatmaps)"),
             "l2_policy": f"inputs larger than L2 ({feats.numel() * esz / 2**20:.0f} MiB of features per step)", "parallelism": f"dp{world}",
         },
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": feats.numel() * esz, "d2h_bytes_per_step": 16},
-        "gpu_launches": HotPath.LAUNCHES_FWD * args.steps if args.fwd_only else None,
+        "gpu_launches": (HotPath.LAUNCHES_FWD + (0 if args.fwd_only else HotPath.LAUNCHES_BWD)) * args.steps,
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": br[dom]["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": br[dom]["gbs"] / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src},
         "stages": {k: {"ms": round(v["ms"], 4), "GBps": round(v["gbs"], 1), "frac_hbm": round(v["gbs"] / pk["hbm_gbs"], 4)} for k, v in br.items()},
     }
+    if fwd_only_value is not None:
+        line["forward_only"] = fwd_only_value
     if flat is not None:
         line["fresh_init_regime"] = flat
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference(seed=1234, clips=1, reps=1)
+        line["cpu_baseline"] = cpu_reference(seed=1234, clips=1, reps=1, train=not args.fwd_only)
     print(json.dumps(line))
     if dist:
         dist.barrier()
@@ -327,13 +348,21 @@ def run_ours(args):
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU oracle (restated reference path) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step(prob):
+def cpu_threads() -> int:
+    """torch CPU ops on these small tensors stop scaling (and regress) beyond ~32 threads; override with LPB_CPU_THREADS."""
+    return int(os.environ.get("LPB_CPU_THREADS", min(os.cpu_count() or 1, 32)))
+
+
+def cpu_step(prob, train: bool = True):
+    """The same step on the CPU oracle (restated reference path): forward, and with ``train`` the autograd
+    backward into the features and the head parameters (the reference trains through exactly these torch ops)."""
     from oracle import lp_oracle as O
 
     n = prob["n_clips"]
     deconvs = list(prob["head"].upsampling_layers)[1:]
-    with torch.no_grad():
-        hm = O.head_forward(prob["feats"], [d.weight for d in deconvs], [d.bias for d in deconvs])
+    feats = prob["feats"].detach().requires_grad_(train)
+    with torch.set_grad_enabled(train):
+        hm = O.head_forward(feats, [d.weight for d in deconvs], [d.bias for d in deconvs])
         targ = O.gaussian_targets(prob["kp_lab"], IMG, IMG, (HM, HM), visibility=prob["vis"])
         l_sup = O.heatmap_mse_loss(targ, hm[: n * B_LABELED])
         kp, cf = O.decode_softargmax(hm, 2, 1000.0)
@@ -341,18 +370,22 @@ def cpu_step(prob):
         tot = 0.5 * l_sup
         for c in range(n):
             sl = slice(c * T_UNLABELED, (c + 1) * T_UNLABELED)
-            tot = tot + (O.temporal_loss(kp_unl[sl], cf[n * B_LABELED :][sl], 20.0, 0.05)
+            tot = tot + (O.temporal_loss(kp_unl[sl], cf[n * B_LABELED :][sl].detach(), 20.0, 0.05)
                          + O.pca_loss(O.pca_format_singleview(kp_unl[sl]), prob["pca"]["mean"], prob["pca"]["kept"], prob["pca"]["eps"])) / (2.0 * np.exp(5.0))
-    return tot
+    if train:
+        for d in deconvs:
+            d.weight.grad = d.bias.grad = None
+        tot.backward()
+    return tot.detach()
 
 
-def cpu_reference(seed, clips, reps):
-    torch.set_num_threads(os.cpu_count() or 1)
+def cpu_reference(seed, clips, reps, train=True):
+    torch.set_num_threads(cpu_threads())
     prob = make_problem(clips, seed=seed, device="cpu", regime="trained")
-    cpu_step(prob)  # warm-up
+    cpu_step(prob, train)  # warm-up
     t0 = time.perf_counter()
     for _ in range(reps):
-        cpu_step(prob)
+        cpu_step(prob, train)
     dt = (time.perf_counter() - t0) / reps
     frames = clips * (B_LABELED + T_UNLABELED)
     model = "?"
@@ -361,28 +394,29 @@ def cpu_reference(seed, clips, reps):
     except Exception:
         pass
     return {"value": frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{clips} clip(s) = {frames} frames of the same workload, forward pass, torch CPU oracle (oracle/lp_oracle.py), {model}",
+            "sample": f"{clips} clip(s) = {frames} frames of the same workload, {'forward+backward' if train else 'forward'} pass, torch CPU oracle (oracle/lp_oracle.py), {model}",
             "seconds_per_sample": dt}
 
 
 def run_reference(args):
     if int(os.environ.get("RANK", 0)) != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     clips = 1
     prob = make_problem(clips, seed=1234, device="cpu", regime=args.regime)
+    train = not args.fwd_only
     for _ in range(min(args.warmup, 1)):
-        cpu_step(prob)
+        cpu_step(prob, train)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(prob)
+        cpu_step(prob, train)
     dt = time.perf_counter() - t0
     frames = clips * (B_LABELED + T_UNLABELED)
     value = frames * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1] hot path, bounded sample: {clips} clip/step x (16 labeled + 32 unlabeled) frames, forward pass, CPU"},
+        "config": {"workload": f"BASELINE configs[1] hot path, bounded sample: {clips} clip/step x (16 labeled + 32 unlabeled) frames, {'forward+backward' if train else 'forward'} pass, CPU"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{frames} frames/step, torch CPU restatement of the reference path (oracle/lp_oracle.py)"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -400,7 +434,7 @@ def main():
     ap.add_argument("--regime", default="trained", choices=["trained", "fresh"], help="synthetic input regime (see make_problem)")
     ap.add_argument("--dtype", default="bf16", choices=["f32", "bf16"], help="feature dtype (bf16 = tcgen05 head)")
     ap.add_argument("--no-flat", action="store_true", help="skip the secondary fresh-init (flat heatmap) regime")
-    ap.add_argument("--fwd-only", action="store_true", default=True)
+    ap.add_argument("--fwd-only", action="store_true", help="time the forward pass only (default: full training step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

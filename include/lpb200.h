@@ -118,6 +118,16 @@ int lpb_remap_keypoints(const float* keypoints_in, int64_t n, int K, const float
                         int per_frame, int num_views, const float* bbox, int64_t n_bbox,
                         float model_height, float model_width, float* keypoints_out, void* stream);
 
+/* gradient of lpb_remap_keypoints wrt keypoints_in (a linear map: transpose of the same transform) */
+int lpb_remap_keypoints_bwd(const float* grad_out, int64_t n, int K, const float* transforms, int per_frame,
+                            int num_views, const float* bbox, int64_t n_bbox, float model_height, float model_width,
+                            float* grad_in, void* stream);
+
+/* backward of the head's final spatial softmax: grad_logits = p * (g - sum(g * p)) per plane
+ * (reference: autograd of spatial_softmax2d, lightning_pose/models/heads/heatmap.py:211) */
+int lpb_plane_softmax_bwd(const float* probs, const float* grad_probs, int64_t n_planes, int hw, float* grad_logits,
+                          void* stream);
+
 /* ---- heatmap losses ---------------------------------------------------------------------------
  * replaces HeatmapMSELoss / HeatmapKLLoss / HeatmapJSLoss (remove_nans + compute_loss + mean)
  *   lightning_pose/losses/losses.py:229-289, :314-335, :360-378, :404-423

@@ -266,6 +266,53 @@ __global__ void remap_kernel(const float* __restrict__ in, int64_t n, int K, con
   out[2 * idx + 1] = (y * inv_mh) * bb[2] + bb[1];
 }
 
+
+// backward of remap_kernel: out = S * A^-1 (p - t) + b  =>  d/dp = (A^-1)^T S g
+__global__ void remap_bwd_kernel(const float* __restrict__ gout, int64_t n, int K, const float* __restrict__ tf,
+                                 int per_frame, int num_views, const float* __restrict__ bbox, int bbox_row_off,
+                                 float inv_mh, float inv_mw, float* __restrict__ gin) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * K) return;
+  const int64_t f = idx / K;
+  const int k = (int)(idx - f * K);
+  const int per = K / num_views;
+  const int v = min(k / per, num_views - 1);
+  const float* bb = bbox + (f + bbox_row_off) * (int64_t)(4 * num_views) + 4 * v;
+  float gx = gout[2 * idx] * inv_mw * bb[3], gy = gout[2 * idx + 1] * inv_mh * bb[2];
+  if (tf) {
+    const float* m = tf + (per_frame ? f * 6 : (num_views > 1 ? (int64_t)v * 6 : 0));
+    const float a = m[0], b = m[1], c = m[3], d = m[4];
+    const float idet = 1.0f / (a * d - b * c);
+    // A^-1 = idet * [[d, -b], [-c, a]];  transpose applied to (gx, gy)
+    const float ox = (d * gx - c * gy) * idet;
+    const float oy = (-b * gx + a * gy) * idet;
+    gx = ox;
+    gy = oy;
+  }
+  gin[2 * idx] = gx;
+  gin[2 * idx + 1] = gy;
+}
+
+// plane softmax backward: out = p * (g - sum(g * p)) per plane; one HBM read of p and g, one write
+__global__ void __launch_bounds__(HL_THREADS) plane_softmax_bwd_kernel(const float* __restrict__ p,
+                                                                       const float* __restrict__ g, int hw,
+                                                                       float* __restrict__ out) {
+  extern __shared__ float sm[];  // pp[hw], gg[hw]
+  __shared__ float red[HL_THREADS / 32];
+  float* pp = sm;
+  float* gg = sm + hw;
+  const size_t base = (size_t)blockIdx.x * hw;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < hw; i += HL_THREADS) {
+    const float a = __ldg(p + base + i), b = __ldg(g + base + i);
+    pp[i] = a;
+    gg[i] = b;
+    acc = fmaf(a, b, acc);
+  }
+  const float dot = block_sum_256(acc, red);
+  for (int i = threadIdx.x; i < hw; i += HL_THREADS) out[base + i] = pp[i] * (gg[i] - dot);
+}
+
 // ---- unsupervised losses on (T, K, 2) ------------------------------------------------------------
 struct PcaDev {
   const int32_t* kp_index;
@@ -727,6 +774,39 @@ extern "C" int lpb_heatmap_mse_from_keypoints_bwd(const float* keypoints, const 
   heatmap_mse_from_kp_bwd_kernel<<<(unsigned)n_planes, HL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       keypoints, visibility, preds, (float)((double)ow / (double)img_width), (float)((double)oh / (double)img_height), oh,
       ow, (float)(2.0 * (double)sigma * (double)sigma), fwd_out, grad_out, grad_preds);
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}
+
+extern "C" int lpb_remap_keypoints_bwd(const float* grad_out, int64_t n, int K, const float* transforms, int per_frame,
+                                       int num_views, const float* bbox, int64_t n_bbox, float model_height,
+                                       float model_width, float* grad_in, void* stream) {
+  using namespace lpb;
+  LPB_REQUIRE(grad_out && grad_in && bbox, "remap_keypoints_bwd: null pointer");
+  LPB_REQUIRE(n >= 0 && K >= 1 && num_views >= 1 && K % num_views == 0, "remap_keypoints_bwd: bad shape");
+  LPB_REQUIRE(n_bbox == n || n_bbox == n + 4, "remap_keypoints_bwd: bbox rows %lld vs %lld frames", (long long)n_bbox,
+              (long long)n);
+  if (n == 0) return LPB_OK;
+  const int64_t total = n * K;
+  remap_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      grad_out, n, K, transforms, per_frame, num_views, bbox, n_bbox == n ? 0 : 2, 1.0f / model_height, 1.0f / model_width,
+      grad_in);
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}
+
+extern "C" int lpb_plane_softmax_bwd(const float* probs, const float* grad_probs, int64_t n_planes, int hw,
+                                     float* grad_logits, void* stream) {
+  using namespace lpb;
+  LPB_REQUIRE(probs && grad_probs && grad_logits, "plane_softmax_bwd: null pointer");
+  LPB_REQUIRE(n_planes >= 0 && n_planes < (1ll << 31) && hw >= 1, "plane_softmax_bwd: bad shape");
+  if (n_planes == 0) return LPB_OK;
+  const size_t smem = (size_t)2 * hw * sizeof(float);
+  LPB_REQUIRE(smem <= 200 * 1024, "plane_softmax_bwd: plane of %d pixels too large", hw);
+  if (smem > 48 * 1024)
+    LPB_CUDA(cudaFuncSetAttribute(plane_softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  plane_softmax_bwd_kernel<<<(unsigned)n_planes, HL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(probs, grad_probs, hw,
+                                                                                                      grad_logits);
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
 }

@@ -81,7 +81,7 @@ class _HeadFunction(torch.autograd.Function):
         weights, biases = params[:n], params[n:]
         g = g.contiguous().float()
         if ctx.final_softmax:  # d softmax: p * (g - sum(g * p)) per plane
-            g = out * (g - (g * out).sum(dim=(2, 3), keepdim=True))
+            g = ops.plane_softmax_backward(out, g)
         # interim: transposed-conv dgrad/wgrad through the framework's conv ops ("backward")
         cdt = torch.bfloat16 if features.dtype == torch.bfloat16 else torch.float32  # same precision as the forward
         with torch.enable_grad():

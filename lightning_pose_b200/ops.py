@@ -224,8 +224,33 @@ def head_forward(features, weights, biases, final_softmax=True):
 # =====================================================================================
 # coordinate remap
 # =====================================================================================
+class _Remap(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kp, tf, per_frame, num_views, bb, model_height, model_width, out):
+        n, k2 = kp.shape
+        res = out if out is not None else torch.empty_like(kp)
+        with torch.cuda.device(kp.device):
+            check(lib.lpb_remap_keypoints(_ptr(kp), n, k2 // 2, _ptr(tf), per_frame, num_views, _ptr(bb), bb.shape[0], model_height, model_width, _ptr(res), _stream()))
+        ctx.save_for_backward(tf, bb)
+        ctx.meta = (per_frame, num_views, model_height, model_width)
+        if out is not None:
+            ctx.mark_dirty(out)
+        return res
+
+    @staticmethod
+    def backward(ctx, g):
+        tf, bb = ctx.saved_tensors
+        per_frame, num_views, mh, mw = ctx.meta
+        g = g.contiguous().float()
+        n, k2 = g.shape
+        gi = torch.empty_like(g)
+        with torch.cuda.device(g.device):
+            check(lib.lpb_remap_keypoints_bwd(_ptr(g), n, k2 // 2, _ptr(tf), per_frame, num_views, _ptr(bb), bb.shape[0], mh, mw, _ptr(gi), _stream()))
+        return gi, None, None, None, None, None, None, None
+
+
 def remap_keypoints(keypoints, transforms, bbox, model_height, model_width, is_multiview=False, num_views=1, out=None):
-    """undo_affine_transform_batch + model_to_frame_batch in one launch (forward; linear map)."""
+    """undo_affine_transform_batch + model_to_frame_batch in one launch; differentiable in ``keypoints``."""
     kp = _cuda_f32(keypoints, "keypoints")
     n, k2 = kp.shape
     tf = None
@@ -237,10 +262,19 @@ def remap_keypoints(keypoints, transforms, bbox, model_height, model_width, is_m
             if tf.shape[0] != n:
                 raise ValueError(f"per-frame transforms {tuple(tf.shape)} vs {n} frames")
     bb = _cuda_f32(bbox, "bbox")
-    res = out if out is not None else torch.empty_like(kp)
-    with torch.cuda.device(kp.device):
-        check(lib.lpb_remap_keypoints(_ptr(kp), n, k2 // 2, _ptr(tf), per_frame, int(num_views), _ptr(bb), bb.shape[0], float(model_height), float(model_width), _ptr(res), _stream()))
-    return res
+    if out is not None and kp.requires_grad:
+        out = None  # writing through a tensor that autograd tracks is not allowed; return a fresh one
+    return _Remap.apply(kp, tf, per_frame, int(num_views), bb, float(model_height), float(model_width), out)
+
+
+def plane_softmax_backward(probs: torch.Tensor, grad_probs: torch.Tensor) -> torch.Tensor:
+    p = _cuda_f32(probs, "probs")
+    g = _cuda_f32(grad_probs, "grad_probs")
+    b, k, h, w = p.shape
+    out = torch.empty_like(p)
+    with torch.cuda.device(p.device):
+        check(lib.lpb_plane_softmax_bwd(_ptr(p), _ptr(g), b * k, h * w, _ptr(out), _stream()))
+    return out
 
 
 # =====================================================================================

@@ -487,3 +487,22 @@ def test_semisupervised_tracker_training_step(lpb, dev):
     close(pk, ku, atol=2e-3, rtol=RTOL)
     kl, _ = O.decode_softargmax(hl, 2, 1000.0)
     close(model.last_rmse, O.model_to_frame(kl, bbox_l, 64, 96).sub(O.model_to_frame(kps.reshape(4, -1), bbox_l, 64, 96)).reshape(-1, 2).pow(2).mean(1).sqrt().mean(), atol=1e-3, rtol=1e-3)
+
+
+def test_remap_and_fused_mse_backward(lpb, dev, golden):
+    g = golden("remap")
+    kp0 = T(g["in_keypoints"])
+    tf, bbox = T(g["in_transform_perframe"]), T(g["in_bbox"])
+    wgt = torch.randn(kp0.shape, generator=torch.Generator().manual_seed(1))
+    ref = kp0.clone().requires_grad_(True)
+    (O.model_to_frame(O.undo_affine(ref, tf), bbox, 128, 256) * wgt).sum().backward()
+    x = kp0.to(dev).requires_grad_(True)
+    (lpb.remap_keypoints(x, tf.to(dev), bbox.to(dev), 128, 256) * wgt.to(dev)).sum().backward()
+    close(x.grad, ref.grad, atol=1e-6, rtol=1e-4)
+    gl = golden("losses")
+    kp, vis, pred = T(gl["hmb_in_kp"]), T(gl["hmb_in_vis"]), T(gl["hmb_in_pred"])
+    pr = pred.clone().requires_grad_(True)
+    (O.heatmap_mse_loss(O.gaussian_targets(kp, 128, 128, (32, 32), visibility=vis), pr) * 1.3).backward()
+    p = pred.to(dev).requires_grad_(True)
+    (lpb.heatmap_mse_from_keypoints(kp.to(dev), p, 128, 128, visibility=vis.to(dev)) * 1.3).backward()
+    close(p.grad, pr.grad, atol=1e-8, rtol=1e-3)
