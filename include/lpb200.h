@@ -193,6 +193,12 @@ int lpb_unsup_losses_bwd(const float* keypoints, const float* confidences, int64
                          const lpb_pca_desc* pca_singleview, const lpb_pca_desc* pca_multiview,
                          const float* grad_out, float* grad_keypoints, void* stream);
 
+/* ---- diagnostics ------------------------------------------------------------------------------
+ * UMMA descriptor self-test (tests only): one-CTA GEMM over operands in the library's row layout
+ * [kchunk][row][8] bf16; mode 0 = K-major view, 1 = MN-major view; d [128][n] fp32. */
+int lpb_selftest_umma(const void* a, int kca, int rows_a, const void* b, int kcb, int rows_b, int mode, int n, int k,
+                      int row_shift, int col_off, float* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
