@@ -104,8 +104,22 @@ int lpb_head_fwd_f32(const float* features, int B, int C, int H, int W, const fl
  * build's tiling (callers then use lpb_head_fwd_f32 on up-cast features). */
 int lpb_head_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes);
 int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int W, const float* w1, const float* b1, int c1,
-                      const float* w2, const float* b2, int c2, int final_softmax, float* out, void* workspace,
-                      void* stream);
+                      const float* w2, const float* b2, int c2, int final_softmax, float* out, void* saved_xs,
+                      void* workspace, void* stream);
+/* saved_xs: NULL for inference.  For training pass a device buffer of the same byte size as `features`; it
+ * receives the pixel-shuffled features in the row layout the weight-gradient GEMM reads, and must stay alive
+ * (together with `workspace`, which holds the activations between the two deconvs) until lpb_head_bwd_bf16. */
+
+/* backward of lpb_head_fwd_bf16 (replaces autograd through heatmap.py:203-212; four tcgen05 kernels:
+ * layer-2 wgrad, layer-2 dgrad, layer-1 wgrad, layer-1 dgrad + inverse PixelShuffle).
+ * g_logits [B, c2, 8H, 8W] fp32: gradient at the output of the second deconv (after lpb_plane_softmax_bwd
+ *   when the head ends in a softmax).
+ * dfeat [B, C, H, W] bf16 or NULL (frozen backbone); dw1 [C/4, c1, 3, 3], db1 [c1], dw2 [c1, c2, 3, 3],
+ * db2 [c2] fp32 (overwritten).  workspace: lpb_head_bwd_bf16_workspace_bytes(). */
+int lpb_head_bwd_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes);
+int lpb_head_bwd_bf16(const float* g_logits, const void* saved_xs, const void* fwd_workspace, int B, int C, int H,
+                      int W, const float* w1, int c1, const float* w2, int c2, void* dfeat, float* dw1, float* db1,
+                      float* dw2, float* db2, void* workspace, void* stream);
 
 /* ---- coordinate remap -------------------------------------------------------------------------
  * replaces undo_affine_transform_batch + model_to_frame_batch

@@ -97,6 +97,7 @@ struct K1aParams {
   const __nv_bfloat16* wpk;   // packed weights [nstages][HB_BSTAGE_BYTES]
   const float* bias;          // [c1]
   __nv_bfloat16* mid;         // [B][4][4*Hi*Wi][8]  (A layout of the next layer, no halo)
+  __nv_bfloat16* xs;          // optional [B][C/32][Hi*Wi][8]: shuffled features in row layout, kept for the weight gradient
   int B, C, HW, W;            // feature geometry (C = 4 * Cin)
   int c1, nstages;
   HeadGeom g;
@@ -176,6 +177,11 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
       mbar_wait(&raw_full[r], (it / K1A_RSTAGES) & 1);
       mbar_wait(&empty[s], ((it / K1A_ASTAGES) & 1) ^ 1);
       unsigned char* As = stage_base + s * stage_bytes;
+      __nv_bfloat16* xs_st = nullptr;  // this (frame, stage)'s 4 K-chunks of the saved copy
+      if (P.xs) {
+        const int b = blockIdx.x + (it / P.nstages) * gridDim.x, st = it % P.nstages;
+        xs_st = P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)(g.Hi * g.Wi) * 8;
+      }
       const unsigned char* raw = raw_base + r * raw_bytes;
       for (int task = tid; task < ntasks; task += 128) {
         const int sc = task % nchunk;
@@ -203,6 +209,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
             const int i = sp / P.W, jc = sp - i * P.W;
             const int row = (2 * i + di) * g.P + (2 * jc + dj);
             *reinterpret_cast<uint4*>(As + ((size_t)kc * g.rows_alloc + row) * 16) = o;
+            if (xs_st) *reinterpret_cast<uint4*>(xs_st + ((size_t)kc * (g.Hi * g.Wi) + (2 * i + di) * g.Wi + (2 * jc + dj)) * 8) = o;
           }
         }
       }
@@ -561,8 +568,8 @@ extern "C" int lpb_head_bf16_workspace_bytes(int B, int C, int H, int W, int c1,
 }
 
 extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int W, const float* w1, const float* b1, int c1,
-                                 const float* w2, const float* b2, int c2, int final_softmax, float* out, void* workspace,
-                                 void* stream) {
+                                 const float* w2, const float* b2, int c2, int final_softmax, float* out, void* saved_xs,
+                                 void* workspace, void* stream) {
   using namespace lpb;
   LPB_REQUIRE(features && w1 && b1 && w2 && b2 && out && workspace, "head_fwd_bf16: null pointer");
   LPB_REQUIRE(B >= 0 && C >= 128 && C % 128 == 0 && H >= 1 && W >= 1, "head_fwd_bf16: bad feature shape C=%d H=%d W=%d", C, H, W);
@@ -600,6 +607,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   pa.wpk = wp1;
   pa.bias = b1;
   pa.mid = mid;
+  pa.xs = static_cast<__nv_bfloat16*>(saved_xs);
   pa.B = B;
   pa.C = C;
   pa.HW = H * W;

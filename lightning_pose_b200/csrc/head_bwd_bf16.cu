@@ -1,0 +1,677 @@
+// Backward of the bf16 heatmap head on tcgen05 (data gradients), mirroring head_bf16.cu.
+// Reference: autograd of lightning_pose/models/heads/heatmap.py:203-212 (PixelShuffle + 2 x ConvTranspose2d).
+//
+// Gradients travel in the "class-major row layout"  G[b][kchunk = k/8][row = m*Wi + n][8] bf16  with
+// k = cls*20 + o, cls = (py, px): row (m, n) carries, for every output class and channel, the gradient at
+// output pixel (2m+py, 2n+px).  In this layout the data gradient of a stride-2 3x3 transposed convolution
+//   d in[c, m', n'] = sum_{cls, (dm,dn) valid} G[(m'-dm, n'-dn)][(cls, o)] * W[c, o, ky, kx]
+// is again a 4-shift GEMM (negative row shifts of the same smem operand, tcgen05.cuh), K = 80:
+//   b2d: G2 (48x48 rows)  x W2  -> d mid (48x48 x 17)  written straight into G1 (24x24 rows) for the next stage
+//   b3a: W1 (M = 128 channels) x G1^T -> d Xs[c][row]   un-shuffled in the epilogue into d features (NCHW bf16)
+#include <cuda_bf16.h>
+
+#include <cstdint>
+
+#include "../../include/lpb200.h"
+#include "lpb_common.cuh"
+#include "tcgen05.cuh"
+
+namespace lpb {
+
+constexpr int GB_CLS = 20;            // class stride in K
+constexpr int GB_K = 4 * GB_CLS;      // 80
+constexpr int GB_KC = GB_K / 8;       // 10 K-chunks
+
+// ---- g_logits (fp32, NCHW) -> G2 row layout (bf16) ------------------------------------------------------
+// one CTA per (frame, m); thread n handles the 2x2 output block of row (m, n) for all channels
+__global__ void __launch_bounds__(64) g_relayout_kernel(const float* __restrict__ gl, int B, int C, int Hi, int Wi,
+                                                        __nv_bfloat16* __restrict__ G) {
+  const int b = blockIdx.x / Hi, m = blockIdx.x - b * Hi;
+  const int Wo = 2 * Wi, Ho = 2 * Hi;
+  for (int n = threadIdx.x; n < Wi; n += blockDim.x) {
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      float v0[GB_CLS], v1[GB_CLS];
+#pragma unroll
+      for (int o = 0; o < GB_CLS; ++o) {
+        float2 t = make_float2(0.f, 0.f);
+        if (o < C) t = __ldg(reinterpret_cast<const float2*>(gl + (((size_t)b * C + o) * Ho + 2 * m + py) * Wo + 2 * n));
+        v0[o] = t.x;
+        v1[o] = t.y;
+      }
+      // k = (2*py + px) * 20 + o : 40 consecutive k values = K-chunks 5py .. 5py+4
+#pragma unroll
+      for (int ch = 0; ch < 5; ++ch) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const int k0 = ch * 8 + 2 * e2, k1 = k0 + 1;  // 0..39 within this py
+          const float f0 = k0 < GB_CLS ? v0[k0] : v1[k0 - GB_CLS];
+          const float f1 = k1 < GB_CLS ? v0[k1] : v1[k1 - GB_CLS];
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+          pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(G + ((((size_t)b * GB_KC + 5 * py + ch) * Hi * Wi) + (size_t)m * Wi + n) * 8) =
+            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+}
+
+// ---- weight packing for the data-gradient GEMMs ----------------------------------------------------------
+// out[tile][shift][kchunk][r][8]: element (r, k) = W[tile*rows_per_tile + r][o][ky][kx] for k = cls*20 + o when
+// (cls, shift) is a valid tap, else 0.  rows_per_tile = 32 (layer 2, N operand) or 128 (layer 1, M operand).
+__global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, int Cin, int Cout, int ntiles, int rows_per_tile,
+                                          __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ zero, int nzero) {
+  const int total = ntiles * 4 * GB_KC * rows_per_tile * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7;
+    int r = i >> 3;
+    const int row = r % rows_per_tile;
+    r /= rows_per_tile;
+    const int kc = r % GB_KC;
+    r /= GB_KC;
+    const int sh = r & 3;
+    const int tile = r >> 2;
+    const int c = tile * rows_per_tile + row;
+    const int k = kc * 8 + e;
+    const int cls = k / GB_CLS, o = k % GB_CLS;
+    const int py = cls >> 1, px = cls & 1, dm = sh >> 1, dn = sh & 1;
+    float v = 0.f;
+    if (c < Cin && o < Cout && !(py == 0 && dm == 1) && !(px == 0 && dn == 1)) {
+      const int ky = py == 0 ? 1 : (dm ? 0 : 2);
+      const int kx = px == 0 ? 1 : (dn ? 0 : 2);
+      v = w[((size_t)c * Cout + o) * 9 + ky * 3 + kx];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x) zero[i] = __float2bfloat16_rn(0.f);
+}
+
+// =====================================================================================================
+// b2d: data gradient of the second deconv:  G2 -> d mid, emitted as G1 (+ bias gradient of layer 1)
+// =====================================================================================================
+constexpr int B2D_THREADS = 192;  // warp 0 loader, warp 1 MMA, warps 2-5 epilogue
+constexpr int B2D_ROWS = 7;       // image rows per chunk (7 * 49 = 343 raster rows -> 3 M-tiles)
+constexpr int B2D_TILES = 3;
+
+struct B2dParams {
+  const __nv_bfloat16* G2;    // [B][10][Hi*Wi][8]
+  const __nv_bfloat16* zrow;  // Wi*8 zeros
+  const __nv_bfloat16* wpk;   // [4][10][32][8]
+  __nv_bfloat16* G1;          // [B][10][(Hi/2)*(Wi/2)][8]
+  float* db1;                 // [c1] accumulated with atomics (pre-zeroed)
+  int B, Hi, Wi, c1;
+};
+
+__global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_constant__ B2dParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int Wi = P.Wi, Hi = P.Hi, Pp = Wi + 1;
+  const int LEAD = Pp + 1;  // one zero row + the previous image row
+  const int rows_alloc = (LEAD + B2D_TILES * 128 + 7) & ~7;
+  const int a_bytes = GB_KC * rows_alloc * 16;
+  const int w_bytes = 4 * GB_KC * 32 * 16;
+  unsigned char* As = smem;
+  unsigned char* Ws = smem + a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ws + w_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* w_full = bars + 2;
+  uint64_t* t_full = bars + 3;
+  uint64_t* t_empty = bars + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < a_bytes / 16; i += B2D_THREADS) reinterpret_cast<uint4*>(As)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    mbar_init(w_full, 1);
+    mbar_init(t_full, 1);
+    mbar_init(t_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, 128);
+  fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int nchunk = (Hi + B2D_ROWS - 1) / B2D_ROWS;
+  const int npix = Hi * Wi, npix1 = (Hi / 2) * (Wi / 2);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)w_bytes);
+      bulk_g2s(Ws, P.wpk, (uint32_t)w_bytes, w_full);
+    }
+    int it = 0;
+    for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+      for (int ck = 0; ck < nchunk; ++ck, ++it) {
+        const int y0 = ck * B2D_ROWS;
+        mbar_wait(a_empty, (it & 1) ^ 1);
+        if (lane == 0) mbar_expect_tx(a_full, (uint32_t)(GB_KC * (B2D_ROWS + 1) * Wi * 16));
+        __syncwarp();
+        for (int i = lane; i < GB_KC * (B2D_ROWS + 1); i += 32) {
+          const int kc = i / (B2D_ROWS + 1), yl = i - kc * (B2D_ROWS + 1);  // yl = 0 is the previous image row
+          const int y = y0 - 1 + yl;
+          const __nv_bfloat16* srcp =
+              (y >= 0 && y < Hi) ? P.G2 + (((size_t)b * GB_KC + kc) * npix + (size_t)y * Wi) * 8 : P.zrow;
+          bulk_g2s(As + ((size_t)kc * rows_alloc + 1 + (size_t)yl * Pp) * 16, srcp, (uint32_t)(Wi * 16), a_full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = tc::make_idesc_bf16_f32(128, 32);
+    const uint32_t lbo_a = rows_alloc * 16, lbo_b = 32 * 16;
+    const uint32_t a0 = smem_u32(As), b0 = smem_u32(Ws);
+    mbar_wait(w_full, 0);
+    int it = 0;
+    for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+      for (int ck = 0; ck < nchunk; ++ck, ++it) {
+        mbar_wait(a_full, it & 1);
+        mbar_wait(t_empty, (it & 1) ^ 1);
+        tc::fence_after_sync();
+        if (lane == 0) {
+          for (int t = 0; t < B2D_TILES; ++t) {
+#pragma unroll
+            for (int sh = 0; sh < 4; ++sh) {
+              const int shift_rows = (sh >> 1) * Pp + (sh & 1);
+#pragma unroll
+              for (int k16 = 0; k16 < GB_K / 16; ++k16) {
+                const uint32_t aa = a0 + (2 * k16) * lbo_a + (LEAD + t * 128 - shift_rows) * 16;
+                const uint32_t bb = b0 + (sh * GB_KC + 2 * k16) * lbo_b;
+                tc::umma_bf16(tmem_base + t * 32, tc::make_smem_desc(aa, lbo_a, 128), tc::make_smem_desc(bb, lbo_b, 128), idesc,
+                              (sh | k16) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          tc::umma_commit(t_full);
+          tc::umma_commit(a_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float dbs[GB_CLS];
+#pragma unroll
+    for (int o = 0; o < GB_CLS; ++o) dbs[o] = 0.f;
+    int it = 0;
+    for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+      for (int ck = 0; ck < nchunk; ++ck, ++it) {
+        const int y0 = ck * B2D_ROWS, nrow = min(B2D_ROWS, Hi - y0);
+        mbar_wait(t_full, it & 1);
+        tc::fence_after_sync();
+        for (int t = 0; t < B2D_TILES; ++t) {
+          float d[32];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            float v[16];
+            tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + t * 32 + cc * 16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) d[cc * 16 + i] = v[i];
+          }
+          const int row = t * 128 + 32 * q + lane;
+          const int ml = row / Pp, n = row - ml * Pp;
+          if (ml < nrow && n < Wi) {
+            const int y = y0 + ml;
+            const int row1 = (y >> 1) * (Wi >> 1) + (n >> 1);
+            const int k0 = GB_CLS * (((y & 1) << 1) | (n & 1));
+#pragma unroll
+            for (int o = 0; o < GB_CLS; ++o)
+              if (o < P.c1) dbs[o] += d[o];
+#pragma unroll
+            for (int i = 0; i < GB_CLS / 4; ++i) {
+              uint32_t pk[2];
+#pragma unroll
+              for (int e2 = 0; e2 < 2; ++e2) {
+                const int c0 = 4 * i + 2 * e2;
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(c0 < P.c1 ? d[c0] : 0.f, c0 + 1 < P.c1 ? d[c0 + 1] : 0.f);
+                pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              const int k = k0 + 4 * i;
+              *reinterpret_cast<uint2*>(P.G1 + (((size_t)b * GB_KC + (k >> 3)) * npix1 + row1) * 8 + (k & 7)) = make_uint2(pk[0], pk[1]);
+            }
+          }
+        }
+        tc::fence_before_sync();
+        tc::mbar_arrive(t_empty);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < GB_CLS; ++o) {
+      if (o >= P.c1) break;
+      const float s = warp_sum(dbs[o]);
+      if (lane == 0 && s != 0.f) atomicAdd(P.db1 + o, s);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 128);
+}
+
+// =====================================================================================================
+// b3a: data gradient of the first deconv + inverse PixelShuffle:  G1 -> d features (NCHW bf16)
+// =====================================================================================================
+constexpr int B3A_THREADS = 192;  // warp 0 loader, warp 1 MMA, warps 2-5 epilogue (lane = channel)
+
+struct B3aParams {
+  const __nv_bfloat16* G1;   // [B][10][Hi*Wi][8]
+  const __nv_bfloat16* wpk;  // [C4/128][4][10][128][8]
+  __nv_bfloat16* dfeat;      // [B][4*C4][(Hi/2)*(Wi/2)]
+  int B, C4, Hi, Wi;         // shuffled-image geometry (Hi = 2H, Wi = 2W)
+  int nhalf_cols;            // TMEM columns per half (multiple of 16)
+};
+
+__global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_constant__ B3aParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int Wi = P.Wi, Hi = P.Hi, Pp = Wi + 1, LEAD = Pp + 1;
+  const int Hh = Hi / 2;  // image rows per half
+  const int rows_alloc = (LEAD + 2 * P.nhalf_cols + 7) & ~7;
+  const int g_bytes = GB_KC * rows_alloc * 16;
+  const int w_bytes = 4 * GB_KC * 128 * 16;
+  unsigned char* Gs = smem;
+  unsigned char* Ws = smem + g_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ws + w_bytes);
+  uint64_t* g_full = bars;
+  uint64_t* g_empty = bars + 1;
+  uint64_t* w_full = bars + 2;
+  uint64_t* t_full = bars + 3;
+  uint64_t* t_empty = bars + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntile = P.C4 / 128;
+  const int mt = blockIdx.x % ntile, slot = blockIdx.x / ntile, nslot = gridDim.x / ntile;
+
+  for (int i = tid; i < g_bytes / 16; i += B3A_THREADS) reinterpret_cast<uint4*>(Gs)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(g_full, 1);
+    mbar_init(g_empty, 1);
+    mbar_init(w_full, 1);
+    mbar_init(t_full, 1);
+    mbar_init(t_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
+  fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int npix = Hi * Wi;
+  const int n0 = P.nhalf_cols > 256 ? 160 : P.nhalf_cols;  // first MMA's N; the rest goes into a second MMA
+  const int n1 = P.nhalf_cols - n0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)w_bytes);
+      bulk_g2s(Ws, reinterpret_cast<const unsigned char*>(P.wpk) + (size_t)mt * w_bytes, (uint32_t)w_bytes, w_full);
+    }
+    int it = 0;
+    for (int b = slot; b < P.B; b += nslot, ++it) {
+      mbar_wait(g_empty, (it & 1) ^ 1);
+      if (lane == 0) mbar_expect_tx(g_full, (uint32_t)(GB_KC * npix * 16));
+      __syncwarp();
+      for (int i = lane; i < GB_KC * Hi; i += 32) {
+        const int kc = i / Hi, m = i - kc * Hi;
+        bulk_g2s(Gs + ((size_t)kc * rows_alloc + LEAD + (size_t)m * Pp) * 16,
+                 P.G1 + (((size_t)b * GB_KC + kc) * npix + (size_t)m * Wi) * 8, (uint32_t)(Wi * 16), g_full);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc0 = tc::make_idesc_bf16_f32(128, n0);
+    const uint32_t idesc1 = n1 > 0 ? tc::make_idesc_bf16_f32(128, n1) : 0u;
+    const uint32_t lbo_g = rows_alloc * 16, lbo_w = 128 * 16;
+    const uint32_t g0 = smem_u32(Gs), w0 = smem_u32(Ws);
+    mbar_wait(w_full, 0);
+    int it = 0, nb = 0;
+    for (int b = slot; b < P.B; b += nslot, ++it) {
+      mbar_wait(g_full, it & 1);
+      for (int hf = 0; hf < 2; ++hf, ++nb) {
+        mbar_wait(t_empty, (nb & 1) ^ 1);
+        tc::fence_after_sync();
+        if (lane == 0) {
+#pragma unroll
+          for (int sh = 0; sh < 4; ++sh) {
+            const int shift_rows = (sh >> 1) * Pp + (sh & 1);
+#pragma unroll
+            for (int k16 = 0; k16 < GB_K / 16; ++k16) {
+              const uint32_t ww = w0 + ((sh * GB_KC + 2 * k16) * 128) * 16;
+              const uint32_t gg = g0 + (2 * k16) * lbo_g + (LEAD + hf * Hh * Pp - shift_rows) * 16;
+              const uint64_t wd = tc::make_smem_desc(ww, lbo_w, 128);
+              tc::umma_bf16(tmem_base, wd, tc::make_smem_desc(gg, lbo_g, 128), idesc0, (sh | k16) != 0 ? 1u : 0u);
+              if (n1 > 0)
+                tc::umma_bf16(tmem_base + n0, wd, tc::make_smem_desc(gg + n0 * 16, lbo_g, 128), idesc1, (sh | k16) != 0 ? 1u : 0u);
+            }
+          }
+          tc::umma_commit(t_full);
+          if (hf == 1) tc::umma_commit(g_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int c = mt * 128 + 32 * q + lane;  // shuffled channel owned by this thread (= TMEM lane)
+    const int Ws2 = Wi / 2, HW = (Hi / 2) * Ws2;
+    int nb = 0;
+    for (int b = slot; b < P.B; b += nslot) {
+      for (int hf = 0; hf < 2; ++hf, ++nb) {
+        mbar_wait(t_full, nb & 1);
+        tc::fence_after_sync();
+        for (int ml = 0; ml < Hh; ++ml) {
+          const int m = hf * Hh + ml;
+          const int i = m >> 1, di = m & 1;
+          __nv_bfloat16* base = P.dfeat + ((size_t)b * 4 * P.C4 + 4 * c + 2 * di) * HW + (size_t)i * Ws2;
+          for (int nc = 0; nc < Wi; nc += 16) {  // 16 raster columns = 8 feature columns of each dj
+            float v[16];
+            tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + ml * Pp + nc, v);
+            const int jn = min(8, (Wi - nc) / 2);  // valid feature columns in this group
+#pragma unroll
+            for (int dj = 0; dj < 2; ++dj) {
+              __nv_bfloat16* dst = base + (size_t)dj * HW + nc / 2;
+#pragma unroll
+              for (int j4 = 0; j4 < 2; ++j4) {
+                if (4 * j4 < jn) {
+                  __nv_bfloat162 lo = __floats2bfloat162_rn(v[2 * (4 * j4) + dj], v[2 * (4 * j4 + 1) + dj]);
+                  __nv_bfloat162 hi = __floats2bfloat162_rn(v[2 * (4 * j4 + 2) + dj], v[2 * (4 * j4 + 3) + dj]);
+                  *reinterpret_cast<uint2*>(dst + 4 * j4) =
+                      make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                }
+              }
+            }
+          }
+        }
+        tc::fence_before_sync();
+        tc::mbar_arrive(t_empty);
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
+
+// =====================================================================================================
+// wg: weight gradient of a stride-2 3x3 transposed convolution (both layers)
+// =====================================================================================================
+//   dW[c, o, ky, kx] = sum_{frames, rows} X[row + shift][c] * G[row][(cls, o)]      ((cls, shift) -> tap)
+// a GEMM whose K dimension is the pixel raster.  Both operands are the row layout read TRANSPOSED
+// (MN-major UMMA descriptors, tcgen05.cuh / umma_selftest.cu mode 1): A = G (M = 128 covers the 80 real
+// (cls, o) rows; the descriptor's last 6 K-chunk groups run on into the X stages and fill accumulator lanes
+// 80..127 that nothing reads), B = X at a row offset (the shift), N = this CTA's channel group.
+// The four shifts own four accumulators D_sh[k][c] that stay in TMEM across every (frame, row-chunk) unit of
+// the CTA; one epilogue at the end adds them into dW with atomics.  An all-ones input channel (the bias lane
+// of the mid activations) yields the bias gradient from the same GEMM.
+constexpr int WG_THREADS = 192;  // warp 0 loader, warp 1 MMA, warps 2-5 epilogue
+
+struct WgParams {
+  const __nv_bfloat16* X;     // [B][kcx_total][Hi*Wi][8]
+  const __nv_bfloat16* G;     // [B][10][Hi*Wi][8]
+  const __nv_bfloat16* zrow;  // Wi*8 zeros
+  float* dW;                  // [Cin][Cout][3][3], pre-zeroed
+  float* dbias;               // [Cout] or null: taken from input channel ones_c
+  int B, Hi, Wi;
+  int R;                      // image rows per unit
+  int KR;                     // GEMM-K rows per unit = R*(Wi+1) rounded up to 16
+  int XR;                     // X rows per K-chunk in smem (KR + Wi + 2, multiple of 8)
+  int kcx, kcx_total;         // K-chunks (8 channels) per CTA group / per frame
+  int Cin, Cout, ones_c;
+  int smem_bytes;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int Wi = P.Wi, Hi = P.Hi, Pp = Wi + 1, R = P.R, KR = P.KR, XR = P.XR;
+  const int g_bytes = GB_KC * KR * 16, x_bytes = P.kcx * XR * 16;
+  unsigned char* Gs = smem;
+  unsigned char* Xs = smem + 2 * g_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P.smem_bytes - 64);
+  uint64_t* full = bars;       // [2]
+  uint64_t* empty = bars + 2;  // [2]
+  uint64_t* t_done = bars + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = P.kcx * 8;
+  const int ngroups = P.kcx_total / P.kcx;  // kcx_total may include K-chunks beyond the last group (ignored)
+  const int grp = blockIdx.x % ngroups, slot = blockIdx.x / ngroups, nslot = gridDim.x / ngroups;
+  const int nchunk = (Hi + R - 1) / R, nunits = P.B * nchunk, npix = Hi * Wi;
+  const uint32_t ncols = 4 * N <= 32 ? 32 : (4 * N <= 64 ? 64 : (4 * N <= 128 ? 128 : (4 * N <= 256 ? 256 : 512)));
+
+  for (int i = tid; i < (P.smem_bytes - 64) / 16; i += WG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(t_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, ncols);
+  fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    int j = 0;
+    for (int u = slot; u < nunits; u += nslot, ++j) {
+      const int s = j & 1, b = u / nchunk, y0 = (u - b * nchunk) * R;
+      mbar_wait(&empty[s], ((j >> 1) & 1) ^ 1);
+      if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)((GB_KC * R + P.kcx * (R + 1)) * Wi * 16));
+      __syncwarp();
+      for (int i = lane; i < GB_KC * R; i += 32) {
+        const int kc = i / R, yl = i - kc * R, y = y0 + yl;
+        const __nv_bfloat16* srcp = y < Hi ? P.G + (((size_t)b * GB_KC + kc) * npix + (size_t)y * Wi) * 8 : P.zrow;
+        bulk_g2s(Gs + (size_t)s * g_bytes + ((size_t)kc * KR + (size_t)yl * Pp) * 16, srcp, (uint32_t)(Wi * 16), &full[s]);
+      }
+      for (int i = lane; i < P.kcx * (R + 1); i += 32) {
+        const int kc = i / (R + 1), yl = i - kc * (R + 1), y = y0 + yl;
+        const __nv_bfloat16* srcp =
+            y < Hi ? P.X + (((size_t)b * P.kcx_total + (size_t)grp * P.kcx + kc) * npix + (size_t)y * Wi) * 8 : P.zrow;
+        bulk_g2s(Xs + (size_t)s * x_bytes + ((size_t)kc * XR + (size_t)yl * Pp) * 16, srcp, (uint32_t)(Wi * 16), &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = tc::make_idesc_bf16_f32(128, N) | (1u << 15) | (1u << 16);  // both operands MN-major
+    const uint32_t g0 = smem_u32(Gs), x0 = smem_u32(Xs);
+    int j = 0;
+    for (int u = slot; u < nunits; u += nslot, ++j) {
+      const int s = j & 1;
+      mbar_wait(&full[s], (j >> 1) & 1);
+      tc::fence_after_sync();
+      if (lane == 0) {
+        for (int k16 = 0; k16 < KR / 16; ++k16) {
+          const uint64_t gd = tc::make_smem_desc(g0 + s * g_bytes + k16 * 256, 128, KR * 16);
+#pragma unroll
+          for (int sh = 0; sh < 4; ++sh) {
+            const int shift_rows = (sh >> 1) * Pp + (sh & 1);
+            const uint64_t xd = tc::make_smem_desc(x0 + s * x_bytes + (k16 * 16 + shift_rows) * 16, 128, XR * 16);
+            tc::umma_bf16(tmem_base + sh * N, gd, xd, idesc, (j | k16) != 0 ? 1u : 0u);
+          }
+        }
+        tc::umma_commit(&empty[s]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0 && j > 0) tc::umma_commit(t_done);
+    __syncwarp();
+  } else if (slot < nunits) {
+    const int q = warp & 3;
+    if (32 * q < GB_K) {
+      mbar_wait(t_done, 0);
+      tc::fence_after_sync();
+      const int k = 32 * q + lane;
+      const int cls = k / GB_CLS, o = k - cls * GB_CLS;
+      const int py = cls >> 1, px = cls & 1;
+      for (int sh = 0; sh < 4; ++sh) {
+        const int dm = sh >> 1, dn = sh & 1;
+        const bool valid = k < GB_K && o < P.Cout && !(py == 0 && dm == 1) && !(px == 0 && dn == 1);
+        const int ky = py == 0 ? 1 : (dm ? 0 : 2), kx = px == 0 ? 1 : (dn ? 0 : 2);
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + sh * N + c0, v);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = grp * N + c0 + i;
+              if (c < P.Cin) atomicAdd(P.dW + ((size_t)c * P.Cout + o) * 9 + ky * 3 + kx, v[i]);
+              else if (P.dbias && c == P.ones_c && sh == 0) atomicAdd(P.dbias + o, v[i]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, ncols);
+}
+
+static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, const __nv_bfloat16* zrow, float* dW, float* dbias,
+                        int B, int Hi, int Wi, int R, int kcx, int kcx_total, int Cin, int Cout, int ones_c, int sms,
+                        cudaStream_t s) {
+  WgParams p;
+  p.X = X;
+  p.G = G;
+  p.zrow = zrow;
+  p.dW = dW;
+  p.dbias = dbias;
+  p.B = B;
+  p.Hi = Hi;
+  p.Wi = Wi;
+  p.R = R;
+  p.KR = (R * (Wi + 1) + 15) & ~15;
+  p.XR = (p.KR + Wi + 2 + 7) & ~7;
+  p.kcx = kcx;
+  p.kcx_total = kcx_total;
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.ones_c = ones_c;
+  const size_t gb = (size_t)GB_KC * p.KR * 16, xb = (size_t)kcx * p.XR * 16;
+  size_t body = 2 * gb + 2 * xb;
+  const size_t phantom = gb + (size_t)16 * p.KR * 16;  // address range the 16-chunk A descriptor of stage 1 spans
+  if (body < phantom) body = phantom;
+  body = (body + 15) & ~(size_t)15;
+  p.smem_bytes = (int)(body + 64);
+  LPB_REQUIRE(p.smem_bytes <= 225 * 1024, "head_bwd_bf16: weight-gradient stages need %d B shared memory", p.smem_bytes);
+  LPB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+  const int ngroups = kcx_total / kcx;
+  const int nunits = B * ((Hi + R - 1) / R);
+  int slots = sms / ngroups;
+  if (slots < 1) slots = 1;
+  if (slots > nunits) slots = nunits;
+  wgrad_kernel<<<slots * ngroups, WG_THREADS, p.smem_bytes, s>>>(p);
+  return LPB_OK;
+}
+
+}  // namespace lpb
+
+// workspace: [W1 dgrad pack][W2 dgrad pack][zero row][G2][G1]
+extern "C" int lpb_head_bwd_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes) {
+  using namespace lpb;
+  LPB_REQUIRE(bytes, "head_bwd_bf16_workspace_bytes: null pointer");
+  LPB_REQUIRE(B >= 0 && C >= 512 && C % 512 == 0 && H >= 1 && W >= 1 && c1 >= 1 && c2 >= 1, "head_bwd_bf16_workspace_bytes: bad shape");
+  const size_t w1 = (size_t)(C / 4 / 128) * 4 * GB_KC * 128 * 16, w2 = (size_t)4 * GB_KC * 32 * 16;
+  const size_t zrow = ((size_t)4 * W * 16 + 255) & ~(size_t)255;
+  const size_t g2 = (size_t)B * GB_KC * (16 * H * W) * 16, g1 = (size_t)B * GB_KC * (4 * H * W) * 16;
+  *bytes = w1 + w2 + zrow + g2 + g1;
+  return LPB_OK;
+}
+
+extern "C" int lpb_head_bwd_bf16(const float* g_logits, const void* saved_xs, const void* fwd_workspace, int B, int C, int H,
+                                 int W, const float* w1, int c1, const float* w2, int c2, void* dfeat, float* dw1, float* db1,
+                                 float* dw2, float* db2, void* workspace, void* stream) {
+  using namespace lpb;
+  LPB_REQUIRE(g_logits && saved_xs && fwd_workspace && w1 && w2 && dw1 && db1 && dw2 && db2 && workspace, "head_bwd_bf16: null pointer");
+  LPB_REQUIRE(B >= 0 && C >= 512 && C % 512 == 0 && H >= 1 && W >= 1, "head_bwd_bf16: bad feature shape C=%d H=%d W=%d", C, H, W);
+  LPB_REQUIRE(c1 >= 1 && c1 < GB_CLS && c2 >= 1 && c2 <= GB_CLS && (W % 4) == 0, "head_bwd_bf16: unsupported channels/width");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int C4 = C / 4, Hi1 = 2 * H, Wi1 = 2 * W, Hi2 = 4 * H, Wi2 = 4 * W;
+  LPB_CUDA(cudaMemsetAsync(dw1, 0, sizeof(float) * (size_t)C4 * c1 * 9, s));
+  LPB_CUDA(cudaMemsetAsync(dw2, 0, sizeof(float) * (size_t)c1 * c2 * 9, s));
+  LPB_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * c1, s));
+  LPB_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * c2, s));
+  if (B == 0) return LPB_OK;
+  const int nhalf = ((Hi1 / 2) * (Wi1 + 1) + 15) & ~15;
+  if (nhalf > 304 || (Hi1 & 1)) {
+    set_error("head_bwd_bf16: feature map %dx%d outside this build's TMEM tiling", H, W);
+    return LPB_ERR_UNSUPPORTED;
+  }
+  int dev = 0, sms = 0;
+  LPB_CUDA(cudaGetDevice(&dev));
+  LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  const size_t w1b = (size_t)(C4 / 128) * 4 * GB_KC * 128 * 16, w2b = (size_t)4 * GB_KC * 32 * 16;
+  const size_t zrowb = ((size_t)4 * W * 16 + 255) & ~(size_t)255;
+  __nv_bfloat16* wp1 = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* wp2 = reinterpret_cast<__nv_bfloat16*>(ws + w1b);
+  __nv_bfloat16* zrow = reinterpret_cast<__nv_bfloat16*>(ws + w1b + w2b);
+  __nv_bfloat16* G2 = reinterpret_cast<__nv_bfloat16*>(ws + w1b + w2b + zrowb);
+  __nv_bfloat16* G1 = reinterpret_cast<__nv_bfloat16*>(ws + w1b + w2b + zrowb + (size_t)B * GB_KC * Hi2 * Wi2 * 16);
+  // the forward pass's mid activations (head_bf16.cu workspace layout: [packed w1][packed w2][zero row][mid])
+  const size_t fwd_mid_off = (size_t)(C4 / 32 + 1) * (4 * 4 * 80 * 16) + zrowb;
+  const __nv_bfloat16* mid = reinterpret_cast<const __nv_bfloat16*>(static_cast<const unsigned char*>(fwd_workspace) + fwd_mid_off);
+
+  pack_dgrad_weights_kernel<<<128, 256, 0, s>>>(w1, C4, c1, C4 / 128, 128, wp1, zrow, (int)(zrowb / 2));
+  pack_dgrad_weights_kernel<<<8, 256, 0, s>>>(w2, c1, c2, 1, 32, wp2, nullptr, 0);
+  g_relayout_kernel<<<(unsigned)(B * Hi2), 64, 0, s>>>(g_logits, B, c2, Hi2, Wi2, G2);
+  // layer 2: weight + bias gradient (bias from the all-ones channel c1 of mid), then data gradient -> G1 (+ db1)
+  {
+    int R = 8;
+    while (R > 1 && ((size_t)2 * GB_KC * ((R * (Wi2 + 1) + 15) & ~15) * 16 + 2 * 4 * (((R * (Wi2 + 1) + 15) & ~15) + Wi2 + 10) * 16) > 200 * 1024) --R;
+    const int rc = launch_wgrad(mid, G2, zrow, dw2, db2, B, Hi2, Wi2, R, 4, 4, c1, c2, c1, sms, s);
+    if (rc != LPB_OK) return rc;
+  }
+  {
+    B2dParams p;
+    p.G2 = G2;
+    p.zrow = zrow;
+    p.wpk = wp2;
+    p.G1 = G1;
+    p.db1 = db1;
+    p.B = B;
+    p.Hi = Hi2;
+    p.Wi = Wi2;
+    p.c1 = c1;
+    const int rows_alloc = (Wi2 + 2 + B2D_TILES * 128 + 7) & ~7;
+    const size_t smem = (size_t)GB_KC * rows_alloc * 16 + (size_t)4 * GB_KC * 32 * 16 + 64;
+    LPB_REQUIRE(smem <= 113 * 1024 && (B2D_ROWS * (Wi2 + 1)) <= B2D_TILES * 128, "head_bwd_bf16: layer-2 width %d too large", Wi2);
+    LPB_CUDA(cudaFuncSetAttribute(b2d_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = B < 2 * sms ? B : 2 * sms;
+    b2d_dgrad_kernel<<<grid, B2D_THREADS, smem, s>>>(p);
+  }
+  // layer 1: weight gradient from the saved shuffled features, data gradient -> d features
+  {
+    int R = 8;
+    while (R > 1 && ((size_t)2 * GB_KC * ((R * (Wi1 + 1) + 15) & ~15) * 16 + 2 * 16 * (((R * (Wi1 + 1) + 15) & ~15) + Wi1 + 10) * 16) > 200 * 1024) --R;
+    const int rc = launch_wgrad(static_cast<const __nv_bfloat16*>(saved_xs), G1, zrow, dw1, nullptr, B, Hi1, Wi1, R, 16, C4 / 8, C4,
+                                c1, -1, sms, s);
+    if (rc != LPB_OK) return rc;
+  }
+  if (dfeat) {
+    B3aParams p;
+    p.G1 = G1;
+    p.wpk = wp1;
+    p.dfeat = static_cast<__nv_bfloat16*>(dfeat);
+    p.B = B;
+    p.C4 = C4;
+    p.Hi = Hi1;
+    p.Wi = Wi1;
+    p.nhalf_cols = nhalf;
+    const int rows_alloc = (Wi1 + 2 + 2 * nhalf + 7) & ~7;
+    const size_t smem = (size_t)GB_KC * rows_alloc * 16 + (size_t)4 * GB_KC * 128 * 16 + 64;
+    LPB_REQUIRE(smem <= 220 * 1024, "head_bwd_bf16: layer-1 operands need %zu B shared memory", smem);
+    LPB_CUDA(cudaFuncSetAttribute(b3a_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntile = C4 / 128;
+    int slots = sms / ntile;
+    if (slots < 1) slots = 1;
+    if (slots > B) slots = B;
+    b3a_dgrad_kernel<<<slots * ntile, B3A_THREADS, smem, s>>>(p);
+  }
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}

@@ -63,15 +63,22 @@ def run_subpixelmaxima(
 
 
 class _HeadFunction(torch.autograd.Function):
-    """Forward: fused CUDA head.  Backward: see ``HeatmapHead`` docstring."""
+    """Forward: fused CUDA head.  Backward: native tcgen05 kernels for the bf16 head (see ``HeatmapHead``)."""
 
     @staticmethod
     def forward(ctx, features, final_softmax, *params):
         n = len(params) // 2
         weights, biases = list(params[:n]), list(params[n:])
-        out = ops.head_forward(features, weights, biases, final_softmax)
+        saved = None
+        out = None
+        if features.dtype == torch.bfloat16 and n == 2 and features.is_cuda:
+            res = ops._head_forward_bf16(features.contiguous(), weights, biases, final_softmax, train=True)
+            if res is not None:
+                out, saved = res
+        if out is None:
+            out = ops.head_forward(features, weights, biases, final_softmax)
         ctx.save_for_backward(features, out, *params)
-        ctx.final_softmax, ctx.n = final_softmax, n
+        ctx.final_softmax, ctx.n, ctx.saved = final_softmax, n, saved
         return out
 
     @staticmethod
@@ -82,7 +89,14 @@ class _HeadFunction(torch.autograd.Function):
         g = g.contiguous().float()
         if ctx.final_softmax:  # d softmax: p * (g - sum(g * p)) per plane
             g = ops.plane_softmax_backward(out, g)
-        # interim: transposed-conv dgrad/wgrad through the framework's conv ops ("backward")
+        if ctx.saved is not None:
+            dfeat, dw1, db1, dw2, db2 = ops.head_backward_bf16(
+                g, ctx.saved, tuple(features.shape), weights[0], weights[1], need_dfeat=ctx.needs_input_grad[0]
+            )
+            ctx.saved = None
+            return (dfeat, None, dw1.to(weights[0].dtype), dw2.to(weights[1].dtype), db1.to(biases[0].dtype), db2.to(biases[1].dtype))
+        # shapes outside the tensor-core tiling and the fp32 head: transposed-conv dgrad/wgrad through the
+        # framework's conv ops ("backward")
         cdt = torch.bfloat16 if features.dtype == torch.bfloat16 else torch.float32  # same precision as the forward
         with torch.enable_grad():
             f = features.detach().to(cdt).requires_grad_(ctx.needs_input_grad[0])

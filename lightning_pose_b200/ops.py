@@ -18,6 +18,7 @@ __all__ = [
     "generate_heatmaps",
     "evaluate_heatmaps_at_location",
     "head_forward",
+    "head_backward_bf16",
     "remap_keypoints",
     "heatmap_loss",
     "heatmap_mse_from_keypoints",
@@ -167,21 +168,48 @@ def evaluate_heatmaps_at_location(heatmaps, locs, radius: int = 2):
 # =====================================================================================
 # heatmap head
 # =====================================================================================
-def _head_forward_bf16(f, weights, biases, final_softmax):
-    """tcgen05 path; returns None when the shape is outside the tensor-core tiling of this build."""
+def _head_forward_bf16(f, weights, biases, final_softmax, train=False):
+    """tcgen05 path; returns None when the shape is outside the tensor-core tiling of this build.
+
+    ``train=True`` returns ``(out, saved)`` where ``saved`` carries what ``head_backward_bf16`` needs
+    (the forward workspace with the inter-layer activations, and the row-layout copy of the shuffled features).
+    """
     b, c, h, w = f.shape
     w1, w2 = (_cuda_f32(x, "weight") for x in weights)
     b1, b2 = (_cuda_f32(x, "bias") for x in biases)
     c1, c2 = w1.shape[1], w2.shape[1]
-    if c % 128 or (h * w) % 8 or c1 > 20 or c2 > 20 or (2 * h * (2 * w + 1) + 127) // 128 * 80 > 512:
+    if c % 128 or (h * w) % 8 or c1 >= 20 or c2 > 20 or (2 * h * (2 * w + 1) + 127) // 128 * 80 > 512:
         return None
     nbytes = C.c_size_t(0)
     check(lib.lpb_head_bf16_workspace_bytes(b, c, h, w, c1, c2, C.byref(nbytes)))
     ws = torch.empty((nbytes.value,), device=f.device, dtype=torch.uint8)
     out = torch.empty((b, c2, 8 * h, 8 * w), device=f.device, dtype=torch.float32)
+    native_bwd = train and c % 512 == 0 and w % 4 == 0 and ((h * (2 * w + 1) + 15) & ~15) <= 304
+    xs = torch.empty_like(f) if native_bwd else None
     with torch.cuda.device(f.device):
-        check(lib.lpb_head_fwd_bf16(_ptr(f), b, c, h, w, _ptr(w1), _ptr(b1), c1, _ptr(w2), _ptr(b2), c2, int(bool(final_softmax)), _ptr(out), _ptr(ws), _stream()))
+        check(lib.lpb_head_fwd_bf16(_ptr(f), b, c, h, w, _ptr(w1), _ptr(b1), c1, _ptr(w2), _ptr(b2), c2, int(bool(final_softmax)), _ptr(out), _ptr(xs), _ptr(ws), _stream()))
+    if train:
+        return out, ((xs, ws) if native_bwd else None)
     return out
+
+
+def head_backward_bf16(g_logits, saved, feat_shape, w1, w2, need_dfeat=True):
+    """Gradients of the bf16 head (tcgen05): returns (dfeat bf16 | None, dw1, db1, dw2, db2)."""
+    xs, fws = saved
+    b, c, h, w = feat_shape
+    g = _cuda_f32(g_logits, "g_logits")
+    w1, w2 = _cuda_f32(w1, "w1"), _cuda_f32(w2, "w2")
+    c1, c2 = w1.shape[1], w2.shape[1]
+    nbytes = C.c_size_t(0)
+    check(lib.lpb_head_bwd_bf16_workspace_bytes(b, c, h, w, c1, c2, C.byref(nbytes)))
+    ws = torch.empty((nbytes.value,), device=g.device, dtype=torch.uint8)
+    dfeat = torch.empty((b, c, h, w), device=g.device, dtype=torch.bfloat16) if need_dfeat else None
+    dw1, dw2 = torch.empty_like(w1), torch.empty_like(w2)
+    db1 = torch.empty((c1,), device=g.device, dtype=torch.float32)
+    db2 = torch.empty((c2,), device=g.device, dtype=torch.float32)
+    with torch.cuda.device(g.device):
+        check(lib.lpb_head_bwd_bf16(_ptr(g), _ptr(xs), _ptr(fws), b, c, h, w, _ptr(w1), c1, _ptr(w2), c2, _ptr(dfeat), _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _ptr(ws), _stream()))
+    return dfeat, dw1, db1, dw2, db2
 
 
 def head_forward(features, weights, biases, final_softmax=True):

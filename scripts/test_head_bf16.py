@@ -33,7 +33,7 @@ out = torch.zeros(B, K, 96, 96, device=dev)
 args = [t.to(dev).contiguous() for t in (feats, w1, b1, w2, b2)]
 p = lambda t: C.c_void_p(t.data_ptr())
 for softmax in (0, 1):
-    check(lib.lpb_head_fwd_bf16(p(args[0]), B, Cf, H, W, p(args[1]), p(args[2]), K, p(args[3]), p(args[4]), K, softmax, p(out), p(ws), None))
+    check(lib.lpb_head_fwd_bf16(p(args[0]), B, Cf, H, W, p(args[1]), p(args[2]), K, p(args[3]), p(args[4]), K, softmax, p(out), None, p(ws), None))
     torch.cuda.synchronize()
     nst = Cf // 4 // 32
     zrow = (4 * W * 16 + 255) // 256 * 256
