@@ -432,6 +432,51 @@ def test_head_bf16_tcgen05_vs_oracle(lpb, dev, shape):
     conf_ok = cf_ref > 0.5
     assert float(((kp.cpu() - kp_ref).abs().reshape(b, 17, 2).amax(-1))[conf_ok].max()) < 0.5
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("softmax", [True, False])
+def test_head_bf16_tcgen05_backward_vs_oracle_autograd(lpb, dev, softmax):
+    """lpb_head_bwd_bf16 (dgrad + wgrad on tcgen05) against fp32 autograd of the oracle head evaluated on the
+    same bf16-rounded operands; tolerance 1e-2 of each gradient's max (north star, bf16)."""
+    import torch.nn.functional as F
+    from lightning_pose_b200.models.heads.heatmap import HeatmapHead
+
+    b, c, fh, fw = 7, 2048, 12, 12
+    torch.manual_seed(29)
+    head = HeatmapHead("resnet50", c, 17, final_softmax=softmax)
+    for layer in list(head.upsampling_layers)[1:]:
+        torch.nn.init.xavier_uniform_(layer.weight, gain=3.0)
+        torch.nn.init.uniform_(layer.bias, -0.3, 0.3)
+    feats = (torch.randn(b, c, fh, fw) * 0.5).bfloat16()
+    gout = torch.randn(b, 17, 8 * fh, 8 * fw)
+    # oracle: fp32 autograd, weights / stored activations rounded to bf16 as in the kernels
+    r = lambda t: (t.bfloat16().float() - t).detach() + t
+    d1, d2 = list(head.upsampling_layers)[1:]
+    f_ref = feats.float().requires_grad_(True)
+    p_ref = [t.detach().clone().requires_grad_(True) for t in (d1.weight, d1.bias, d2.weight, d2.bias)]
+    mid = F.conv_transpose2d(F.pixel_shuffle(f_ref, 2), r(p_ref[0]), p_ref[1], stride=2, padding=1, output_padding=1)
+    y = F.conv_transpose2d(r(mid), r(p_ref[2]), p_ref[3], stride=2, padding=1, output_padding=1)
+    if softmax:
+        y = O.spatial_softmax2d(y, 1.0)
+    (y * gout).sum().backward()
+    head = head.to(dev)
+    f_dev = feats.to(dev).requires_grad_(True)
+    out = head(f_dev)
+    (out * gout.to(dev)).sum().backward()
+    d1, d2 = list(head.upsampling_layers)[1:]
+    assert f_dev.grad.dtype == torch.bfloat16
+    for name, got, ref in [("dfeat", f_dev.grad.float(), f_ref.grad), ("dw1", d1.weight.grad, p_ref[0].grad), ("db1", d1.bias.grad, p_ref[1].grad),
+                           ("dw2", d2.weight.grad, p_ref[2].grad), ("db2", d2.bias.grad, p_ref[3].grad)]:
+        err = float((got.cpu() - ref).abs().max())
+        scale = float(ref.abs().max())
+        if name == "db2" and softmax:  # exactly 0 in exact arithmetic (softmax ignores a per-plane constant):
+            scale = float(p_ref[2].grad.abs().max())  # both sides are rounding noise; bound it by the dw2 scale
+        assert err <= 1e-2 * scale + 1e-9, (name, err, scale)
+    # frozen backbone: no feature gradient requested, weight gradients unchanged
+    head.zero_grad()
+    out = head(feats.to(dev))
+    (out * gout.to(dev)).sum().backward()
+    close(d1.weight.grad, p_ref[0].grad, atol=1e-2 * float(p_ref[0].grad.abs().max()), rtol=0)
+
 
 def test_decode_multimodal_random_fields(lpb, dev):
     """Random spiky planes (several comparable peaks scattered over the plane) exercise the per-strip
