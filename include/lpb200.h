@@ -106,9 +106,11 @@ int lpb_head_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, si
 int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int W, const float* w1, const float* b1, int c1,
                       const float* w2, const float* b2, int c2, int final_softmax, float* out, void* saved_xs,
                       void* workspace, void* stream);
-/* saved_xs: NULL for inference.  For training pass a device buffer of the same byte size as `features`; it
- * receives the pixel-shuffled features in the row layout the weight-gradient GEMM reads, and must stay alive
- * (together with `workspace`, which holds the activations between the two deconvs) until lpb_head_bwd_bf16. */
+/* saved_xs: NULL for inference.  For training pass a device buffer of lpb_head_bf16_saved_bytes() bytes; it
+ * receives the pixel-shuffled features in the padded row layout the weight-gradient GEMM reads, and must stay
+ * alive (together with `workspace`, which holds the activations between the two deconvs) until
+ * lpb_head_bwd_bf16. */
+int lpb_head_bf16_saved_bytes(int B, int C, int H, int W, size_t* bytes);
 
 /* backward of lpb_head_fwd_bf16 (replaces autograd through heatmap.py:203-212; four tcgen05 kernels:
  * layer-2 wgrad, layer-2 dgrad, layer-1 wgrad, layer-1 dgrad + inverse PixelShuffle).

@@ -24,6 +24,7 @@
 
 #include "../../include/lpb200.h"
 #include "lpb_common.cuh"
+#include "row_layout.cuh"
 #include "tcgen05.cuh"
 
 namespace lpb {
@@ -32,6 +33,30 @@ constexpr int HB_NCOLS = 80;         // 4 classes x 20 (>= 17 keypoints), multip
 constexpr int HB_CLS = 20;
 constexpr int HB_KSTAGE = 32;        // channels per pipeline stage (4 K-chunks of 8)
 constexpr int HB_BSTAGE_BYTES = 4 * 4 * HB_NCOLS * 16;  // [shift][kchunk][80 rows][16 B]
+
+__global__ void zero_row_pads_kernel(__nv_bfloat16* __restrict__ buf, RowLayout L, long long nslabs) {
+  const int body0 = L.lead, body1 = L.lead + L.Hi * L.Pp;
+  const int npad = L.lead + (L.rows - body1) + L.Hi;  // lead rows, trail rows, one pad column entry per image row
+  const long long total = nslabs * npad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long slab = i / npad;
+    const int e = (int)(i - slab * npad);
+    int row;
+    if (e < L.lead) row = e;
+    else if (e < L.lead + (L.rows - body1)) row = body1 + (e - L.lead);
+    else row = body0 + (e - L.lead - (L.rows - body1)) * L.Pp + L.Wi;
+    *reinterpret_cast<uint4*>(buf + ((size_t)slab * L.rows + row) * 8) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+int launch_zero_row_pads(__nv_bfloat16* buf, RowLayout L, long long nslabs, void* stream) {
+  const int npad = L.lead + (L.rows - L.lead - L.Hi * L.Pp) + L.Hi;
+  long long blocks = (nslabs * npad + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) return LPB_OK;
+  zero_row_pads_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(buf, L, nslabs);
+  return LPB_OK;
+}
 
 struct HeadGeom {
   int Hi, Wi;       // conv input spatial size (after PixelShuffle for layer 1)
@@ -96,8 +121,9 @@ struct K1aParams {
   const __nv_bfloat16* feat;  // [B][C][H*W]
   const __nv_bfloat16* wpk;   // packed weights [nstages][HB_BSTAGE_BYTES]
   const float* bias;          // [c1]
-  __nv_bfloat16* mid;         // [B][4][4*Hi*Wi][8]  (A layout of the next layer, no halo)
-  __nv_bfloat16* xs;          // optional [B][C/32][Hi*Wi][8]: shuffled features in row layout, kept for the weight gradient
+  __nv_bfloat16* mid;         // [B][4][Lmid.rows][8]  padded row layout of the next layer's input (row_layout.cuh)
+  __nv_bfloat16* xs;          // optional [B][C/32][Lxs.rows][8]: shuffled features in the padded row layout (weight gradient)
+  RowLayout Lmid, Lxs;
   int B, C, HW, W;            // feature geometry (C = 4 * Cin)
   int c1, nstages;
   HeadGeom g;
@@ -142,7 +168,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int Wo = 2 * g.Wi, rows_mid = 4 * g.Hi * g.Wi;
+  const int rows_mid = P.Lmid.rows;
   int nframes = 0;
   for (int b = blockIdx.x; b < P.B; b += gridDim.x) ++nframes;
   const int total_it = nframes * P.nstages;
@@ -180,7 +206,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
       __nv_bfloat16* xs_st = nullptr;  // this (frame, stage)'s 4 K-chunks of the saved copy
       if (P.xs) {
         const int b = blockIdx.x + (it / P.nstages) * gridDim.x, st = it % P.nstages;
-        xs_st = P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)(g.Hi * g.Wi) * 8;
+        xs_st = P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)P.Lxs.rows * 8;
       }
       const unsigned char* raw = raw_base + r * raw_bytes;
       for (int task = tid; task < ntasks; task += 128) {
@@ -209,7 +235,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
             const int i = sp / P.W, jc = sp - i * P.W;
             const int row = (2 * i + di) * g.P + (2 * jc + dj);
             *reinterpret_cast<uint4*>(As + ((size_t)kc * g.rows_alloc + row) * 16) = o;
-            if (xs_st) *reinterpret_cast<uint4*>(xs_st + ((size_t)kc * (g.Hi * g.Wi) + (2 * i + di) * g.Wi + (2 * jc + dj)) * 8) = o;
+            if (xs_st) *reinterpret_cast<uint4*>(xs_st + ((size_t)kc * P.Lxs.rows + P.Lxs.lead + row) * 8) = o;
           }
         }
       }
@@ -277,7 +303,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
 #pragma unroll
           for (int cls = 0; cls < 4; ++cls) {
             const int y = 2 * m + (cls >> 1), x = 2 * n + (cls & 1);
-            const size_t row2 = (size_t)y * Wo + x;
+            const size_t row2 = (size_t)P.Lmid.lead + (size_t)y * P.Lmid.Pp + x;
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) {
               uint32_t pk[4];
@@ -325,8 +351,8 @@ constexpr int K1B_TPB = 3;      // M-tiles per batch (3 * 80 = 240 of the CTA's 
 constexpr int K1B_EPI = 256;    // epilogue threads
 
 struct K1bParams {
-  const __nv_bfloat16* mid;   // [B][4][Hi*Wi][8]
-  const __nv_bfloat16* zrow;  // Wi*8 zeros (halo row below the last image row)
+  const __nv_bfloat16* mid;   // [B][4][L.rows][8] padded row layout
+  RowLayout L;
   const __nv_bfloat16* wpk;   // packed weights, one stage (K = 32); bias folded into channel c1
   float* out;                 // [B][c2][2Hi][2Wi]
   int B, c2, final_softmax;
@@ -385,13 +411,13 @@ __global__ void __launch_bounds__(K1B_THREADS, 2) k1b_convt_softmax_kernel(const
       for (int phase = 0; phase < nphase; ++phase, ++ph) {
         const int hf = phase & 1;
         mbar_wait(a_empty, (ph & 1) ^ 1);
-        if (lane == 0) mbar_expect_tx(a_full, (uint32_t)(4 * (P.Hh + 1) * Wi * 16));
-        __syncwarp();
-        for (int i = lane; i < 4 * (P.Hh + 1); i += 32) {
-          const int kc = i / (P.Hh + 1), yl = i - kc * (P.Hh + 1);
-          const int y = hf * P.Hh + yl;  // image row; y == Hi is the zero halo row
-          const __nv_bfloat16* srcp = (y < Hi) ? P.mid + (((size_t)b * 4 + kc) * npix + (size_t)y * Wi) * 8 : P.zrow;
-          bulk_g2s(As + ((size_t)kc * g.rows_alloc + (size_t)yl * g.P) * 16, srcp, (uint32_t)(Wi * 16), a_full);
+        // one contiguous copy per K-chunk: Hh image rows + the halo row below, zero column included
+        const uint32_t nbytes = (uint32_t)((P.Hh + 1) * g.P * 16);
+        if (lane < 4) {
+          if (lane == 0) mbar_expect_tx(a_full, 4 * nbytes);
+          __syncwarp(0xf);
+          bulk_g2s(As + (size_t)lane * g.rows_alloc * 16,
+                   P.mid + (((size_t)b * 4 + lane) * P.L.rows + P.L.lead + (size_t)hf * P.Hh * g.P) * 8, nbytes, a_full);
         }
       }
     }
@@ -555,15 +581,21 @@ __host__ inline HeadGeom make_half_geom(int Hh, int Wi) {
 
 }  // namespace lpb
 
-// workspace layout: [packed w1][packed w2][zero row][mid activations]
+// workspace layout: [packed w1][packed w2][mid activations (padded row layout)]
+extern "C" int lpb_head_bf16_saved_bytes(int B, int C, int H, int W, size_t* bytes) {
+  using namespace lpb;
+  LPB_REQUIRE(bytes && B >= 0 && C >= 32 && C % 32 == 0 && H >= 1 && W >= 1, "head_bf16_saved_bytes: bad arguments");
+  *bytes = (size_t)B * (C / 32) * make_row_layout(2 * H, 2 * W).rows * 16;
+  return LPB_OK;
+}
+
 extern "C" int lpb_head_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes) {
   using namespace lpb;
   LPB_REQUIRE(bytes, "head_bf16_workspace_bytes: null pointer");
   LPB_REQUIRE(B >= 0 && C >= 128 && C % 128 == 0 && H >= 1 && W >= 1 && c1 >= 1 && c2 >= 1, "head_bf16_workspace_bytes: bad shape");
   const size_t w1 = (size_t)(C / 4 / HB_KSTAGE) * HB_BSTAGE_BYTES, w2 = HB_BSTAGE_BYTES;
-  const size_t zrow = ((size_t)4 * W * 16 + 255) & ~(size_t)255;
-  const size_t mid = (size_t)B * 4 * (16 * H * W) * 16;
-  *bytes = w1 + w2 + zrow + mid;
+  const size_t mid = (size_t)B * 4 * make_row_layout(4 * H, 4 * W).rows * 16;
+  *bytes = w1 + w2 + mid;
   return LPB_OK;
 }
 
@@ -593,21 +625,24 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nst = C / 4 / HB_KSTAGE;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
-  const size_t zrow_bytes = ((size_t)4 * W * 16 + 255) & ~(size_t)255;
+  const RowLayout Lxs = make_row_layout(2 * H, 2 * W), Lmid = make_row_layout(4 * H, 4 * W);
   __nv_bfloat16* wp1 = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* wp2 = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)nst * HB_BSTAGE_BYTES);
-  __nv_bfloat16* zrow = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES);
-  __nv_bfloat16* mid = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES + zrow_bytes);
+  __nv_bfloat16* mid = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES);
+  launch_zero_row_pads(mid, Lmid, (long long)B * 4, stream);
+  if (saved_xs) launch_zero_row_pads(static_cast<__nv_bfloat16*>(saved_xs), Lxs, (long long)B * (C / 32), stream);
   pack_convt_weights_kernel<<<64, 256, 0, s>>>(w1, nullptr, C / 4, c1, nst, wp1, nullptr, 0);
   // layer 2: bias rides on the constant-one channel c1 of the mid activations (only needed without softmax:
-  // a per-plane constant does not change a softmax); the same launch clears the halo row
-  pack_convt_weights_kernel<<<8, 256, 0, s>>>(w2, final_softmax ? nullptr : b2, c1, c2, 1, wp2, zrow, (int)(zrow_bytes / 2));
+  // a per-plane constant does not change a softmax)
+  pack_convt_weights_kernel<<<8, 256, 0, s>>>(w2, final_softmax ? nullptr : b2, c1, c2, 1, wp2, nullptr, 0);
   K1aParams pa;
   pa.feat = static_cast<const __nv_bfloat16*>(features);
   pa.wpk = wp1;
   pa.bias = b1;
   pa.mid = mid;
   pa.xs = static_cast<__nv_bfloat16*>(saved_xs);
+  pa.Lmid = Lmid;
+  pa.Lxs = Lxs;
   pa.B = B;
   pa.C = C;
   pa.HW = H * W;
@@ -619,7 +654,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   k1a_shuffle_convt_kernel<<<B < sms ? B : sms, K1A_THREADS, s1, s>>>(pa);
   K1bParams pb;
   pb.mid = mid;
-  pb.zrow = zrow;
+  pb.L = Lmid;
   pb.wpk = wp2;
   pb.out = out;
   pb.B = B;

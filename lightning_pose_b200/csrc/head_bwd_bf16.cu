@@ -14,6 +14,7 @@
 
 #include "../../include/lpb200.h"
 #include "lpb_common.cuh"
+#include "row_layout.cuh"
 #include "tcgen05.cuh"
 
 namespace lpb {
@@ -25,7 +26,7 @@ constexpr int GB_KC = GB_K / 8;       // 10 K-chunks
 // ---- g_logits (fp32, NCHW) -> G2 row layout (bf16) ------------------------------------------------------
 // one CTA per (frame, m); thread n handles the 2x2 output block of row (m, n) for all channels
 __global__ void __launch_bounds__(64) g_relayout_kernel(const float* __restrict__ gl, int B, int C, int Hi, int Wi,
-                                                        __nv_bfloat16* __restrict__ G) {
+                                                        __nv_bfloat16* __restrict__ G, RowLayout L) {
   const int b = blockIdx.x / Hi, m = blockIdx.x - b * Hi;
   const int Wo = 2 * Wi, Ho = 2 * Hi;
   for (int n = threadIdx.x; n < Wi; n += blockDim.x) {
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(64) g_relayout_kernel(const float* __restrict_
           __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
           pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        *reinterpret_cast<uint4*>(G + ((((size_t)b * GB_KC + 5 * py + ch) * Hi * Wi) + (size_t)m * Wi + n) * 8) =
+        *reinterpret_cast<uint4*>(G + ((((size_t)b * GB_KC + 5 * py + ch) * L.rows) + L.lead + (size_t)m * L.Pp + n) * 8) =
             make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
@@ -96,10 +97,10 @@ constexpr int B2D_ROWS = 7;       // image rows per chunk (7 * 49 = 343 raster r
 constexpr int B2D_TILES = 3;
 
 struct B2dParams {
-  const __nv_bfloat16* G2;    // [B][10][Hi*Wi][8]
-  const __nv_bfloat16* zrow;  // Wi*8 zeros
+  const __nv_bfloat16* G2;    // [B][10][L2.rows][8] padded row layout
   const __nv_bfloat16* wpk;   // [4][10][32][8]
-  __nv_bfloat16* G1;          // [B][10][(Hi/2)*(Wi/2)][8]
+  __nv_bfloat16* G1;          // [B][10][L1.rows][8] padded row layout of the (Hi/2 x Wi/2) grid
+  RowLayout L2, L1;
   float* db1;                 // [c1] accumulated with atomics (pre-zeroed)
   int B, Hi, Wi, c1;
 };
@@ -138,7 +139,6 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   const int nchunk = (Hi + B2D_ROWS - 1) / B2D_ROWS;
-  const int npix = Hi * Wi, npix1 = (Hi / 2) * (Wi / 2);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -150,14 +150,14 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
       for (int ck = 0; ck < nchunk; ++ck, ++it) {
         const int y0 = ck * B2D_ROWS;
         mbar_wait(a_empty, (it & 1) ^ 1);
-        if (lane == 0) mbar_expect_tx(a_full, (uint32_t)(GB_KC * (B2D_ROWS + 1) * Wi * 16));
-        __syncwarp();
-        for (int i = lane; i < GB_KC * (B2D_ROWS + 1); i += 32) {
-          const int kc = i / (B2D_ROWS + 1), yl = i - kc * (B2D_ROWS + 1);  // yl = 0 is the previous image row
-          const int y = y0 - 1 + yl;
-          const __nv_bfloat16* srcp =
-              (y >= 0 && y < Hi) ? P.G2 + (((size_t)b * GB_KC + kc) * npix + (size_t)y * Wi) * 8 : P.zrow;
-          bulk_g2s(As + ((size_t)kc * rows_alloc + 1 + (size_t)yl * Pp) * 16, srcp, (uint32_t)(Wi * 16), a_full);
+        // per K-chunk ONE copy: the zero entry before image row y0-1, that row, and the chunk's rows (zero columns
+        // included); rows above the image / below it come from the layout's zero lead / trail rows
+        const uint32_t nbytes = (uint32_t)((1 + (B2D_ROWS + 1) * Pp) * 16);
+        if (lane < GB_KC) {
+          if (lane == 0) mbar_expect_tx(a_full, GB_KC * nbytes);
+          __syncwarp((1u << GB_KC) - 1);
+          bulk_g2s(As + (size_t)lane * rows_alloc * 16,
+                   P.G2 + (((size_t)b * GB_KC + lane) * P.L2.rows + P.L2.lead + (size_t)(y0 - 1) * Pp - 1) * 8, nbytes, a_full);
         }
       }
     }
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
           const int ml = row / Pp, n = row - ml * Pp;
           if (ml < nrow && n < Wi) {
             const int y = y0 + ml;
-            const int row1 = (y >> 1) * (Wi >> 1) + (n >> 1);
+            const int row1 = P.L1.lead + (y >> 1) * P.L1.Pp + (n >> 1);
             const int k0 = GB_CLS * (((y & 1) << 1) | (n & 1));
 #pragma unroll
             for (int o = 0; o < GB_CLS; ++o)
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
                 pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
               }
               const int k = k0 + 4 * i;
-              *reinterpret_cast<uint2*>(P.G1 + (((size_t)b * GB_KC + (k >> 3)) * npix1 + row1) * 8 + (k & 7)) = make_uint2(pk[0], pk[1]);
+              *reinterpret_cast<uint2*>(P.G1 + (((size_t)b * GB_KC + (k >> 3)) * P.L1.rows + row1) * 8 + (k & 7)) = make_uint2(pk[0], pk[1]);
             }
           }
         }
@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
 constexpr int B3A_THREADS = 192;  // warp 0 loader, warp 1 MMA, warps 2-5 epilogue (lane = channel)
 
 struct B3aParams {
-  const __nv_bfloat16* G1;   // [B][10][Hi*Wi][8]
+  const __nv_bfloat16* G1;   // [B][10][L.rows][8] padded row layout
+  RowLayout L;
   const __nv_bfloat16* wpk;  // [C4/128][4][10][128][8]
   __nv_bfloat16* dfeat;      // [B][4*C4][(Hi/2)*(Wi/2)]
   int B, C4, Hi, Wi;         // shuffled-image geometry (Hi = 2H, Wi = 2W)
@@ -299,7 +300,6 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  const int npix = Hi * Wi;
   const int n0 = P.nhalf_cols > 256 ? 160 : P.nhalf_cols;  // first MMA's N; the rest goes into a second MMA
   const int n1 = P.nhalf_cols - n0;
 
@@ -311,12 +311,12 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
     int it = 0;
     for (int b = slot; b < P.B; b += nslot, ++it) {
       mbar_wait(g_empty, (it & 1) ^ 1);
-      if (lane == 0) mbar_expect_tx(g_full, (uint32_t)(GB_KC * npix * 16));
-      __syncwarp();
-      for (int i = lane; i < GB_KC * Hi; i += 32) {
-        const int kc = i / Hi, m = i - kc * Hi;
-        bulk_g2s(Gs + ((size_t)kc * rows_alloc + LEAD + (size_t)m * Pp) * 16,
-                 P.G1 + (((size_t)b * GB_KC + kc) * npix + (size_t)m * Wi) * 8, (uint32_t)(Wi * 16), g_full);
+      // the smem operand IS the padded row layout (same lead): one copy per K-chunk
+      const uint32_t nbytes = (uint32_t)((LEAD + Hi * Pp) * 16);
+      if (lane < GB_KC) {
+        if (lane == 0) mbar_expect_tx(g_full, GB_KC * nbytes);
+        __syncwarp((1u << GB_KC) - 1);
+        bulk_g2s(Gs + (size_t)lane * rows_alloc * 16, P.G1 + (((size_t)b * GB_KC + lane) * P.L.rows) * 8, nbytes, g_full);
       }
     }
   } else if (warp == 1) {
@@ -408,9 +408,9 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
 constexpr int WG_THREADS = 192;  // warp 0 loader, warp 1 MMA, warps 2-5 epilogue
 
 struct WgParams {
-  const __nv_bfloat16* X;     // [B][kcx_total][Hi*Wi][8]
-  const __nv_bfloat16* G;     // [B][10][Hi*Wi][8]
-  const __nv_bfloat16* zrow;  // Wi*8 zeros
+  const __nv_bfloat16* X;     // [B][kcx_total][L.rows][8] padded row layout
+  const __nv_bfloat16* G;     // [B][10][L.rows][8]
+  RowLayout L;
   float* dW;                  // [Cin][Cout][3][3], pre-zeroed
   float* dbias;               // [Cout] or null: taken from input channel ones_c
   int B, Hi, Wi;
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   const int N = P.kcx * 8;
   const int ngroups = P.kcx_total / P.kcx;  // kcx_total may include K-chunks beyond the last group (ignored)
   const int grp = blockIdx.x % ngroups, slot = blockIdx.x / ngroups, nslot = gridDim.x / ngroups;
-  const int nchunk = (Hi + R - 1) / R, nunits = P.B * nchunk, npix = Hi * Wi;
+  const int nchunk = Hi / R, nunits = P.B * nchunk;  // R divides Hi (host)
   const uint32_t ncols = 4 * N <= 32 ? 32 : (4 * N <= 64 ? 64 : (4 * N <= 128 ? 128 : (4 * N <= 256 ? 256 : 512)));
 
   for (int i = tid; i < (P.smem_bytes - 64) / 16; i += WG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -461,19 +461,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     for (int u = slot; u < nunits; u += nslot, ++j) {
       const int s = j & 1, b = u / nchunk, y0 = (u - b * nchunk) * R;
       mbar_wait(&empty[s], ((j >> 1) & 1) ^ 1);
-      if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)((GB_KC * R + P.kcx * (R + 1)) * Wi * 16));
+      // one copy per K-chunk: R image rows of G; R + 1 rows of X (the row below is the shifts' halo)
+      const uint32_t gbytes = (uint32_t)(R * Pp * 16), xbytes = (uint32_t)((R + 1) * Pp * 16);
+      if (lane == 0) mbar_expect_tx(&full[s], GB_KC * gbytes + P.kcx * xbytes);
       __syncwarp();
-      for (int i = lane; i < GB_KC * R; i += 32) {
-        const int kc = i / R, yl = i - kc * R, y = y0 + yl;
-        const __nv_bfloat16* srcp = y < Hi ? P.G + (((size_t)b * GB_KC + kc) * npix + (size_t)y * Wi) * 8 : P.zrow;
-        bulk_g2s(Gs + (size_t)s * g_bytes + ((size_t)kc * KR + (size_t)yl * Pp) * 16, srcp, (uint32_t)(Wi * 16), &full[s]);
-      }
-      for (int i = lane; i < P.kcx * (R + 1); i += 32) {
-        const int kc = i / (R + 1), yl = i - kc * (R + 1), y = y0 + yl;
-        const __nv_bfloat16* srcp =
-            y < Hi ? P.X + (((size_t)b * P.kcx_total + (size_t)grp * P.kcx + kc) * npix + (size_t)y * Wi) * 8 : P.zrow;
-        bulk_g2s(Xs + (size_t)s * x_bytes + ((size_t)kc * XR + (size_t)yl * Pp) * 16, srcp, (uint32_t)(Wi * 16), &full[s]);
-      }
+      const size_t row0 = (size_t)P.L.lead + (size_t)y0 * Pp;
+      if (lane < GB_KC)
+        bulk_g2s(Gs + (size_t)s * g_bytes + (size_t)lane * KR * 16, P.G + (((size_t)b * GB_KC + lane) * P.L.rows + row0) * 8, gbytes,
+                 &full[s]);
+      if (lane < P.kcx)
+        bulk_g2s(Xs + (size_t)s * x_bytes + (size_t)lane * XR * 16,
+                 P.X + (((size_t)b * P.kcx_total + (size_t)grp * P.kcx + lane) * P.L.rows + row0) * 8, xbytes, &full[s]);
     }
   } else if (warp == 1) {
     const uint32_t idesc = tc::make_idesc_bf16_f32(128, N) | (1u << 15) | (1u << 16);  // both operands MN-major
@@ -531,13 +529,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   if (warp == 1) tc::tmem_dealloc(tmem_base, ncols);
 }
 
-static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, const __nv_bfloat16* zrow, float* dW, float* dbias,
-                        int B, int Hi, int Wi, int R, int kcx, int kcx_total, int Cin, int Cout, int ones_c, int sms,
-                        cudaStream_t s) {
+static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, float* dW, float* dbias, int B, int Hi, int Wi,
+                        int kcx, int kcx_total, int Cin, int Cout, int ones_c, int sms, cudaStream_t s) {
+  // image rows per unit: the largest divisor of Hi (<= 8) whose two stages fit in shared memory
+  int R = 0;
+  for (int r = Hi < 8 ? Hi : 8; r >= 1; --r) {
+    if (Hi % r) continue;
+    const int kr = (r * (Wi + 1) + 15) & ~15, xr = (kr + Wi + 2 + 7) & ~7;
+    if ((size_t)2 * GB_KC * kr * 16 + (size_t)2 * kcx * xr * 16 + 64 <= 225 * 1024) {
+      R = r;
+      break;
+    }
+  }
+  LPB_REQUIRE(R >= 1, "head_bwd_bf16: image width %d too large for the weight-gradient stages", Wi);
   WgParams p;
   p.X = X;
   p.G = G;
-  p.zrow = zrow;
+  p.L = make_row_layout(Hi, Wi);
   p.dW = dW;
   p.dbias = dbias;
   p.B = B;
@@ -560,7 +568,7 @@ static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, const __
   LPB_REQUIRE(p.smem_bytes <= 225 * 1024, "head_bwd_bf16: weight-gradient stages need %d B shared memory", p.smem_bytes);
   LPB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
   const int ngroups = kcx_total / kcx;
-  const int nunits = B * ((Hi + R - 1) / R);
+  const int nunits = B * (Hi / R);
   int slots = sms / ngroups;
   if (slots < 1) slots = 1;
   if (slots > nunits) slots = nunits;
@@ -570,15 +578,15 @@ static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, const __
 
 }  // namespace lpb
 
-// workspace: [W1 dgrad pack][W2 dgrad pack][zero row][G2][G1]
+// workspace: [W1 dgrad pack][W2 dgrad pack][G2][G1]   (G2 / G1: padded row layouts, row_layout.cuh)
 extern "C" int lpb_head_bwd_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes) {
   using namespace lpb;
   LPB_REQUIRE(bytes, "head_bwd_bf16_workspace_bytes: null pointer");
   LPB_REQUIRE(B >= 0 && C >= 512 && C % 512 == 0 && H >= 1 && W >= 1 && c1 >= 1 && c2 >= 1, "head_bwd_bf16_workspace_bytes: bad shape");
   const size_t w1 = (size_t)(C / 4 / 128) * 4 * GB_KC * 128 * 16, w2 = (size_t)4 * GB_KC * 32 * 16;
-  const size_t zrow = ((size_t)4 * W * 16 + 255) & ~(size_t)255;
-  const size_t g2 = (size_t)B * GB_KC * (16 * H * W) * 16, g1 = (size_t)B * GB_KC * (4 * H * W) * 16;
-  *bytes = w1 + w2 + zrow + g2 + g1;
+  const size_t g2 = (size_t)B * GB_KC * make_row_layout(4 * H, 4 * W).rows * 16;
+  const size_t g1 = (size_t)B * GB_KC * make_row_layout(2 * H, 2 * W).rows * 16;
+  *bytes = w1 + w2 + g2 + g1;
   return LPB_OK;
 }
 
@@ -604,34 +612,34 @@ extern "C" int lpb_head_bwd_bf16(const float* g_logits, const void* saved_xs, co
   int dev = 0, sms = 0;
   LPB_CUDA(cudaGetDevice(&dev));
   LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const RowLayout L2 = make_row_layout(Hi2, Wi2), L1 = make_row_layout(Hi1, Wi1);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   const size_t w1b = (size_t)(C4 / 128) * 4 * GB_KC * 128 * 16, w2b = (size_t)4 * GB_KC * 32 * 16;
-  const size_t zrowb = ((size_t)4 * W * 16 + 255) & ~(size_t)255;
   __nv_bfloat16* wp1 = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* wp2 = reinterpret_cast<__nv_bfloat16*>(ws + w1b);
-  __nv_bfloat16* zrow = reinterpret_cast<__nv_bfloat16*>(ws + w1b + w2b);
-  __nv_bfloat16* G2 = reinterpret_cast<__nv_bfloat16*>(ws + w1b + w2b + zrowb);
-  __nv_bfloat16* G1 = reinterpret_cast<__nv_bfloat16*>(ws + w1b + w2b + zrowb + (size_t)B * GB_KC * Hi2 * Wi2 * 16);
-  // the forward pass's mid activations (head_bf16.cu workspace layout: [packed w1][packed w2][zero row][mid])
-  const size_t fwd_mid_off = (size_t)(C4 / 32 + 1) * (4 * 4 * 80 * 16) + zrowb;
+  __nv_bfloat16* G2 = reinterpret_cast<__nv_bfloat16*>(ws + w1b + w2b);
+  __nv_bfloat16* G1 = reinterpret_cast<__nv_bfloat16*>(ws + w1b + w2b + (size_t)B * GB_KC * L2.rows * 16);
+  // the forward pass's mid activations (head_bf16.cu workspace layout: [packed w1][packed w2][mid])
+  const size_t fwd_mid_off = (size_t)(C4 / 32 + 1) * (4 * 4 * 80 * 16);
   const __nv_bfloat16* mid = reinterpret_cast<const __nv_bfloat16*>(static_cast<const unsigned char*>(fwd_workspace) + fwd_mid_off);
 
-  pack_dgrad_weights_kernel<<<128, 256, 0, s>>>(w1, C4, c1, C4 / 128, 128, wp1, zrow, (int)(zrowb / 2));
+  pack_dgrad_weights_kernel<<<128, 256, 0, s>>>(w1, C4, c1, C4 / 128, 128, wp1, nullptr, 0);
   pack_dgrad_weights_kernel<<<8, 256, 0, s>>>(w2, c1, c2, 1, 32, wp2, nullptr, 0);
-  g_relayout_kernel<<<(unsigned)(B * Hi2), 64, 0, s>>>(g_logits, B, c2, Hi2, Wi2, G2);
+  launch_zero_row_pads(G2, L2, (long long)B * GB_KC, stream);
+  launch_zero_row_pads(G1, L1, (long long)B * GB_KC, stream);
+  g_relayout_kernel<<<(unsigned)(B * Hi2), 64, 0, s>>>(g_logits, B, c2, Hi2, Wi2, G2, L2);
   // layer 2: weight + bias gradient (bias from the all-ones channel c1 of mid), then data gradient -> G1 (+ db1)
   {
-    int R = 8;
-    while (R > 1 && ((size_t)2 * GB_KC * ((R * (Wi2 + 1) + 15) & ~15) * 16 + 2 * 4 * (((R * (Wi2 + 1) + 15) & ~15) + Wi2 + 10) * 16) > 200 * 1024) --R;
-    const int rc = launch_wgrad(mid, G2, zrow, dw2, db2, B, Hi2, Wi2, R, 4, 4, c1, c2, c1, sms, s);
+    const int rc = launch_wgrad(mid, G2, dw2, db2, B, Hi2, Wi2, 4, 4, c1, c2, c1, sms, s);
     if (rc != LPB_OK) return rc;
   }
   {
     B2dParams p;
     p.G2 = G2;
-    p.zrow = zrow;
     p.wpk = wp2;
     p.G1 = G1;
+    p.L2 = L2;
+    p.L1 = L1;
     p.db1 = db1;
     p.B = B;
     p.Hi = Hi2;
@@ -646,15 +654,13 @@ extern "C" int lpb_head_bwd_bf16(const float* g_logits, const void* saved_xs, co
   }
   // layer 1: weight gradient from the saved shuffled features, data gradient -> d features
   {
-    int R = 8;
-    while (R > 1 && ((size_t)2 * GB_KC * ((R * (Wi1 + 1) + 15) & ~15) * 16 + 2 * 16 * (((R * (Wi1 + 1) + 15) & ~15) + Wi1 + 10) * 16) > 200 * 1024) --R;
-    const int rc = launch_wgrad(static_cast<const __nv_bfloat16*>(saved_xs), G1, zrow, dw1, nullptr, B, Hi1, Wi1, R, 16, C4 / 8, C4,
-                                c1, -1, sms, s);
+    const int rc = launch_wgrad(static_cast<const __nv_bfloat16*>(saved_xs), G1, dw1, nullptr, B, Hi1, Wi1, 16, C4 / 8, C4, c1, -1, sms, s);
     if (rc != LPB_OK) return rc;
   }
   if (dfeat) {
     B3aParams p;
     p.G1 = G1;
+    p.L = L1;
     p.wpk = wp1;
     p.dfeat = static_cast<__nv_bfloat16*>(dfeat);
     p.B = B;

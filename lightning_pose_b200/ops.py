@@ -185,7 +185,10 @@ def _head_forward_bf16(f, weights, biases, final_softmax, train=False):
     ws = torch.empty((nbytes.value,), device=f.device, dtype=torch.uint8)
     out = torch.empty((b, c2, 8 * h, 8 * w), device=f.device, dtype=torch.float32)
     native_bwd = train and c % 512 == 0 and w % 4 == 0 and ((h * (2 * w + 1) + 15) & ~15) <= 304
-    xs = torch.empty_like(f) if native_bwd else None
+    xs = None
+    if native_bwd:  # row-layout copy of the shuffled features for the weight-gradient GEMM
+        check(lib.lpb_head_bf16_saved_bytes(b, c, h, w, C.byref(nbytes)))
+        xs = torch.empty((nbytes.value,), device=f.device, dtype=torch.uint8)
     with torch.cuda.device(f.device):
         check(lib.lpb_head_fwd_bf16(_ptr(f), b, c, h, w, _ptr(w1), _ptr(b1), c1, _ptr(w2), _ptr(b2), c2, int(bool(final_softmax)), _ptr(out), _ptr(xs), _ptr(ws), _stream()))
     if train:

@@ -36,8 +36,13 @@ for softmax in (0, 1):
     check(lib.lpb_head_fwd_bf16(p(args[0]), B, Cf, H, W, p(args[1]), p(args[2]), K, p(args[3]), p(args[4]), K, softmax, p(out), None, p(ws), None))
     torch.cuda.synchronize()
     nst = Cf // 4 // 32
-    zrow = (4 * W * 16 + 255) // 256 * 256
-    mid = ws[(nst + 1) * 20480 + zrow :].view(torch.bfloat16).reshape(B, 4, 48 * 48, 8).permute(0, 1, 3, 2).reshape(B, 32, 48, 48).float().cpu()
+    # mid lives in the padded row layout (csrc/row_layout.cuh): rows = lead + y * (Wi + 1) + x, lead = Wi + 2
+    Hi, Wi = 4 * H, 4 * W
+    lead, rows = Wi + 2, (Hi * (Wi + 1) + 2 * (Wi + 2) + 7) // 8 * 8
+    slab = ws[(nst + 1) * 20480 :].view(torch.bfloat16).reshape(B, 4, rows, 8)
+    body = slab[:, :, lead : lead + Hi * (Wi + 1)].reshape(B, 4, Hi, Wi + 1, 8)
+    pads_zero = float(slab[:, :, :lead].abs().max()) == 0 and float(body[:, :, :, Wi].abs().max()) == 0 and float(slab[:, :, lead + Hi * (Wi + 1) :].abs().max()) == 0
+    mid = body[:, :, :, :Wi].permute(0, 1, 4, 2, 3).reshape(B, 32, Hi, Wi).float().cpu()
     e_mid = (mid[:, :K] - mid_ref).abs().max().item()
     pad = mid[:, K + 1 :].abs().max().item()  # channel K is the constant-one channel
     ref = hm_ref if softmax else logit_ref
@@ -46,5 +51,5 @@ for softmax in (0, 1):
     rel = ((o - ref).abs() / (ref.abs() + 1e-6)).max().item() if softmax else err / ref.abs().max().item()
     print(f"softmax={softmax} swap={os.environ.get('LPB_DESC_SWAP','0')}: mid max|err|={e_mid:.4g} (ref max {mid_ref.abs().max():.3g}), pad={pad:.3g}; "
           f"out max|err|={err:.4g} rel={rel:.4g} sums={o.sum((2,3)).flatten()[:3].tolist() if softmax else ''}")
-    ok = e_mid < 0.05 * mid_ref.abs().max().item() and (rel < 2e-2)
+    ok = e_mid < 0.05 * mid_ref.abs().max().item() and (rel < 2e-2) and pads_zero
     print("RESULT", "PASS" if ok else "FAIL")
