@@ -155,8 +155,12 @@ def make_problem(n_clips: int, seed: int, device, regime: str = "trained"):
 # ------------------------------------------------------------------------------------------------
 class HotPath:
     # our own kernel launches per step (library kernels of torch are not counted)
-    LAUNCHES_FWD = 4 + 1 + 2 + 1 + 1  # head (2 weight packs + k1a + k1b), decode, target+mse (2), remap, unsup losses
-    LAUNCHES_BWD = 1 + 1 + 1 + 1 + 1  # unsup bwd, remap bwd, decode bwd, target+mse bwd, plane-softmax bwd
+    # per head call: 2 weight packs + 2 pad clears + k1a + k1b + decode = 7 (two calls: labeled, unlabeled);
+    # + target+mse (2) + remap + unsup losses
+    LAUNCHES_FWD = 2 * 7 + 2 + 1 + 1
+    # unsup bwd, remap bwd, target+mse bwd; per head backward: 2 packs + 2 pad clears + plane dots + G2 front end
+    # + wgrad2 + dgrad2 + wgrad1 + dgrad1 = 10 (x2), + decode windows and its dense-fallback launch (unlabeled)
+    LAUNCHES_BWD = 3 + 2 * 10 + 2
 
     def __init__(self, prob, device, fwd_only: bool, world: int = 1):
         from lightning_pose_b200 import ops
@@ -179,15 +183,19 @@ class HotPath:
     def step(self, feats: torch.Tensor):
         ops, n = self.ops, self.n_clips
         nl = n * B_LABELED
+        # the reference runs the labeled and the unlabeled batch through the model separately
+        # (heatmap_tracker.py:163-179, :299-340): two feature tensors, two head calls
+        f_lab, f_unl = feats[:nl].detach(), feats[nl:].detach()
         if not self.fwd_only:
             self.opt.zero_grad(set_to_none=True)
-            feats = feats.detach().requires_grad_(True)  # d loss / d features feeds the backbone's backward
+            f_lab.requires_grad_(True)  # d loss / d features feeds the backbone's backward
+            f_unl.requires_grad_(True)
         with torch.set_grad_enabled(not self.fwd_only):
-            hm = self.head(feats)  # (n*48, 17, 96, 96)
-            l_sup = ops.heatmap_mse_from_keypoints(self.kp_lab, hm[:nl], IMG, IMG, visibility=self.vis)
-            kp, cf = ops.decode_softargmax(hm, 2, 1000.0)
-            kp_unl = ops.remap_keypoints(kp[nl:], self.tf, self.bbox, IMG, IMG)
-            per_clip = ops.unsup_losses(kp_unl.reshape(n, T_UNLABELED, 2 * K_PTS), cf[nl:].reshape(n, T_UNLABELED, K_PTS),
+            hm_lab, _kp_lab, _cf_lab = self.head.forward_with_keypoints(f_lab)  # (n*16, 17, 96, 96); keypoints -> rmse metric
+            l_sup = ops.heatmap_mse_from_keypoints(self.kp_lab, hm_lab, IMG, IMG, visibility=self.vis)
+            _hm_unl, kp, cf = self.head.forward_with_keypoints(f_unl)  # (n*32, ...)
+            kp_unl = ops.remap_keypoints(kp, self.tf, self.bbox, IMG, IMG)
+            per_clip = ops.unsup_losses(kp_unl.reshape(n, T_UNLABELED, 2 * K_PTS), cf.reshape(n, T_UNLABELED, K_PTS),
                                         temporal_eps=self.teps, prob_threshold=0.05, pca_singleview=self.sv)
             total = 0.5 * l_sup + self.w_unsup * per_clip[:, :2].sum()
         scalars = [total.detach(), l_sup.detach(), per_clip[:, 0].mean().detach(), per_clip[:, 1].mean().detach()]
@@ -321,7 +329,7 @@ def run_ours(args):
         "config": {
             "workload": f"BASELINE configs[1] hot path on ResNet-50 features (B,2048,12,12): {args.clips} clips/step/GPU x (16 labeled + 32 unlabeled) frames, "
                         f"K=17, heatmaps 96x96, decode field 384x384; pass = {'forward' if args.fwd_only else 'forward + backward + Adam step on the head (+ one flat all-reduce when N>1)'}",
-            "backward": "native kernels: loss stack, remap, soft-argmax decode, target+mse, plane softmax; torch library (cuDNN): dgrad/wgrad of the two transposed convolutions (interim, DESIGN.md 7)",
+            "backward": "all native: loss stack, remap, sparse soft-argmax windows, target+mse, fused softmax-backward/G2 front end, tcgen05 dgrad+wgrad of both transposed convolutions; torch library: fused Adam on the head parameters",
             "frames_per_step_per_gpu": n_frames, "regime": ("trained-like synthetic response (unimodal Gaussian-like heatmaps; planted features + bilinear per-keypoint deconvs, see bench.make_problem); fresh_init_regime = reference initialiser"
                                                                                   if args.regime == "trained" else "fresh init (reference initialiser, flat heatmaps)"),
             "l2_policy": f"inputs larger than L2 ({feats.numel() * esz / 2**20:.0f} MiB of features per step)", "parallelism": f"dp{world}",

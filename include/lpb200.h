@@ -59,6 +59,14 @@ int lpb_decode_fwd(const float* heatmaps, int64_t n_planes, int h, int w, int ds
 int lpb_decode_bwd(const float* heatmaps, const float* stats, const float* grad_xy, int64_t n_planes,
                    int h, int w, int ds, float temperature, float* grad_heatmaps, void* stream);
 
+/* sparse form of lpb_decode_bwd for the fused head backward: per plane a 32x32 window of d loss / d heatmap
+ * (win [n_planes, 32, 32]) and meta [n_planes, 4] = {window row0, col0, flag, float bits of sum(win * heatmap)};
+ * flag 0: zero gradient, 1: window valid, 2: the support does not fit a window -- that plane's dense
+ * gradient is written to g_overflow [n_planes, h, w] instead (other planes of g_overflow are not touched). */
+int lpb_decode_bwd_windows(const float* heatmaps, const float* stats, const float* grad_xy, int64_t n_planes, int h,
+                           int w, int ds, float temperature, float* win, int32_t* meta, float* g_overflow,
+                           void* stream);
+
 /* one materialised upsampling stage: drop-in for `upsample`
  *   lightning_pose/models/heads/heatmap.py:86-100 ; in [n_planes,h,w] -> out [n_planes,2h,2w] */
 int lpb_upsample2x(const float* in, int64_t n_planes, int h, int w, float* out, void* stream);
@@ -112,14 +120,19 @@ int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int W, const fl
  * lpb_head_bwd_bf16. */
 int lpb_head_bf16_saved_bytes(int B, int C, int H, int W, size_t* bytes);
 
-/* backward of lpb_head_fwd_bf16 (replaces autograd through heatmap.py:203-212; four tcgen05 kernels:
- * layer-2 wgrad, layer-2 dgrad, layer-1 wgrad, layer-1 dgrad + inverse PixelShuffle).
- * g_logits [B, c2, 8H, 8W] fp32: gradient at the output of the second deconv (after lpb_plane_softmax_bwd
- *   when the head ends in a softmax).
+/* backward of lpb_head_fwd_bf16 (replaces autograd through heatmap.py:203-212 and, fused into its front end,
+ * through spatial_softmax2d :211 and run_subpixelmaxima :103-144).  Kernels: gradient front end (G2 writer),
+ * layer-2 wgrad, layer-2 dgrad, layer-1 wgrad, layer-1 dgrad + inverse PixelShuffle (all tcgen05).
+ * The gradient w.r.t. the head OUTPUT [B, c2, 8H, 8W] is the sum of
+ *   g_out        dense fp32 gradient (heatmap losses), or NULL
+ *   win/win_meta/g_overflow   sparse soft-argmax gradient from lpb_decode_bwd_windows, or NULL/NULL/NULL
+ * probs: the head output itself when the head ends in the spatial softmax (its backward is applied on the fly),
+ *   NULL when the head returns logits.
  * dfeat [B, C, H, W] bf16 or NULL (frozen backbone); dw1 [C/4, c1, 3, 3], db1 [c1], dw2 [c1, c2, 3, 3],
  * db2 [c2] fp32 (overwritten).  workspace: lpb_head_bwd_bf16_workspace_bytes(). */
 int lpb_head_bwd_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes);
-int lpb_head_bwd_bf16(const float* g_logits, const void* saved_xs, const void* fwd_workspace, int B, int C, int H,
+int lpb_head_bwd_bf16(const float* g_out, const float* probs, const float* win, const int32_t* win_meta,
+                      const float* g_overflow, const void* saved_xs, const void* fwd_workspace, int B, int C, int H,
                       int W, const float* w1, int c1, const float* w2, int c2, void* dfeat, float* dw1, float* db1,
                       float* dw2, float* db2, void* workspace, void* stream);
 

@@ -479,6 +479,7 @@ struct DecodeBwdParams {
   const float* tabH;
   const float* tabW;
   float* gheat;
+  const int* only_meta;  // optional [n_planes][4]: process only planes whose meta flag (word 2) is 2
   int h, w, pitch, padl, bulk;
   float T;
   float phase[F][W];
@@ -495,6 +496,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_co
   uint64_t* bar = reinterpret_cast<uint64_t*>(gtile + tile_floats);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t plane = blockIdx.x;
+  if (P.only_meta && P.only_meta[4 * plane + 2] != 2) return;  // window path took this plane (uniform per CTA)
   const float* __restrict__ src = P.heat + plane * (size_t)h * w;
 
   if (P.bulk) {
@@ -630,6 +632,134 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_co
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Sparse form of the decode backward.  With T = 1000 the softmax weights vanish a few fine pixels away from
+// the peak, so d loss / d heatmap is supported on the forward pass's candidate box dilated by the R-tap halo:
+// a window of at most DEC_WIN x DEC_WIN coarse pixels instead of the whole plane.  One warp per plane loads that
+// window straight from global memory, runs the same transpose-of-the-upsample accumulation as decode_bwd_kernel
+// and emits   win[plane][32][32], meta[plane] = {row0, col0, flag, bits(sum(win * heat))}
+// flag 0: zero gradient, 1: window valid, 2: the box does not fit (dense fallback plane, decode_bwd_kernel).
+constexpr int DEC_WIN = 32, DEC_WP = 33;
+
+template <int DS>
+__global__ void __launch_bounds__(128) decode_bwd_window_kernel(const __grid_constant__ DecodeBwdParams<DS> P, float* __restrict__ win,
+                                                                int* __restrict__ meta, long long n_planes) {
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  __shared__ float tile_s[4][DEC_WIN * DEC_WP];
+  __shared__ float g_s[4][DEC_WIN * DEC_WP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long plane = (long long)blockIdx.x * 4 + warp;
+  if (plane >= n_planes) return;
+  const int h = P.h, w = P.w;
+  const float gx = P.gxy[2 * plane], gy = P.gxy[2 * plane + 1];
+  int4* mout = reinterpret_cast<int4*>(meta) + plane;
+  if (gx == 0.f && gy == 0.f) {
+    if (lane == 0) *mout = make_int4(0, 0, 0, 0);
+    return;
+  }
+  const float* st = P.stats + 8 * plane;
+  const float M = st[0], S = st[1], xhat = st[2], yhat = st[3];
+  const int A0 = (int)st[4], A1 = (int)st[5], B0 = (int)st[6], B1 = (int)st[7];
+  const int nrows = A1 - A0 + 1, ncols = B1 - B0 + 1;
+  if (nrows > DEC_WIN - 2 * R || ncols > DEC_WIN - 2 * R || nrows < 1 || ncols < 1) {
+    if (lane == 0) *mout = make_int4(0, 0, 2, 0);
+    return;
+  }
+  float* tile = tile_s[warp];
+  float* gt = g_s[warp];
+  const int r0w = A0 - R, c0w = B0 - R;
+  const float* __restrict__ src = P.heat + (size_t)plane * h * w;
+  {
+    const int x = c0w + lane;
+    const bool xin = x >= 0 && x < w;
+#pragma unroll 8
+    for (int r = 0; r < DEC_WIN; ++r) {
+      const int y = r0w + r;
+      tile[r * DEC_WP + lane] = (xin && y >= 0 && y < h) ? __ldg(src + (size_t)y * w + x) : 0.f;
+      gt[r * DEC_WP + lane] = 0.f;
+    }
+  }
+  __syncwarp();
+  const float c = P.T * 1.4426950408889634f;
+  const float kscale = P.T / S;
+  const int J0 = B0 * F, J1 = (B1 + 1) * F;
+  const int nstrips = (J1 - J0 + 31) >> 5;
+  for (int sidx = 0; sidx < nstrips; ++sidx) {
+    const int jf = J0 + sidx * 32 + lane;
+    const bool ok = jf < J1;
+    const int jc = ok ? jf : (J1 - 1);
+    float wc[W];
+#pragma unroll
+    for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
+    const int cbl = jc / F - B0;  // window column of coarse column jc/F - R
+    const float* colbase = tile + cbl;
+    float tmp[W], gacc[W];
+#pragma unroll
+    for (int t = 0; t < W; ++t) {
+      tmp[t] = dot_w<W>(colbase + t * DEC_WP, wc);
+      gacc[t] = 0.f;
+    }
+    const float dx = (float)jf - xhat;
+    for (int a = A0; a <= A1; ++a) {
+      const int la = a - A0;
+      const bool interior = (a >= R && a <= h - 1 - R);
+      const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
+#pragma unroll
+      for (int p = 0; p < F; ++p) {
+        float wr[W];
+#pragma unroll
+        for (int t = 0; t < W; ++t) wr[t] = interior ? P.phase[p][t] : __ldg(tr + p * W + t);
+        float v = 0.f;
+#pragma unroll
+        for (int t = 0; t < W; ++t) v = fmaf(wr[t], tmp[t], v);
+        const float pr = fast_exp2((v - M) * c);
+        const float gval = ok ? kscale * pr * fmaf(dx, gx, ((float)(a * F + p) - yhat) * gy) : 0.f;
+#pragma unroll
+        for (int t = 0; t < W; ++t) gacc[t] = fmaf(wr[t], gval, gacc[t]);
+      }
+      {
+        float* grow = gt + la * DEC_WP + cbl;
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+          float val = gacc[0] * wc[u];
+#pragma unroll
+          for (int o = 1; o < F; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+          if ((lane & (F - 1)) == 0 && val != 0.f) atomicAdd(grow + u, val);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < W - 1; ++t) {
+        gacc[t] = gacc[t + 1];
+        tmp[t] = tmp[t + 1];
+      }
+      gacc[W - 1] = 0.f;
+      tmp[W - 1] = (a + 1 <= A1) ? dot_w<W>(colbase + (la + 1 + 2 * R) * DEC_WP, wc) : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < W - 1; ++t) {
+      float* grow = gt + (nrows + t) * DEC_WP + cbl;
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+        float val = gacc[t] * wc[u];
+#pragma unroll
+        for (int o = 1; o < F; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        if ((lane & (F - 1)) == 0 && val != 0.f) atomicAdd(grow + u, val);
+      }
+    }
+    __syncwarp();
+  }
+  float dot = 0.f;
+  float* wout = win + (size_t)plane * (DEC_WIN * DEC_WIN);
+#pragma unroll 8
+  for (int r = 0; r < DEC_WIN; ++r) {
+    const float g = gt[r * DEC_WP + lane];
+    dot = fmaf(g, tile[r * DEC_WP + lane], dot);
+    wout[r * DEC_WIN + lane] = g;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) *mout = make_int4(r0w, c0w, 1, __float_as_int(dot));
+}
+
 // One materialised upsampling stage (drop-in for `upsample`, lightning_pose/models/heads/heatmap.py:86-100).
 // Not on the fused path (the decode never materialises the field); kept for API completeness.
 __global__ void __launch_bounds__(DEC_THREADS) upsample2x_kernel(const float* __restrict__ in, int h, int w, int pitch,
@@ -697,7 +827,7 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
 
 template <int DS>
 static int launch_decode_bwd(const float* heat, const float* stats, const float* gxy, int64_t n_planes, int h, int w,
-                             float T, float* gheat, cudaStream_t stream) {
+                             float T, float* gheat, cudaStream_t stream, float* win = nullptr, int* meta = nullptr) {
   using G = UpsampleGeom<DS>;
   const DeviceTable* th = get_device_table(h, DS);
   const DeviceTable* tw = get_device_table(w, DS);
@@ -709,6 +839,7 @@ static int launch_decode_bwd(const float* heat, const float* stats, const float*
   P.tabH = th->win;
   P.tabW = tw->win;
   P.gheat = gheat;
+  P.only_meta = meta;
   P.h = h;
   P.w = w;
   P.padl = dec_padl(G::R);
@@ -717,6 +848,9 @@ static int launch_decode_bwd(const float* heat, const float* stats, const float*
   P.T = T;
   for (int p = 0; p < G::F; ++p)
     for (int t = 0; t < G::W; ++t) P.phase[p][t] = th->host.phase[(size_t)p * G::W + t];
+  if (win) {  // sparse windows first; the dense kernel below then only runs the planes they flagged
+    decode_bwd_window_kernel<DS><<<(unsigned)((n_planes + 3) / 4), 128, 0, stream>>>(P, win, meta, (long long)n_planes);
+  }
   const size_t smem = ((size_t)2 * (h + 2 * G::R) * P.pitch) * sizeof(float) + 16;
   int dev = 0, max_smem = 0;
   LPB_CUDA(cudaGetDevice(&dev));
@@ -771,6 +905,22 @@ extern "C" int lpb_decode_bwd(const float* heatmaps, const float* stats, const f
     case 1: return launch_decode_bwd<1>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, grad_heatmaps, s);
     case 2: return launch_decode_bwd<2>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, grad_heatmaps, s);
     default: return launch_decode_bwd<3>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, grad_heatmaps, s);
+  }
+}
+
+extern "C" int lpb_decode_bwd_windows(const float* heatmaps, const float* stats, const float* grad_xy, int64_t n_planes, int h,
+                                      int w, int ds, float temperature, float* win, int32_t* meta, float* g_overflow,
+                                      void* stream) {
+  using namespace lpb;
+  LPB_REQUIRE(heatmaps && stats && grad_xy && win && meta && g_overflow, "decode_bwd_windows: null pointer");
+  LPB_REQUIRE(h >= 1 && w >= 1 && ds >= 1 && ds <= 3, "decode_bwd_windows: bad shape h=%d w=%d ds=%d", h, w, ds);
+  LPB_REQUIRE(n_planes >= 0 && n_planes < (1ll << 31), "decode_bwd_windows: bad n_planes");
+  if (n_planes == 0) return LPB_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (ds) {
+    case 1: return launch_decode_bwd<1>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, g_overflow, s, win, meta);
+    case 2: return launch_decode_bwd<2>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, g_overflow, s, win, meta);
+    default: return launch_decode_bwd<3>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, g_overflow, s, win, meta);
   }
 }
 

@@ -23,20 +23,101 @@ constexpr int GB_CLS = 20;            // class stride in K
 constexpr int GB_K = 4 * GB_CLS;      // 80
 constexpr int GB_KC = GB_K / 8;       // 10 K-chunks
 
-// ---- g_logits (fp32, NCHW) -> G2 row layout (bf16) ------------------------------------------------------
+// ---- gradient front end: everything upstream of the second deconv's output, fused into the G2 writer --------
+// The gradient w.r.t. the head output arrives as a sum of
+//   g_out   dense [B, c2, Ho, Wo] fp32 (heatmap losses)                      -- optional
+//   win     sparse 32x32 windows of the soft-argmax decode (decode.cu)        -- optional, flag 2 = dense plane in gov
+// and, when the head ends in the spatial softmax, is pulled back through it on the fly:
+//   g_logit = p * (g - dot),  dot = sum_plane(g * p) = ddot (dense part, plane_dot_kernel) + window dot (meta).
+// Neither the dense decode gradient, nor its sum with g_out, nor g_logit ever exist in memory.
+struct G2Src {
+  const float* g_out;   // or null
+  const float* probs;   // head output when it ends in softmax, else null
+  const float* win;     // [planes][32*32] or null
+  const int* meta;      // [planes][4] {row0, col0, flag, bits(dot)}
+  const float* gov;     // dense fallback planes (flag 2)
+  const float* ddot;    // [planes] dense part of the softmax dot (valid when probs && (g_out || win))
+};
+
+// ddot[plane] = sum(p * (g_out + [flag == 2] gov)); one CTA per plane
+__global__ void __launch_bounds__(256) plane_dot_kernel(G2Src S, int hw, float* __restrict__ ddot) {
+  const size_t plane = blockIdx.x;
+  const bool ov = S.meta && S.meta[4 * plane + 2] == 2;
+  float acc = 0.f;
+  if (S.g_out || ov) {
+    const float4* p4 = reinterpret_cast<const float4*>(S.probs + plane * hw);
+    const float4* g4 = S.g_out ? reinterpret_cast<const float4*>(S.g_out + plane * hw) : nullptr;
+    const float4* o4 = ov ? reinterpret_cast<const float4*>(S.gov + plane * hw) : nullptr;
+    for (int i = threadIdx.x; i < hw / 4; i += 256) {
+      const float4 p = __ldg(p4 + i);
+      float4 g = g4 ? __ldg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o4) {
+        const float4 o = __ldg(o4 + i);
+        g.x += o.x, g.y += o.y, g.z += o.z, g.w += o.w;
+      }
+      acc += p.x * g.x + p.y * g.y + p.z * g.z + p.w * g.w;
+    }
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    ddot[plane] = t;
+  }
+}
+
 // one CTA per (frame, m); thread n handles the 2x2 output block of row (m, n) for all channels
-__global__ void __launch_bounds__(64) g_relayout_kernel(const float* __restrict__ gl, int B, int C, int Hi, int Wi,
-                                                        __nv_bfloat16* __restrict__ G, RowLayout L) {
+__global__ void __launch_bounds__(64) g2_build_kernel(G2Src S, int B, int C, int Hi, int Wi, __nv_bfloat16* __restrict__ G,
+                                                      RowLayout L) {
   const int b = blockIdx.x / Hi, m = blockIdx.x - b * Hi;
   const int Wo = 2 * Wi, Ho = 2 * Hi;
+  __shared__ int4 smeta[GB_CLS];
+  __shared__ float sdot[GB_CLS];
+  if (threadIdx.x < GB_CLS) {
+    int4 mt = make_int4(0, 0, 0, 0);
+    float d = 0.f;
+    if (threadIdx.x < C) {
+      const size_t plane = (size_t)b * C + threadIdx.x;
+      if (S.meta) mt = reinterpret_cast<const int4*>(S.meta)[plane];
+      if (S.probs) d = (mt.z == 1 ? __int_as_float(mt.w) : 0.f) + (S.ddot ? S.ddot[plane] : 0.f);
+    }
+    smeta[threadIdx.x] = mt;
+    sdot[threadIdx.x] = d;
+  }
+  __syncthreads();
   for (int n = threadIdx.x; n < Wi; n += blockDim.x) {
 #pragma unroll
     for (int py = 0; py < 2; ++py) {
+      const int y = 2 * m + py, x = 2 * n;
       float v0[GB_CLS], v1[GB_CLS];
 #pragma unroll
       for (int o = 0; o < GB_CLS; ++o) {
         float2 t = make_float2(0.f, 0.f);
-        if (o < C) t = __ldg(reinterpret_cast<const float2*>(gl + (((size_t)b * C + o) * Ho + 2 * m + py) * Wo + 2 * n));
+        if (o < C) {
+          const size_t off = (((size_t)b * C + o) * Ho + y) * Wo + x;
+          if (S.g_out) t = __ldg(reinterpret_cast<const float2*>(S.g_out + off));
+          const int4 mt = smeta[o];
+          if (mt.z == 1) {
+            const int ly = y - mt.x, lx = x - mt.y;
+            if ((unsigned)ly < 32u) {
+              const float* wr = S.win + ((size_t)b * C + o) * 1024 + ly * 32;
+              if ((unsigned)lx < 32u) t.x += __ldg(wr + lx);
+              if ((unsigned)(lx + 1) < 32u) t.y += __ldg(wr + lx + 1);
+            }
+          } else if (mt.z == 2) {
+            const float2 u = __ldg(reinterpret_cast<const float2*>(S.gov + off));
+            t.x += u.x, t.y += u.y;
+          }
+          if (S.probs) {
+            const float2 p = __ldg(reinterpret_cast<const float2*>(S.probs + off));
+            const float d = sdot[o];
+            t.x = p.x * (t.x - d);
+            t.y = p.y * (t.y - d);
+          }
+        }
         v0[o] = t.x;
         v1[o] = t.y;
       }
@@ -578,7 +659,7 @@ static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, float* d
 
 }  // namespace lpb
 
-// workspace: [W1 dgrad pack][W2 dgrad pack][G2][G1]   (G2 / G1: padded row layouts, row_layout.cuh)
+// workspace: [W1 dgrad pack][W2 dgrad pack][G2][G1][plane dots]   (G2 / G1: padded row layouts, row_layout.cuh)
 extern "C" int lpb_head_bwd_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes) {
   using namespace lpb;
   LPB_REQUIRE(bytes, "head_bwd_bf16_workspace_bytes: null pointer");
@@ -586,15 +667,18 @@ extern "C" int lpb_head_bwd_bf16_workspace_bytes(int B, int C, int H, int W, int
   const size_t w1 = (size_t)(C / 4 / 128) * 4 * GB_KC * 128 * 16, w2 = (size_t)4 * GB_KC * 32 * 16;
   const size_t g2 = (size_t)B * GB_KC * make_row_layout(4 * H, 4 * W).rows * 16;
   const size_t g1 = (size_t)B * GB_KC * make_row_layout(2 * H, 2 * W).rows * 16;
-  *bytes = w1 + w2 + g2 + g1;
+  *bytes = w1 + w2 + g2 + g1 + (((size_t)B * c2 * 4 + 255) & ~(size_t)255);
   return LPB_OK;
 }
 
-extern "C" int lpb_head_bwd_bf16(const float* g_logits, const void* saved_xs, const void* fwd_workspace, int B, int C, int H,
+extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const float* win, const int32_t* win_meta,
+                                 const float* g_overflow, const void* saved_xs, const void* fwd_workspace, int B, int C, int H,
                                  int W, const float* w1, int c1, const float* w2, int c2, void* dfeat, float* dw1, float* db1,
                                  float* dw2, float* db2, void* workspace, void* stream) {
   using namespace lpb;
-  LPB_REQUIRE(g_logits && saved_xs && fwd_workspace && w1 && w2 && dw1 && db1 && dw2 && db2 && workspace, "head_bwd_bf16: null pointer");
+  LPB_REQUIRE(saved_xs && fwd_workspace && w1 && w2 && dw1 && db1 && dw2 && db2 && workspace, "head_bwd_bf16: null pointer");
+  LPB_REQUIRE(g_out || win, "head_bwd_bf16: neither a dense gradient nor decode windows given");
+  LPB_REQUIRE(!win || (win_meta && g_overflow), "head_bwd_bf16: windows need their meta and overflow buffers");
   LPB_REQUIRE(B >= 0 && C >= 512 && C % 512 == 0 && H >= 1 && W >= 1, "head_bwd_bf16: bad feature shape C=%d H=%d W=%d", C, H, W);
   LPB_REQUIRE(c1 >= 1 && c1 < GB_CLS && c2 >= 1 && c2 <= GB_CLS && (W % 4) == 0, "head_bwd_bf16: unsupported channels/width");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -627,7 +711,22 @@ extern "C" int lpb_head_bwd_bf16(const float* g_logits, const void* saved_xs, co
   pack_dgrad_weights_kernel<<<8, 256, 0, s>>>(w2, c1, c2, 1, 32, wp2, nullptr, 0);
   launch_zero_row_pads(G2, L2, (long long)B * GB_KC, stream);
   launch_zero_row_pads(G1, L1, (long long)B * GB_KC, stream);
-  g_relayout_kernel<<<(unsigned)(B * Hi2), 64, 0, s>>>(g_logits, B, c2, Hi2, Wi2, G2, L2);
+  {
+    G2Src src;
+    src.g_out = g_out;
+    src.probs = probs;
+    src.win = win;
+    src.meta = win ? win_meta : nullptr;
+    src.gov = g_overflow;
+    float* ddot = reinterpret_cast<float*>(ws + w1b + w2b + (size_t)B * GB_KC * L2.rows * 16 + (size_t)B * GB_KC * L1.rows * 16);
+    src.ddot = nullptr;
+    if (probs) {
+      LPB_REQUIRE(((4 * Hi2 * Wi2) % 4) == 0, "head_bwd_bf16: plane size");
+      plane_dot_kernel<<<(unsigned)(B * c2), 256, 0, s>>>(src, 4 * Hi2 * Wi2, ddot);
+      src.ddot = ddot;
+    }
+    g2_build_kernel<<<(unsigned)(B * Hi2), 64, 0, s>>>(src, B, c2, Hi2, Wi2, G2, L2);
+  }
   // layer 2: weight + bias gradient (bias from the all-ones channel c1 of mid), then data gradient -> G1 (+ db1)
   {
     const int rc = launch_wgrad(mid, G2, dw2, db2, B, Hi2, Wi2, 4, 4, c1, c2, c1, sms, s);

@@ -62,11 +62,34 @@ def run_subpixelmaxima(
     return ops.decode_softargmax(heatmaps, int(downsample_factor), float(temperature))
 
 
+def _conv_backward(features, params, n, g_logits, need_dfeat):
+    """Head shapes outside the tensor-core tiling and the fp32 head: transposed-conv dgrad/wgrad through the
+    framework's conv ops ("backward")."""
+    cdt = torch.bfloat16 if features.dtype == torch.bfloat16 else torch.float32  # same precision as the forward
+    with torch.enable_grad():
+        f = features.detach().to(cdt).requires_grad_(need_dfeat)
+        ps = [p.detach().float().requires_grad_(True) for p in params]
+        x = torch.nn.functional.pixel_shuffle(f, 2)
+        for wt, bs in zip(ps[:n], ps[n:]):
+            x = torch.nn.functional.conv_transpose2d(x, wt.to(cdt), bs.to(cdt), stride=2, padding=1, output_padding=1)
+        ins = ([f] if need_dfeat else []) + ps
+        grads = torch.autograd.grad(x, ins, g_logits.to(cdt))
+    gf = grads[0] if need_dfeat else None
+    gp = grads[1:] if need_dfeat else grads
+    return (gf, *gp)
+
+
 class _HeadFunction(torch.autograd.Function):
-    """Forward: fused CUDA head.  Backward: native tcgen05 kernels for the bf16 head (see ``HeatmapHead``)."""
+    """Fused head, optionally with the soft-argmax decode riding along (``decode = (ds, temperature)``).
+
+    Forward: tcgen05 head (+ decode kernel).  Backward: ONE native pass.  The gradient w.r.t. the heatmaps is
+    never materialised for the decode branch: the sparse decode windows, a dense heatmap-loss gradient if there
+    is one, and the softmax backward are all folded into the kernel that writes the deconv-gradient operand.
+    Outputs: heatmaps [, keypoints (B, 2K), confidences (B, K)].
+    """
 
     @staticmethod
-    def forward(ctx, features, final_softmax, *params):
+    def forward(ctx, features, final_softmax, decode, *params):
         n = len(params) // 2
         weights, biases = list(params[:n]), list(params[n:])
         saved = None
@@ -77,38 +100,47 @@ class _HeadFunction(torch.autograd.Function):
                 out, saved = res
         if out is None:
             out = ops.head_forward(features, weights, biases, final_softmax)
-        ctx.save_for_backward(features, out, *params)
-        ctx.final_softmax, ctx.n, ctx.saved = final_softmax, n, saved
-        return out
+        ctx.set_materialize_grads(False)
+        ctx.final_softmax, ctx.n, ctx.saved, ctx.decode = final_softmax, n, saved, decode
+        if decode is None:
+            ctx.save_for_backward(features, out, *params)
+            return out
+        ds, temperature = decode
+        xy, conf, stats = ops._decode_fwd(out, int(ds), float(temperature))
+        ctx.save_for_backward(features, out, *params, stats)
+        ctx.mark_non_differentiable(conf)
+        return out, xy.reshape(-1, out.shape[1] * 2), conf
 
     @staticmethod
-    def backward(ctx, g):
-        features, out, *params = ctx.saved_tensors
+    def backward(ctx, g, g_xy=None, g_conf=None):
+        tensors = list(ctx.saved_tensors)
+        stats = tensors.pop() if ctx.decode is not None else None
+        features, out, *params = tensors
         n = ctx.n
         weights, biases = params[:n], params[n:]
-        g = g.contiguous().float()
-        if ctx.final_softmax:  # d softmax: p * (g - sum(g * p)) per plane
-            g = ops.plane_softmax_backward(out, g)
+        need_dfeat = ctx.needs_input_grad[0]
+        if g is None and g_xy is None:
+            return (None,) * (3 + 2 * n)
+        if g is not None:
+            g = g.contiguous().float()
         if ctx.saved is not None:
+            windows = None
+            if g_xy is not None:
+                windows = ops.decode_backward_windows(out, stats, g_xy.contiguous().float(), int(ctx.decode[0]), float(ctx.decode[1]))
             dfeat, dw1, db1, dw2, db2 = ops.head_backward_bf16(
-                g, ctx.saved, tuple(features.shape), weights[0], weights[1], need_dfeat=ctx.needs_input_grad[0]
+                g, ctx.saved, tuple(features.shape), weights[0], weights[1], need_dfeat=need_dfeat,
+                probs=out if ctx.final_softmax else None, windows=windows,
             )
             ctx.saved = None
-            return (dfeat, None, dw1.to(weights[0].dtype), dw2.to(weights[1].dtype), db1.to(biases[0].dtype), db2.to(biases[1].dtype))
-        # shapes outside the tensor-core tiling and the fp32 head: transposed-conv dgrad/wgrad through the
-        # framework's conv ops ("backward")
-        cdt = torch.bfloat16 if features.dtype == torch.bfloat16 else torch.float32  # same precision as the forward
-        with torch.enable_grad():
-            f = features.detach().to(cdt).requires_grad_(ctx.needs_input_grad[0])
-            ps = [p.detach().float().requires_grad_(True) for p in params]
-            x = torch.nn.functional.pixel_shuffle(f, 2)
-            for wt, bs in zip(ps[:n], ps[n:]):
-                x = torch.nn.functional.conv_transpose2d(x, wt.to(cdt), bs.to(cdt), stride=2, padding=1, output_padding=1)
-            ins = ([f] if ctx.needs_input_grad[0] else []) + ps
-            grads = torch.autograd.grad(x, ins, g.to(cdt))
-        gf = grads[0] if ctx.needs_input_grad[0] else None
-        gp = grads[1:] if ctx.needs_input_grad[0] else grads
-        return (gf, None, *gp)
+            return (dfeat, None, None, dw1.to(weights[0].dtype), dw2.to(weights[1].dtype), db1.to(biases[0].dtype), db2.to(biases[1].dtype))
+        # generic path: dense decode gradient, softmax backward kernel, library conv backward
+        if g_xy is not None:
+            gd = ops._decode_bwd(out, stats, g_xy.contiguous().float(), int(ctx.decode[0]), float(ctx.decode[1]))
+            g = gd if g is None else g + gd
+        if ctx.final_softmax:  # d softmax: p * (g - sum(g * p)) per plane
+            g = ops.plane_softmax_backward(out, g)
+        gf, *gp = _conv_backward(features, params, n, g, need_dfeat)
+        return (gf, None, None, *gp)
 
 
 class HeatmapHead(nn.Module):
@@ -151,7 +183,18 @@ class HeatmapHead(nn.Module):
     def forward(self, features: torch.Tensor) -> torch.Tensor:
         deconvs = self._deconvs()
         params = [d.weight for d in deconvs] + [d.bias for d in deconvs]
-        return _HeadFunction.apply(features, bool(self.final_softmax), *params)
+        return _HeadFunction.apply(features, bool(self.final_softmax), None, *params)
+
+    def forward_with_keypoints(self, features: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """``forward`` + ``run_subpixelmaxima`` as one autograd node: (heatmaps, keypoints, confidences).
+
+        Same values as calling the two methods in sequence (reference flow, heatmap_tracker.py:163-179); the
+        difference is the backward, which never materialises the dense gradient of the soft-argmax.
+        """
+        deconvs = self._deconvs()
+        params = [d.weight for d in deconvs] + [d.bias for d in deconvs]
+        decode = (int(self.downsample_factor), float(self.temperature))
+        return _HeadFunction.apply(features, bool(self.final_softmax), decode, *params)
 
     def run_subpixelmaxima(self, heatmaps: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         return run_subpixelmaxima(heatmaps, self.downsample_factor, self.temperature)

@@ -87,9 +87,20 @@ class HeatmapTracker(nn.Module):
             return heatmaps.reshape(shape[0], -1, heatmaps.shape[-2], heatmaps.shape[-1])
         return self.head(self.get_representations(images))
 
+    def forward_with_keypoints(self, images: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """``forward`` followed by ``head.run_subpixelmaxima`` as one fused autograd node (training paths)."""
+        shape = images.shape
+        if len(shape) > 4:
+            images = images.reshape(-1, *shape[-3:])
+        heatmaps, keypoints, confidence = self.head.forward_with_keypoints(self.get_representations(images))
+        if len(shape) > 4:  # fold the views back (reference :120-128); decode is per plane, so it commutes
+            heatmaps = heatmaps.reshape(shape[0], -1, heatmaps.shape[-2], heatmaps.shape[-1])
+            keypoints = keypoints.reshape(shape[0], -1)
+            confidence = confidence.reshape(shape[0], -1)
+        return heatmaps, keypoints, confidence
+
     def get_loss_inputs_labeled(self, batch_dict: dict) -> HeatmapTrackerLabeledOutputsDict:
-        predicted_heatmaps = self.forward(batch_dict["images"])
-        predicted_keypoints, confidence = self.head.run_subpixelmaxima(predicted_heatmaps)
+        predicted_heatmaps, predicted_keypoints, confidence = self.forward_with_keypoints(batch_dict["images"])
         predicted_keypoints = model_to_frame_batch(batch_dict, predicted_keypoints)
         target_keypoints = model_to_frame_batch(batch_dict, batch_dict["keypoints"])
         return {
@@ -151,8 +162,7 @@ class SemiSupervisedHeatmapTracker(HeatmapTracker):
 
     def get_loss_inputs_unlabeled(self, batch_dict: dict) -> HeatmapTrackerUnlabeledOutputsDict:
         frames = batch_dict["frames"]
-        pred_heatmaps = self.forward(frames)
-        pred_keypoints_augmented, confidence = self.head.run_subpixelmaxima(pred_heatmaps)
+        pred_heatmaps, pred_keypoints_augmented, confidence = self.forward_with_keypoints(frames)
         is_multiview = bool(batch_dict.get("is_multiview", False))
         transforms = batch_dict["transforms"]
         num_views = batch_dict["bbox"].shape[1] // 4 if is_multiview else 1

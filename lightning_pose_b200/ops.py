@@ -19,6 +19,7 @@ __all__ = [
     "evaluate_heatmaps_at_location",
     "head_forward",
     "head_backward_bf16",
+    "decode_backward_windows",
     "remap_keypoints",
     "heatmap_loss",
     "heatmap_mse_from_keypoints",
@@ -196,22 +197,45 @@ def _head_forward_bf16(f, weights, biases, final_softmax, train=False):
     return out
 
 
-def head_backward_bf16(g_logits, saved, feat_shape, w1, w2, need_dfeat=True):
-    """Gradients of the bf16 head (tcgen05): returns (dfeat bf16 | None, dw1, db1, dw2, db2)."""
+def decode_backward_windows(heatmaps, stats, grad_xy, ds, temperature):
+    """Sparse soft-argmax gradient for the fused head backward: (win, meta, overflow) of ``lpb_decode_bwd_windows``."""
+    b, k, h, w = heatmaps.shape
+    win = torch.empty((b * k, 32, 32), device=heatmaps.device, dtype=torch.float32)
+    meta = torch.empty((b * k, 4), device=heatmaps.device, dtype=torch.int32)
+    # only planes whose support overflows a window are ever written/read here (none for peaked heatmaps);
+    # the caching allocator hands the block back without touching it
+    overflow = torch.empty_like(heatmaps)
+    with torch.cuda.device(heatmaps.device):
+        check(lib.lpb_decode_bwd_windows(_ptr(heatmaps), _ptr(stats), _ptr(grad_xy), b * k, h, w, ds, temperature, _ptr(win), _ptr(meta), _ptr(overflow), _stream()))
+    return win, meta, overflow
+
+
+def head_backward_bf16(g_out, saved, feat_shape, w1, w2, need_dfeat=True, probs=None, windows=None):
+    """Gradients of the bf16 head (tcgen05): returns (dfeat bf16 | None, dw1, db1, dw2, db2).
+
+    ``g_out``: dense gradient w.r.t. the head output or None; ``probs``: the head output when it ends in the
+    spatial softmax (its backward is fused in), None for a logits head; ``windows``: result of
+    ``decode_backward_windows`` or None.
+    """
     xs, fws = saved
     b, c, h, w = feat_shape
-    g = _cuda_f32(g_logits, "g_logits")
+    g = _cuda_f32(g_out, "g_out") if g_out is not None else None
+    if g is None and windows is None:
+        raise ValueError("head_backward_bf16 needs a dense gradient and/or decode windows")
     w1, w2 = _cuda_f32(w1, "w1"), _cuda_f32(w2, "w2")
     c1, c2 = w1.shape[1], w2.shape[1]
+    dev = w1.device
     nbytes = C.c_size_t(0)
     check(lib.lpb_head_bwd_bf16_workspace_bytes(b, c, h, w, c1, c2, C.byref(nbytes)))
-    ws = torch.empty((nbytes.value,), device=g.device, dtype=torch.uint8)
-    dfeat = torch.empty((b, c, h, w), device=g.device, dtype=torch.bfloat16) if need_dfeat else None
+    ws = torch.empty((nbytes.value,), device=dev, dtype=torch.uint8)
+    dfeat = torch.empty((b, c, h, w), device=dev, dtype=torch.bfloat16) if need_dfeat else None
     dw1, dw2 = torch.empty_like(w1), torch.empty_like(w2)
-    db1 = torch.empty((c1,), device=g.device, dtype=torch.float32)
-    db2 = torch.empty((c2,), device=g.device, dtype=torch.float32)
-    with torch.cuda.device(g.device):
-        check(lib.lpb_head_bwd_bf16(_ptr(g), _ptr(xs), _ptr(fws), b, c, h, w, _ptr(w1), c1, _ptr(w2), c2, _ptr(dfeat), _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _ptr(ws), _stream()))
+    db1 = torch.empty((c1,), device=dev, dtype=torch.float32)
+    db2 = torch.empty((c2,), device=dev, dtype=torch.float32)
+    win, meta, ov = windows if windows is not None else (None, None, None)
+    with torch.cuda.device(dev):
+        check(lib.lpb_head_bwd_bf16(_ptr(g), _ptr(probs), _ptr(win), _ptr(meta), _ptr(ov), _ptr(xs), _ptr(fws), b, c, h, w, _ptr(w1), c1, _ptr(w2), c2,
+                                    _ptr(dfeat), _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _ptr(ws), _stream()))
     return dfeat, dw1, db1, dw2, db2
 
 

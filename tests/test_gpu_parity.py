@@ -477,6 +477,111 @@ def test_head_bf16_tcgen05_backward_vs_oracle_autograd(lpb, dev, softmax):
     (out * gout.to(dev)).sum().backward()
     close(d1.weight.grad, p_ref[0].grad, atol=1e-2 * float(p_ref[0].grad.abs().max()), rtol=0)
 
+def _peaked_heatmaps(b, k, h, w, seed, sigma=1.6):
+    g = torch.Generator().manual_seed(seed)
+    cy = torch.rand(b, k, 1, 1, generator=g) * (h - 1)
+    cx = torch.rand(b, k, 1, 1, generator=g) * (w - 1)
+    yy = torch.arange(h).view(1, 1, h, 1).float()
+    xx = torch.arange(w).view(1, 1, 1, w).float()
+    logits = -((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * sigma**2) * 1.0 + 0.05 * torch.randn(b, k, h, w, generator=g)
+    return torch.softmax(logits.reshape(b, k, -1), -1).reshape(b, k, h, w)
+
+
+@pytest.mark.parametrize("ds", [1, 2, 3])
+def test_decode_backward_windows_match_dense(lpb, dev, ds):
+    """lpb_decode_bwd_windows: the 32x32 windows (+ overflow planes) re-assembled equal lpb_decode_bwd, and
+    meta's dot equals sum(g * heatmap); includes peaks at the border, zero-gradient planes and diffuse planes
+    that must take the dense fallback."""
+    from lightning_pose_b200 import ops
+
+    b, k, h, w = 3, 6, 48, 40
+    hm = _peaked_heatmaps(b, k, h, w, seed=5 + ds)
+    hm[0, 0] = torch.softmax(torch.randn(h * w, generator=torch.Generator().manual_seed(1)) * 0.01, 0).reshape(h, w)  # diffuse
+    hm[1, 1] = 0.0
+    hm[1, 1, 0, 0] = 1.0  # corner peak
+    hm = hm.to(dev).contiguous()
+    xy, conf, stats = ops._decode_fwd(hm, ds, 1000.0)
+    gxy = torch.randn(b, k, 2, generator=torch.Generator().manual_seed(2)).to(dev)
+    gxy[2, 3] = 0.0  # zero-gradient plane
+    dense = ops._decode_bwd(hm, stats, gxy, ds, 1000.0)
+    win, meta, ov = ops.decode_backward_windows(hm, stats, gxy, ds, 1000.0)
+    meta_c, win_c = meta.cpu(), win.cpu()
+    rebuilt = torch.zeros(b * k, h, w)
+    flags = meta_c[:, 2].tolist()
+    assert flags[0] == 2 and flags[2 * k + 3] == 0 and flags.count(1) >= b * k - 3
+    for pl in range(b * k):
+        r0, c0, flag, dbits = meta_c[pl].tolist()
+        if flag == 2:
+            rebuilt[pl] = ov.reshape(b * k, h, w)[pl].cpu()
+        elif flag == 1:
+            ys = [(r0 + i, i) for i in range(32) if 0 <= r0 + i < h]
+            xs = [(c0 + j, j) for j in range(32) if 0 <= c0 + j < w]
+            sub = win_c[pl][[i for _, i in ys]][:, [j for _, j in xs]]
+            rebuilt[pl][ys[0][0] : ys[-1][0] + 1, xs[0][0] : xs[-1][0] + 1] = sub
+            # nothing may fall outside the plane
+            mask = torch.ones(32, 32, dtype=torch.bool)
+            mask[[i for _, i in ys][0] : [i for _, i in ys][-1] + 1, [j for _, j in xs][0] : [j for _, j in xs][-1] + 1] = False
+            assert float(win_c[pl][mask].abs().max() if mask.any() else 0.0) == 0.0
+            dot = torch.tensor([dbits], dtype=torch.int32).view(torch.float32).item()
+            ref_dot = float((dense.reshape(b * k, h, w)[pl].cpu() * hm.reshape(b * k, h, w)[pl].cpu()).sum())
+            assert abs(dot - ref_dot) <= 1e-4 * max(1.0, abs(ref_dot)) + 1e-6
+    d = dense.reshape(b * k, h, w).cpu()
+    close(rebuilt, d, atol=2e-5 * float(d.abs().max()), rtol=1e-4)
+
+
+@pytest.mark.parametrize("use_dense", [True, False])
+def test_head_with_keypoints_fused_backward_vs_oracle(lpb, dev, use_dense):
+    """forward_with_keypoints: heatmaps + soft-argmax keypoints from one node; its single fused backward (decode
+    windows [+ dense heatmap-loss gradient] + softmax backward folded into the deconv-gradient operand) against
+    oracle autograd.  The soft-argmax gradient (T = 1000: exponentially sensitive to the heatmap values) is taken
+    by oracle autograd AT the kernel's heatmaps; everything else is the oracle's own fp32 chain."""
+    import torch.nn.functional as F
+    from lightning_pose_b200.models.heads.heatmap import HeatmapHead
+
+    b, c, fh, fw, k = 6, 2048, 12, 12, 17
+    torch.manual_seed(31)
+    head = HeatmapHead("resnet50", c, k)
+    for layer in list(head.upsampling_layers)[1:]:
+        torch.nn.init.xavier_uniform_(layer.weight, gain=4.0)
+        torch.nn.init.uniform_(layer.bias, -0.3, 0.3)
+    feats = (torch.randn(b, c, fh, fw) * 0.5).bfloat16()
+    g_hm = torch.randn(b, k, 8 * fh, 8 * fw) if use_dense else None
+    g_kp = torch.randn(b, 2 * k)
+    head = head.to(dev)
+    f_dev = feats.to(dev).requires_grad_(True)
+    hm, kp, cf = head.forward_with_keypoints(f_dev)
+    loss = (kp * g_kp.to(dev)).sum()
+    if use_dense:
+        loss = loss + (hm * g_hm.to(dev)).sum()
+    loss.backward()
+    # oracle
+    hm_k = hm.detach().cpu().requires_grad_(True)
+    kp_o, cf_o = O.decode_softargmax(hm_k, 2, 1000.0)
+    close(kp, kp_o.detach(), atol=2e-3, rtol=RTOL)
+    close(cf, cf_o.detach(), atol=1e-4, rtol=1e-3)
+    (kp_o * g_kp).sum().backward()
+    g_total = hm_k.grad + (g_hm if use_dense else 0.0)
+    r = lambda t: (t.bfloat16().float() - t).detach() + t
+    d1, d2 = [m.cpu() for m in list(head.upsampling_layers)[1:]]
+    f_ref = feats.float().requires_grad_(True)
+    p_ref = [t.detach().clone().requires_grad_(True) for t in (d1.weight, d1.bias, d2.weight, d2.bias)]
+    mid = F.conv_transpose2d(F.pixel_shuffle(f_ref, 2), r(p_ref[0]), p_ref[1], stride=2, padding=1, output_padding=1)
+    mid.retain_grad()
+    y = O.spatial_softmax2d(F.conv_transpose2d(r(mid), r(p_ref[2]), p_ref[3], stride=2, padding=1, output_padding=1), 1.0)
+    y.backward(g_total)
+    # Bias gradients of a softmax head are sums that cancel (db2 is exactly 0, db1 only sees the image border):
+    # what is left of them in bf16 is the random-walk rounding noise of the gradient operand,
+    # 2^-8 * ||d mid||_2 per channel -- that, not max|ref|, is the meaningful error scale for them.
+    noise1 = 2.0**-8 * mid.grad.pow(2).sum((0, 2, 3)).sqrt()
+    for name, got, ref in [("dfeat", f_dev.grad.float(), f_ref.grad), ("dw1", d1.weight.grad, p_ref[0].grad), ("db1", d1.bias.grad, p_ref[1].grad),
+                           ("dw2", d2.weight.grad, p_ref[2].grad), ("db2", d2.bias.grad, p_ref[3].grad)]:
+        err = (got.cpu() - ref).abs()
+        if name == "db1":
+            assert bool((err <= 2e-2 * ref.abs().max() + 4.0 * noise1).all()), (name, err, noise1)
+            continue
+        scale = float(ref.abs().max()) if name != "db2" else float(p_ref[2].grad.abs().max())
+        assert float(err.max()) <= 2e-2 * scale + 1e-9, (name, float(err.max()), scale)
+
 
 def test_decode_multimodal_random_fields(lpb, dev):
     """Random spiky planes (several comparable peaks scattered over the plane) exercise the per-strip
