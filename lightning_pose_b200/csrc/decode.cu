@@ -480,6 +480,7 @@ struct DecodeBwdParams {
   const float* tabW;
   float* gheat;
   const int* only_meta;  // optional [n_planes][4]: process only planes whose meta flag (word 2) is 2
+  long long n_planes;
   int h, w, pitch, padl, bulk;
   float T;
   float phase[F][W];
@@ -495,142 +496,151 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_co
   float* gtile = tile + tile_floats;  // same padded geometry, accumulates U_H^T G U_W
   uint64_t* bar = reinterpret_cast<uint64_t*>(gtile + tile_floats);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t plane = blockIdx.x;
-  if (P.only_meta && P.only_meta[4 * plane + 2] != 2) return;  // window path took this plane (uniform per CTA)
-  const float* __restrict__ src = P.heat + plane * (size_t)h * w;
-
   if (P.bulk) {
     if (tid == 0) {
       mbar_init(bar, 1);
       fence_mbar_init();
     }
     __syncthreads();
-    if (warp == 0) {
-      if (lane == 0) mbar_expect_tx(bar, (uint32_t)(h * w * 4));
-      __syncwarp();
-      for (int a = lane; a < h; a += 32)
-        bulk_g2s(tile + (a + R) * pitch + padl, src + (size_t)a * w, (uint32_t)(w * 4), bar);
-    }
   }
-  for (int i = tid; i < tile_floats; i += DEC_THREADS) gtile[i] = 0.f;
-  for (int r = warp; r < h + 2 * R; r += DEC_WARPS) {
-    float* row = tile + r * pitch;
-    if (r < R || r >= h + R) {
-      for (int b = lane; b < pitch; b += 32) row[b] = 0.f;
-    } else {
-      for (int b = lane; b < padl; b += 32) row[b] = 0.f;
-      for (int b = padl + w + lane; b < pitch; b += 32) row[b] = 0.f;
-      if (!P.bulk) {
-        const float* g = src + (size_t)(r - R) * w;
-        for (int b = lane; b < w; b += 32) row[padl + b] = __ldg(g + b);
+  uint32_t phase = 0;
+  // dense launch: one plane per CTA.  Fallback launch (only_meta): a few resident CTAs scan the window
+  // kernel's flags and run only the planes it could not take.
+  for (size_t plane = blockIdx.x; plane < (size_t)P.n_planes; plane += gridDim.x) {
+    if (P.only_meta && P.only_meta[4 * plane + 2] != 2) continue;  // uniform per CTA
+    const float* __restrict__ src = P.heat + plane * (size_t)h * w;
+
+    if (P.bulk) {
+      if (warp == 0) {
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)(h * w * 4));
+        __syncwarp();
+        for (int a = lane; a < h; a += 32)
+          bulk_g2s(tile + (a + R) * pitch + padl, src + (size_t)a * w, (uint32_t)(w * 4), bar);
       }
     }
-  }
-  if (P.bulk) mbar_wait(bar, 0);
-  __syncthreads();
-
-  const float* st = P.stats + 8 * plane;
-  const float M = st[0], S = st[1], xhat = st[2], yhat = st[3];
-  const int A0 = (int)st[4], A1 = (int)st[5], B0 = (int)st[6], B1 = (int)st[7];
-  const float gx = P.gxy[2 * plane], gy = P.gxy[2 * plane + 1];
-  const float c = P.T * 1.4426950408889634f;
-  const float kscale = P.T / S;
-
-  if (gx != 0.f || gy != 0.f) {
-    const int J0 = B0 * F, J1 = (B1 + 1) * F;
-    const int nstrips = (J1 - J0 + 31) >> 5;
-    const int nrows = A1 - A0 + 1;
-    int G = 1, seg = nrows;
-    {
-      int bestcost = 0x7fffffff;
-      for (int g = 1; g <= 8; ++g) {
-        const int sg = (nrows + g - 1) / g;
-        const int cost = ((nstrips * g + DEC_WARPS - 1) / DEC_WARPS) * (sg + 2 * R);
-        if (cost < bestcost) {
-          bestcost = cost;
-          G = g;
-          seg = sg;
+    for (int i = tid; i < tile_floats; i += DEC_THREADS) gtile[i] = 0.f;
+    for (int r = warp; r < h + 2 * R; r += DEC_WARPS) {
+      float* row = tile + r * pitch;
+      if (r < R || r >= h + R) {
+        for (int b = lane; b < pitch; b += 32) row[b] = 0.f;
+      } else {
+        for (int b = lane; b < padl; b += 32) row[b] = 0.f;
+        for (int b = padl + w + lane; b < pitch; b += 32) row[b] = 0.f;
+        if (!P.bulk) {
+          const float* g = src + (size_t)(r - R) * w;
+          for (int b = lane; b < w; b += 32) row[padl + b] = __ldg(g + b);
         }
       }
     }
-    const int nitems = nstrips * G;
-    for (int item = warp; item < nitems; item += DEC_WARPS) {
-      const int sidx = item % nstrips, g = item / nstrips;
-      const int r0 = A0 + g * seg, r1 = min(r0 + seg, A1 + 1);
-      if (r0 >= r1) continue;
-      const int jf = J0 + sidx * 32 + lane;
-      const bool ok = jf < J1;
-      const int jc = ok ? jf : (J1 - 1);
-      float wc[W];
-#pragma unroll
-      for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
-      const int cb = padl + (jc / F - R);
-      const float* colbase = tile + cb;
-      float tmp[W];   // horizontal pass of h, rows a-R .. a+R
-      float gacc[W];  // vertical-transpose accumulators: sum_i wr[i][t] * G[i][j] for coarse row a-R+t
-#pragma unroll
-      for (int t = 0; t < W; ++t) {
-        tmp[t] = dot_w<W>(colbase + (r0 + t) * pitch, wc);
-        gacc[t] = 0.f;
-      }
-      const float dx = (float)jf - xhat;
-      for (int a = r0; a < r1; ++a) {
-        const bool interior = (a >= R && a <= h - 1 - R);
-        const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
-#pragma unroll
-        for (int p = 0; p < F; ++p) {
-          float wr[W];
-#pragma unroll
-          for (int t = 0; t < W; ++t) wr[t] = interior ? P.phase[p][t] : __ldg(tr + p * W + t);
-          float v = 0.f;
-#pragma unroll
-          for (int t = 0; t < W; ++t) v = fmaf(wr[t], tmp[t], v);
-          const float pr = fast_exp2((v - M) * c);
-          const float gval = ok ? kscale * pr * fmaf(dx, gx, ((float)(a * F + p) - yhat) * gy) : 0.f;
-#pragma unroll
-          for (int t = 0; t < W; ++t) gacc[t] = fmaf(wr[t], gval, gacc[t]);
+    if (P.bulk) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+    }
+    __syncthreads();
+
+    const float* st = P.stats + 8 * plane;
+    const float M = st[0], S = st[1], xhat = st[2], yhat = st[3];
+    const int A0 = (int)st[4], A1 = (int)st[5], B0 = (int)st[6], B1 = (int)st[7];
+    const float gx = P.gxy[2 * plane], gy = P.gxy[2 * plane + 1];
+    const float c = P.T * 1.4426950408889634f;
+    const float kscale = P.T / S;
+
+    if (gx != 0.f || gy != 0.f) {
+      const int J0 = B0 * F, J1 = (B1 + 1) * F;
+      const int nstrips = (J1 - J0 + 31) >> 5;
+      const int nrows = A1 - A0 + 1;
+      int G = 1, seg = nrows;
+      {
+        int bestcost = 0x7fffffff;
+        for (int g = 1; g <= 8; ++g) {
+          const int sg = (nrows + g - 1) / g;
+          const int cost = ((nstrips * g + DEC_WARPS - 1) / DEC_WARPS) * (sg + 2 * R);
+          if (cost < bestcost) {
+            bestcost = cost;
+            G = g;
+            seg = sg;
+          }
         }
-        // coarse row a-R is complete for this lane's column: scatter through the horizontal taps
-        {
-          float* grow = gtile + a * pitch + cb;  // padded row (a-R)+R; lanes of one coarse column pre-reduce
-#pragma unroll
+      }
+      const int nitems = nstrips * G;
+      for (int item = warp; item < nitems; item += DEC_WARPS) {
+        const int sidx = item % nstrips, g = item / nstrips;
+        const int r0 = A0 + g * seg, r1 = min(r0 + seg, A1 + 1);
+        if (r0 >= r1) continue;
+        const int jf = J0 + sidx * 32 + lane;
+        const bool ok = jf < J1;
+        const int jc = ok ? jf : (J1 - 1);
+        float wc[W];
+  #pragma unroll
+        for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
+        const int cb = padl + (jc / F - R);
+        const float* colbase = tile + cb;
+        float tmp[W];   // horizontal pass of h, rows a-R .. a+R
+        float gacc[W];  // vertical-transpose accumulators: sum_i wr[i][t] * G[i][j] for coarse row a-R+t
+  #pragma unroll
+        for (int t = 0; t < W; ++t) {
+          tmp[t] = dot_w<W>(colbase + (r0 + t) * pitch, wc);
+          gacc[t] = 0.f;
+        }
+        const float dx = (float)jf - xhat;
+        for (int a = r0; a < r1; ++a) {
+          const bool interior = (a >= R && a <= h - 1 - R);
+          const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
+  #pragma unroll
+          for (int p = 0; p < F; ++p) {
+            float wr[W];
+  #pragma unroll
+            for (int t = 0; t < W; ++t) wr[t] = interior ? P.phase[p][t] : __ldg(tr + p * W + t);
+            float v = 0.f;
+  #pragma unroll
+            for (int t = 0; t < W; ++t) v = fmaf(wr[t], tmp[t], v);
+            const float pr = fast_exp2((v - M) * c);
+            const float gval = ok ? kscale * pr * fmaf(dx, gx, ((float)(a * F + p) - yhat) * gy) : 0.f;
+  #pragma unroll
+            for (int t = 0; t < W; ++t) gacc[t] = fmaf(wr[t], gval, gacc[t]);
+          }
+          // coarse row a-R is complete for this lane's column: scatter through the horizontal taps
+          {
+            float* grow = gtile + a * pitch + cb;  // padded row (a-R)+R; lanes of one coarse column pre-reduce
+  #pragma unroll
+            for (int u = 0; u < W; ++u) {
+              float val = gacc[0] * wc[u];
+  #pragma unroll
+              for (int o = 1; o < F; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+              if ((lane & (F - 1)) == 0 && val != 0.f) atomicAdd(grow + u, val);
+            }
+          }
+  #pragma unroll
+          for (int t = 0; t < W - 1; ++t) {
+            gacc[t] = gacc[t + 1];
+            tmp[t] = tmp[t + 1];
+          }
+          gacc[W - 1] = 0.f;
+          tmp[W - 1] = (a + 1 < r1) ? dot_w<W>(colbase + (a + 1 + 2 * R) * pitch, wc) : 0.f;
+        }
+        // flush the remaining W-1 partial rows (coarse rows r1-R .. r1+R-1)
+  #pragma unroll
+        for (int t = 0; t < W - 1; ++t) {
+          float* grow = gtile + (r1 + t) * pitch + cb;
+  #pragma unroll
           for (int u = 0; u < W; ++u) {
-            float val = gacc[0] * wc[u];
-#pragma unroll
+            float val = gacc[t] * wc[u];
+  #pragma unroll
             for (int o = 1; o < F; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
             if ((lane & (F - 1)) == 0 && val != 0.f) atomicAdd(grow + u, val);
           }
         }
-#pragma unroll
-        for (int t = 0; t < W - 1; ++t) {
-          gacc[t] = gacc[t + 1];
-          tmp[t] = tmp[t + 1];
-        }
-        gacc[W - 1] = 0.f;
-        tmp[W - 1] = (a + 1 < r1) ? dot_w<W>(colbase + (a + 1 + 2 * R) * pitch, wc) : 0.f;
-      }
-      // flush the remaining W-1 partial rows (coarse rows r1-R .. r1+R-1)
-#pragma unroll
-      for (int t = 0; t < W - 1; ++t) {
-        float* grow = gtile + (r1 + t) * pitch + cb;
-#pragma unroll
-        for (int u = 0; u < W; ++u) {
-          float val = gacc[t] * wc[u];
-#pragma unroll
-          for (int o = 1; o < F; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-          if ((lane & (F - 1)) == 0 && val != 0.f) atomicAdd(grow + u, val);
-        }
       }
     }
-  }
-  __syncthreads();
-  float* __restrict__ dst = P.gheat + plane * (size_t)h * w;
-  for (int a = warp; a < h; a += DEC_WARPS) {
-    const float* row = gtile + (a + R) * pitch + padl;
-    for (int b = lane; b < w; b += 32) dst[(size_t)a * w + b] = row[b];
+    __syncthreads();
+    float* __restrict__ dst = P.gheat + plane * (size_t)h * w;
+    for (int a = warp; a < h; a += DEC_WARPS) {
+      const float* row = gtile + (a + R) * pitch + padl;
+      for (int b = lane; b < w; b += 32) dst[(size_t)a * w + b] = row[b];
+    }
+    __syncthreads();  // tile / gtile are reused by the next plane
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // Sparse form of the decode backward.  With T = 1000 the softmax weights vanish a few fine pixels away from
@@ -840,6 +850,7 @@ static int launch_decode_bwd(const float* heat, const float* stats, const float*
   P.tabW = tw->win;
   P.gheat = gheat;
   P.only_meta = meta;
+  P.n_planes = n_planes;
   P.h = h;
   P.w = w;
   P.padl = dec_padl(G::R);
@@ -860,7 +871,13 @@ static int launch_decode_bwd(const float* heat, const float* stats, const float*
     return LPB_ERR_UNSUPPORTED;
   }
   LPB_CUDA(cudaFuncSetAttribute(decode_bwd_kernel<DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  decode_bwd_kernel<DS><<<(unsigned)n_planes, DEC_THREADS, smem, stream>>>(P);
+  unsigned grid = (unsigned)n_planes;
+  if (meta) {  // flag scan: one wave of resident CTAs
+    int sms = 0;
+    LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (grid > (unsigned)(2 * sms)) grid = (unsigned)(2 * sms);
+  }
+  decode_bwd_kernel<DS><<<grid, DEC_THREADS, smem, stream>>>(P);
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
 }

@@ -69,10 +69,15 @@ __global__ void __launch_bounds__(256) plane_dot_kernel(G2Src S, int hw, float* 
   }
 }
 
-// one CTA per (frame, m); thread n handles the 2x2 output block of row (m, n) for all channels
-__global__ void __launch_bounds__(64) g2_build_kernel(G2Src S, int B, int C, int Hi, int Wi, __nv_bfloat16* __restrict__ G,
-                                                      RowLayout L) {
-  const int b = blockIdx.x / Hi, m = blockIdx.x - b * Hi;
+// Thread t of a frame handles input-grid pixel (m, n) = divmod(t, Wi): the 2x2 output block x all channels.
+// Loads are issued as independent batches (probs, dense gradient) before any dependent work; the window
+// look-ups are rare (a 32x32 patch of a 96x96 plane) and come last.
+constexpr int G2B_THREADS = 128;
+
+template <bool HAS_G, bool HAS_P, bool HAS_WIN>
+__global__ void __launch_bounds__(G2B_THREADS) g2_build_kernel(G2Src S, int B, int C, int Hi, int Wi, int ctas_per_frame,
+                                                               __nv_bfloat16* __restrict__ G, RowLayout L) {
+  const int b = blockIdx.x / ctas_per_frame, t = (blockIdx.x - b * ctas_per_frame) * G2B_THREADS + threadIdx.x;
   const int Wo = 2 * Wi, Ho = 2 * Hi;
   __shared__ int4 smeta[GB_CLS];
   __shared__ float sdot[GB_CLS];
@@ -81,63 +86,80 @@ __global__ void __launch_bounds__(64) g2_build_kernel(G2Src S, int B, int C, int
     float d = 0.f;
     if (threadIdx.x < C) {
       const size_t plane = (size_t)b * C + threadIdx.x;
-      if (S.meta) mt = reinterpret_cast<const int4*>(S.meta)[plane];
-      if (S.probs) d = (mt.z == 1 ? __int_as_float(mt.w) : 0.f) + (S.ddot ? S.ddot[plane] : 0.f);
+      if (HAS_WIN) mt = reinterpret_cast<const int4*>(S.meta)[plane];
+      if (HAS_P) d = (mt.z == 1 ? __int_as_float(mt.w) : 0.f) + (S.ddot ? S.ddot[plane] : 0.f);
     }
     smeta[threadIdx.x] = mt;
     sdot[threadIdx.x] = d;
   }
   __syncthreads();
-  for (int n = threadIdx.x; n < Wi; n += blockDim.x) {
+  if (t >= Hi * Wi) return;
+  const int m = t / Wi, n = t - m * Wi;
 #pragma unroll
-    for (int py = 0; py < 2; ++py) {
-      const int y = 2 * m + py, x = 2 * n;
-      float v0[GB_CLS], v1[GB_CLS];
+  for (int py = 0; py < 2; ++py) {
+    const int y = 2 * m + py, x = 2 * n;
+    const size_t off0 = (((size_t)b * C) * Ho + y) * Wo + x;
+    const size_t pstride = (size_t)Ho * Wo;
+    float2 pv[GB_CLS], gv[GB_CLS];
+#pragma unroll
+    for (int o = 0; o < GB_CLS; ++o) {
+      pv[o] = make_float2(0.f, 0.f);
+      gv[o] = make_float2(0.f, 0.f);
+      if (o < C) {
+        if (HAS_P) pv[o] = __ldg(reinterpret_cast<const float2*>(S.probs + off0 + o * pstride));
+        if (HAS_G) gv[o] = __ldg(reinterpret_cast<const float2*>(S.g_out + off0 + o * pstride));
+      }
+    }
+    if (HAS_WIN) {
 #pragma unroll
       for (int o = 0; o < GB_CLS; ++o) {
-        float2 t = make_float2(0.f, 0.f);
         if (o < C) {
-          const size_t off = (((size_t)b * C + o) * Ho + y) * Wo + x;
-          if (S.g_out) t = __ldg(reinterpret_cast<const float2*>(S.g_out + off));
           const int4 mt = smeta[o];
           if (mt.z == 1) {
             const int ly = y - mt.x, lx = x - mt.y;
-            if ((unsigned)ly < 32u) {
+            if ((unsigned)ly < 32u && lx >= -1 && lx < 32) {
               const float* wr = S.win + ((size_t)b * C + o) * 1024 + ly * 32;
-              if ((unsigned)lx < 32u) t.x += __ldg(wr + lx);
-              if ((unsigned)(lx + 1) < 32u) t.y += __ldg(wr + lx + 1);
+              if (lx >= 0) gv[o].x += __ldg(wr + lx);
+              if (lx + 1 < 32) gv[o].y += __ldg(wr + lx + 1);
             }
           } else if (mt.z == 2) {
-            const float2 u = __ldg(reinterpret_cast<const float2*>(S.gov + off));
-            t.x += u.x, t.y += u.y;
-          }
-          if (S.probs) {
-            const float2 p = __ldg(reinterpret_cast<const float2*>(S.probs + off));
-            const float d = sdot[o];
-            t.x = p.x * (t.x - d);
-            t.y = p.y * (t.y - d);
+            const float2 u = __ldg(reinterpret_cast<const float2*>(S.gov + off0 + o * pstride));
+            gv[o].x += u.x, gv[o].y += u.y;
           }
         }
-        v0[o] = t.x;
-        v1[o] = t.y;
-      }
-      // k = (2*py + px) * 20 + o : 40 consecutive k values = K-chunks 5py .. 5py+4
-#pragma unroll
-      for (int ch = 0; ch < 5; ++ch) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int e2 = 0; e2 < 4; ++e2) {
-          const int k0 = ch * 8 + 2 * e2, k1 = k0 + 1;  // 0..39 within this py
-          const float f0 = k0 < GB_CLS ? v0[k0] : v1[k0 - GB_CLS];
-          const float f1 = k1 < GB_CLS ? v0[k1] : v1[k1 - GB_CLS];
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-          pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-        *reinterpret_cast<uint4*>(G + ((((size_t)b * GB_KC + 5 * py + ch) * L.rows) + L.lead + (size_t)m * L.Pp + n) * 8) =
-            make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
+    if (HAS_P) {
+#pragma unroll
+      for (int o = 0; o < GB_CLS; ++o) {
+        const float d = sdot[o];
+        gv[o].x = pv[o].x * (gv[o].x - d);
+        gv[o].y = pv[o].y * (gv[o].y - d);
+      }
+    }
+    // k = (2*py + px) * 20 + o : 40 consecutive k values = K-chunks 5py .. 5py+4
+#pragma unroll
+    for (int ch = 0; ch < 5; ++ch) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e2 = 0; e2 < 4; ++e2) {
+        const int k0 = ch * 8 + 2 * e2, k1 = k0 + 1;  // 0..39 within this py
+        const float f0 = k0 < GB_CLS ? gv[k0].x : gv[k0 - GB_CLS].y;
+        const float f1 = k1 < GB_CLS ? gv[k1].x : gv[k1 - GB_CLS].y;
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+        pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(G + ((((size_t)b * GB_KC + 5 * py + ch) * L.rows) + L.lead + (size_t)m * L.Pp + n) * 8) =
+          make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
   }
+}
+
+template <bool HAS_G, bool HAS_P>
+static void launch_g2_build(const G2Src& S, int B, int C, int Hi, int Wi, __nv_bfloat16* G, RowLayout L, cudaStream_t s) {
+  const int cpf = (Hi * Wi + G2B_THREADS - 1) / G2B_THREADS;
+  if (S.win) g2_build_kernel<HAS_G, HAS_P, true><<<(unsigned)(B * cpf), G2B_THREADS, 0, s>>>(S, B, C, Hi, Wi, cpf, G, L);
+  else g2_build_kernel<HAS_G, HAS_P, false><<<(unsigned)(B * cpf), G2B_THREADS, 0, s>>>(S, B, C, Hi, Wi, cpf, G, L);
 }
 
 // ---- weight packing for the data-gradient GEMMs ----------------------------------------------------------
@@ -725,7 +747,10 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
       plane_dot_kernel<<<(unsigned)(B * c2), 256, 0, s>>>(src, 4 * Hi2 * Wi2, ddot);
       src.ddot = ddot;
     }
-    g2_build_kernel<<<(unsigned)(B * Hi2), 64, 0, s>>>(src, B, c2, Hi2, Wi2, G2, L2);
+    if (g_out && probs) launch_g2_build<true, true>(src, B, c2, Hi2, Wi2, G2, L2, s);
+    else if (g_out) launch_g2_build<true, false>(src, B, c2, Hi2, Wi2, G2, L2, s);
+    else if (probs) launch_g2_build<false, true>(src, B, c2, Hi2, Wi2, G2, L2, s);
+    else launch_g2_build<false, false>(src, B, c2, Hi2, Wi2, G2, L2, s);
   }
   // layer 2: weight + bias gradient (bias from the all-ones channel c1 of mid), then data gradient -> G1 (+ db1)
   {
