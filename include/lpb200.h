@@ -62,10 +62,11 @@ int lpb_decode_bwd(const float* heatmaps, const float* stats, const float* grad_
 /* sparse form of lpb_decode_bwd for the fused head backward: per plane a 32x32 window of d loss / d heatmap
  * (win [n_planes, 32, 32]) and meta [n_planes, 4] = {window row0, col0, flag, float bits of sum(win * heatmap)};
  * flag 0: zero gradient, 1: window valid, 2: the support does not fit a window -- that plane's dense
- * gradient is written to g_overflow [n_planes, h, w] instead (other planes of g_overflow are not touched). */
+ * gradient is written to g_overflow [n_planes, h, w] instead (other planes of g_overflow are not touched).
+ * queue: n_planes + 1 ints of scratch (work list of the overflow planes). */
 int lpb_decode_bwd_windows(const float* heatmaps, const float* stats, const float* grad_xy, int64_t n_planes, int h,
                            int w, int ds, float temperature, float* win, int32_t* meta, float* g_overflow,
-                           void* stream);
+                           int32_t* queue, void* stream);
 
 /* one materialised upsampling stage: drop-in for `upsample`
  *   lightning_pose/models/heads/heatmap.py:86-100 ; in [n_planes,h,w] -> out [n_planes,2h,2w] */

@@ -479,16 +479,99 @@ struct DecodeBwdParams {
   const float* tabH;
   const float* tabW;
   float* gheat;
-  const int* only_meta;  // optional [n_planes][4]: process only planes whose meta flag (word 2) is 2
+  const int* queue;      // optional {count, plane ids...}: dense fallback units of the window path
   long long n_planes;
   int h, w, pitch, padl, bulk;
   float T;
   float phase[F][W];
 };
 
+// Transposed horizontal pass for one coarse row of one 32-fine-column strip.  Lane j holds gv = (U_H^T G)[row][j]
+// for its fine column; the F lanes of a coarse column share the W horizontal taps wc.  Coarse output column
+// c = group + tap; lane c gathers its W contributions by shuffle, so the row costs ONE shared-memory update per
+// output column (shared-memory float atomics are CAS loops on this architecture -- 9 of them per row before).
+template <int DS, bool ATOMIC>
+__device__ __forceinline__ void scatter_row(float* grow0, float gv, const float (&wc)[2 * (DS + 2) + 1], int lane, int maxcols) {
+  constexpr int F = 1 << DS, W = 2 * (DS + 2) + 1, NG = 32 / F;
+  float acc = 0.f;
+#pragma unroll
+  for (int u = 0; u < W; ++u) {
+    float v = gv * wc[u];
+#pragma unroll
+    for (int o = 1; o < F; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float got = __shfl_sync(0xffffffffu, v, ((lane - u) * F) & 31);
+    if ((unsigned)(lane - u) < (unsigned)NG) acc += got;
+  }
+  if (lane < NG + W - 1 && lane < maxcols && acc != 0.f) {
+    if (ATOMIC) atomicAdd(grow0 + lane, acc);
+    else grow0[lane] += acc;
+  }
+}
+
+// One strip (32 fine columns starting at fine column jf0, a multiple of F) over coarse rows [r0, r1): evaluates the
+// softmax weights of the fine field and accumulates U_H^T G U_W into gt.  `tile` / `gt` are addressed as
+// row * pitch + column with (trow0, tcol0) the tile coordinates of coarse row r0 - R and of coarse column jf0/F - R.
+template <int DS, bool ATOMIC>
+__device__ __forceinline__ void decode_bwd_strip(const DecodeBwdParams<DS>& P, const float* tile, float* gt, int pitch,
+                                                 int trow0, int tcol0, int maxcols, int jf0, int J1, int r0, int r1, float M,
+                                                 float c, float kscale, float xhat, float yhat, float gx, float gy, int lane) {
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  const int h = P.h;
+  const int jf = jf0 + lane;
+  const bool ok = jf < J1;
+  const int jc = ok ? jf : (J1 - 1);
+  float wc[W];
+#pragma unroll
+  for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
+  const float* colbase = tile + tcol0 + (jc / F - jf0 / F);
+  float tmp[W];   // horizontal pass of h, rows a-R .. a+R
+  float gacc[W];  // vertical-transpose accumulators: sum_i wr[i][t] * G[i][j] for coarse row a-R+t
+#pragma unroll
+  for (int t = 0; t < W; ++t) {
+    tmp[t] = dot_w<W>(colbase + (trow0 + t) * pitch, wc);
+    gacc[t] = 0.f;
+  }
+  const float dx = (float)jf - xhat;
+  for (int a = r0; a < r1; ++a) {
+    const int la = a - r0;
+    const bool interior = (a >= R && a <= h - 1 - R);
+    const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
+#pragma unroll
+    for (int p = 0; p < F; ++p) {
+      float wr[W];
+#pragma unroll
+      for (int t = 0; t < W; ++t) wr[t] = interior ? P.phase[p][t] : __ldg(tr + p * W + t);
+      float v = 0.f;
+#pragma unroll
+      for (int t = 0; t < W; ++t) v = fmaf(wr[t], tmp[t], v);
+      const float pr = fast_exp2((v - M) * c);
+      const float gval = ok ? kscale * pr * fmaf(dx, gx, ((float)(a * F + p) - yhat) * gy) : 0.f;
+#pragma unroll
+      for (int t = 0; t < W; ++t) gacc[t] = fmaf(wr[t], gval, gacc[t]);
+    }
+    // coarse row a-R is complete for this lane's column
+    scatter_row<DS, ATOMIC>(gt + (trow0 + la) * pitch + tcol0, gacc[0], wc, lane, maxcols);
+#pragma unroll
+    for (int t = 0; t < W - 1; ++t) {
+      gacc[t] = gacc[t + 1];
+      tmp[t] = tmp[t + 1];
+    }
+    gacc[W - 1] = 0.f;
+    tmp[W - 1] = (a + 1 < r1) ? dot_w<W>(colbase + (trow0 + la + 1 + 2 * R) * pitch, wc) : 0.f;
+  }
+  // flush the remaining W-1 partial rows (coarse rows r1-R .. r1+R-1)
+#pragma unroll
+  for (int t = 0; t < W - 1; ++t)
+    scatter_row<DS, ATOMIC>(gt + (trow0 + (r1 - r0) + t) * pitch + tcol0, gacc[t], wc, lane, maxcols);
+}
+
+// Dense form: one CTA per plane (grid = n_planes), or -- queue mode -- per (plane, row segment) unit of the planes
+// the window kernel could not take; a unit adds its rows into the plane's pre-zeroed gradient with global atomics.
+constexpr int DEC_BWD_SEGS = 8;
+
 template <int DS>
 __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_constant__ DecodeBwdParams<DS> P) {
-  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  constexpr int F = 1 << DS, R = DS + 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int h = P.h, w = P.w, pitch = P.pitch, padl = P.padl;
   const int tile_floats = (h + 2 * R) * pitch;
@@ -504,12 +587,22 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_co
     __syncthreads();
   }
   uint32_t phase = 0;
-  // dense launch: one plane per CTA.  Fallback launch (only_meta): a few resident CTAs scan the window
-  // kernel's flags and run only the planes it could not take.
-  for (size_t plane = blockIdx.x; plane < (size_t)P.n_planes; plane += gridDim.x) {
-    if (P.only_meta && P.only_meta[4 * plane + 2] != 2) continue;  // uniform per CTA
+  const long long nunits = P.queue ? (long long)P.queue[0] * DEC_BWD_SEGS : P.n_planes;
+  for (long long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const size_t plane = P.queue ? (size_t)P.queue[1 + unit / DEC_BWD_SEGS] : (size_t)unit;
+    const float* st = P.stats + 8 * plane;
+    const float M = st[0], S = st[1], xhat = st[2], yhat = st[3];
+    const int A0 = (int)st[4], A1 = (int)st[5], B0 = (int)st[6], B1 = (int)st[7];
+    const float gx = P.gxy[2 * plane], gy = P.gxy[2 * plane + 1];
+    const int nrows = A1 - A0 + 1;
+    int useg0 = A0, useg1 = A1 + 1;  // coarse rows this unit evaluates
+    if (P.queue) {
+      const int sg = (nrows + DEC_BWD_SEGS - 1) / DEC_BWD_SEGS;
+      useg0 = A0 + (int)(unit % DEC_BWD_SEGS) * sg;
+      useg1 = min(useg0 + sg, A1 + 1);
+      if (useg0 >= useg1) continue;  // uniform per CTA
+    }
     const float* __restrict__ src = P.heat + plane * (size_t)h * w;
-
     if (P.bulk) {
       if (warp == 0) {
         if (lane == 0) mbar_expect_tx(bar, (uint32_t)(h * w * 4));
@@ -538,22 +631,17 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_co
     }
     __syncthreads();
 
-    const float* st = P.stats + 8 * plane;
-    const float M = st[0], S = st[1], xhat = st[2], yhat = st[3];
-    const int A0 = (int)st[4], A1 = (int)st[5], B0 = (int)st[6], B1 = (int)st[7];
-    const float gx = P.gxy[2 * plane], gy = P.gxy[2 * plane + 1];
     const float c = P.T * 1.4426950408889634f;
     const float kscale = P.T / S;
-
     if (gx != 0.f || gy != 0.f) {
       const int J0 = B0 * F, J1 = (B1 + 1) * F;
       const int nstrips = (J1 - J0 + 31) >> 5;
-      const int nrows = A1 - A0 + 1;
-      int G = 1, seg = nrows;
+      const int urows = useg1 - useg0;
+      int G = 1, seg = urows;  // split the rows further so that all warps have an item
       {
         int bestcost = 0x7fffffff;
         for (int g = 1; g <= 8; ++g) {
-          const int sg = (nrows + g - 1) / g;
+          const int sg = (urows + g - 1) / g;
           const int cost = ((nstrips * g + DEC_WARPS - 1) / DEC_WARPS) * (sg + 2 * R);
           if (cost < bestcost) {
             bestcost = cost;
@@ -565,80 +653,30 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_co
       const int nitems = nstrips * G;
       for (int item = warp; item < nitems; item += DEC_WARPS) {
         const int sidx = item % nstrips, g = item / nstrips;
-        const int r0 = A0 + g * seg, r1 = min(r0 + seg, A1 + 1);
+        const int r0 = useg0 + g * seg, r1 = min(r0 + seg, useg1);
         if (r0 >= r1) continue;
-        const int jf = J0 + sidx * 32 + lane;
-        const bool ok = jf < J1;
-        const int jc = ok ? jf : (J1 - 1);
-        float wc[W];
-  #pragma unroll
-        for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
-        const int cb = padl + (jc / F - R);
-        const float* colbase = tile + cb;
-        float tmp[W];   // horizontal pass of h, rows a-R .. a+R
-        float gacc[W];  // vertical-transpose accumulators: sum_i wr[i][t] * G[i][j] for coarse row a-R+t
-  #pragma unroll
-        for (int t = 0; t < W; ++t) {
-          tmp[t] = dot_w<W>(colbase + (r0 + t) * pitch, wc);
-          gacc[t] = 0.f;
-        }
-        const float dx = (float)jf - xhat;
-        for (int a = r0; a < r1; ++a) {
-          const bool interior = (a >= R && a <= h - 1 - R);
-          const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
-  #pragma unroll
-          for (int p = 0; p < F; ++p) {
-            float wr[W];
-  #pragma unroll
-            for (int t = 0; t < W; ++t) wr[t] = interior ? P.phase[p][t] : __ldg(tr + p * W + t);
-            float v = 0.f;
-  #pragma unroll
-            for (int t = 0; t < W; ++t) v = fmaf(wr[t], tmp[t], v);
-            const float pr = fast_exp2((v - M) * c);
-            const float gval = ok ? kscale * pr * fmaf(dx, gx, ((float)(a * F + p) - yhat) * gy) : 0.f;
-  #pragma unroll
-            for (int t = 0; t < W; ++t) gacc[t] = fmaf(wr[t], gval, gacc[t]);
-          }
-          // coarse row a-R is complete for this lane's column: scatter through the horizontal taps
-          {
-            float* grow = gtile + a * pitch + cb;  // padded row (a-R)+R; lanes of one coarse column pre-reduce
-  #pragma unroll
-            for (int u = 0; u < W; ++u) {
-              float val = gacc[0] * wc[u];
-  #pragma unroll
-              for (int o = 1; o < F; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-              if ((lane & (F - 1)) == 0 && val != 0.f) atomicAdd(grow + u, val);
-            }
-          }
-  #pragma unroll
-          for (int t = 0; t < W - 1; ++t) {
-            gacc[t] = gacc[t + 1];
-            tmp[t] = tmp[t + 1];
-          }
-          gacc[W - 1] = 0.f;
-          tmp[W - 1] = (a + 1 < r1) ? dot_w<W>(colbase + (a + 1 + 2 * R) * pitch, wc) : 0.f;
-        }
-        // flush the remaining W-1 partial rows (coarse rows r1-R .. r1+R-1)
-  #pragma unroll
-        for (int t = 0; t < W - 1; ++t) {
-          float* grow = gtile + (r1 + t) * pitch + cb;
-  #pragma unroll
-          for (int u = 0; u < W; ++u) {
-            float val = gacc[t] * wc[u];
-  #pragma unroll
-            for (int o = 1; o < F; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-            if ((lane & (F - 1)) == 0 && val != 0.f) atomicAdd(grow + u, val);
-          }
-        }
+        const int jf0 = J0 + sidx * 32;
+        const int tcol0 = padl + (jf0 / F - R);
+        decode_bwd_strip<DS, true>(P, tile, gtile, pitch, r0, tcol0, pitch - tcol0, jf0, J1, r0, r1, M, c, kscale, xhat, yhat, gx, gy,
+                                   lane);
       }
     }
     __syncthreads();
     float* __restrict__ dst = P.gheat + plane * (size_t)h * w;
-    for (int a = warp; a < h; a += DEC_WARPS) {
-      const float* row = gtile + (a + R) * pitch + padl;
-      for (int b = lane; b < w; b += 32) dst[(size_t)a * w + b] = row[b];
+    if (P.queue) {  // rows this unit touched: [useg0 - R, useg1 + R)
+      const int a0 = max(useg0 - R, 0), a1 = min(useg1 + R, h);
+      for (int a = a0 + warp; a < a1; a += DEC_WARPS) {
+        const float* row = gtile + (a + R) * pitch + padl;
+        for (int b = lane; b < w; b += 32)
+          if (row[b] != 0.f) atomicAdd(dst + (size_t)a * w + b, row[b]);
+      }
+    } else {
+      for (int a = warp; a < h; a += DEC_WARPS) {
+        const float* row = gtile + (a + R) * pitch + padl;
+        for (int b = lane; b < w; b += 32) dst[(size_t)a * w + b] = row[b];
+      }
     }
-    __syncthreads();  // tile / gtile are reused by the next plane
+    __syncthreads();  // tile / gtile are reused by the next unit
   }
 }
 
@@ -648,18 +686,19 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_co
 // a window of at most DEC_WIN x DEC_WIN coarse pixels instead of the whole plane.  One warp per plane loads that
 // window straight from global memory, runs the same transpose-of-the-upsample accumulation as decode_bwd_kernel
 // and emits   win[plane][32][32], meta[plane] = {row0, col0, flag, bits(sum(win * heat))}
-// flag 0: zero gradient, 1: window valid, 2: the box does not fit (dense fallback plane, decode_bwd_kernel).
+// flag 0: zero gradient, 1: window valid, 2: the box does not fit: the plane is queued for decode_bwd_kernel's
+// queue mode and its dense gradient (cleared here) goes to P.gheat.
 constexpr int DEC_WIN = 32, DEC_WP = 33;
 
 template <int DS>
 __global__ void __launch_bounds__(128) decode_bwd_window_kernel(const __grid_constant__ DecodeBwdParams<DS> P, float* __restrict__ win,
-                                                                int* __restrict__ meta, long long n_planes) {
-  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+                                                                int* __restrict__ meta, int* __restrict__ queue) {
+  constexpr int F = 1 << DS, R = DS + 2;
   __shared__ float tile_s[4][DEC_WIN * DEC_WP];
   __shared__ float g_s[4][DEC_WIN * DEC_WP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long plane = (long long)blockIdx.x * 4 + warp;
-  if (plane >= n_planes) return;
+  if (plane >= P.n_planes) return;
   const int h = P.h, w = P.w;
   const float gx = P.gxy[2 * plane], gy = P.gxy[2 * plane + 1];
   int4* mout = reinterpret_cast<int4*>(meta) + plane;
@@ -672,7 +711,12 @@ __global__ void __launch_bounds__(128) decode_bwd_window_kernel(const __grid_con
   const int A0 = (int)st[4], A1 = (int)st[5], B0 = (int)st[6], B1 = (int)st[7];
   const int nrows = A1 - A0 + 1, ncols = B1 - B0 + 1;
   if (nrows > DEC_WIN - 2 * R || ncols > DEC_WIN - 2 * R || nrows < 1 || ncols < 1) {
-    if (lane == 0) *mout = make_int4(0, 0, 2, 0);
+    if (lane == 0) {
+      *mout = make_int4(0, 0, 2, 0);
+      queue[1 + atomicAdd(queue, 1)] = (int)plane;
+    }
+    float* dst = P.gheat + (size_t)plane * h * w;
+    for (int i = lane; i < h * w; i += 32) dst[i] = 0.f;
     return;
   }
   float* tile = tile_s[warp];
@@ -695,67 +739,10 @@ __global__ void __launch_bounds__(128) decode_bwd_window_kernel(const __grid_con
   const int J0 = B0 * F, J1 = (B1 + 1) * F;
   const int nstrips = (J1 - J0 + 31) >> 5;
   for (int sidx = 0; sidx < nstrips; ++sidx) {
-    const int jf = J0 + sidx * 32 + lane;
-    const bool ok = jf < J1;
-    const int jc = ok ? jf : (J1 - 1);
-    float wc[W];
-#pragma unroll
-    for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
-    const int cbl = jc / F - B0;  // window column of coarse column jc/F - R
-    const float* colbase = tile + cbl;
-    float tmp[W], gacc[W];
-#pragma unroll
-    for (int t = 0; t < W; ++t) {
-      tmp[t] = dot_w<W>(colbase + t * DEC_WP, wc);
-      gacc[t] = 0.f;
-    }
-    const float dx = (float)jf - xhat;
-    for (int a = A0; a <= A1; ++a) {
-      const int la = a - A0;
-      const bool interior = (a >= R && a <= h - 1 - R);
-      const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
-#pragma unroll
-      for (int p = 0; p < F; ++p) {
-        float wr[W];
-#pragma unroll
-        for (int t = 0; t < W; ++t) wr[t] = interior ? P.phase[p][t] : __ldg(tr + p * W + t);
-        float v = 0.f;
-#pragma unroll
-        for (int t = 0; t < W; ++t) v = fmaf(wr[t], tmp[t], v);
-        const float pr = fast_exp2((v - M) * c);
-        const float gval = ok ? kscale * pr * fmaf(dx, gx, ((float)(a * F + p) - yhat) * gy) : 0.f;
-#pragma unroll
-        for (int t = 0; t < W; ++t) gacc[t] = fmaf(wr[t], gval, gacc[t]);
-      }
-      {
-        float* grow = gt + la * DEC_WP + cbl;
-#pragma unroll
-        for (int u = 0; u < W; ++u) {
-          float val = gacc[0] * wc[u];
-#pragma unroll
-          for (int o = 1; o < F; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-          if ((lane & (F - 1)) == 0 && val != 0.f) atomicAdd(grow + u, val);
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < W - 1; ++t) {
-        gacc[t] = gacc[t + 1];
-        tmp[t] = tmp[t + 1];
-      }
-      gacc[W - 1] = 0.f;
-      tmp[W - 1] = (a + 1 <= A1) ? dot_w<W>(colbase + (la + 1 + 2 * R) * DEC_WP, wc) : 0.f;
-    }
-#pragma unroll
-    for (int t = 0; t < W - 1; ++t) {
-      float* grow = gt + (nrows + t) * DEC_WP + cbl;
-#pragma unroll
-      for (int u = 0; u < W; ++u) {
-        float val = gacc[t] * wc[u];
-#pragma unroll
-        for (int o = 1; o < F; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-        if ((lane & (F - 1)) == 0 && val != 0.f) atomicAdd(grow + u, val);
-      }
-    }
+    const int jf0 = J0 + sidx * 32;
+    const int tcol0 = jf0 / F - B0;  // window column of coarse column jf0/F - R
+    decode_bwd_strip<DS, false>(P, tile, gt, DEC_WP, 0, tcol0, DEC_WIN - tcol0, jf0, J1, A0, A1 + 1, M, c, kscale, xhat, yhat, gx, gy,
+                                lane);
     __syncwarp();
   }
   float dot = 0.f;
@@ -837,7 +824,8 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
 
 template <int DS>
 static int launch_decode_bwd(const float* heat, const float* stats, const float* gxy, int64_t n_planes, int h, int w,
-                             float T, float* gheat, cudaStream_t stream, float* win = nullptr, int* meta = nullptr) {
+                             float T, float* gheat, cudaStream_t stream, float* win = nullptr, int* meta = nullptr,
+                             int* queue = nullptr) {
   using G = UpsampleGeom<DS>;
   const DeviceTable* th = get_device_table(h, DS);
   const DeviceTable* tw = get_device_table(w, DS);
@@ -849,7 +837,7 @@ static int launch_decode_bwd(const float* heat, const float* stats, const float*
   P.tabH = th->win;
   P.tabW = tw->win;
   P.gheat = gheat;
-  P.only_meta = meta;
+  P.queue = queue;
   P.n_planes = n_planes;
   P.h = h;
   P.w = w;
@@ -859,8 +847,9 @@ static int launch_decode_bwd(const float* heat, const float* stats, const float*
   P.T = T;
   for (int p = 0; p < G::F; ++p)
     for (int t = 0; t < G::W; ++t) P.phase[p][t] = th->host.phase[(size_t)p * G::W + t];
-  if (win) {  // sparse windows first; the dense kernel below then only runs the planes they flagged
-    decode_bwd_window_kernel<DS><<<(unsigned)((n_planes + 3) / 4), 128, 0, stream>>>(P, win, meta, (long long)n_planes);
+  if (win) {  // sparse windows first; the dense kernel below then only runs the planes they queued
+    LPB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int), stream));
+    decode_bwd_window_kernel<DS><<<(unsigned)((n_planes + 3) / 4), 128, 0, stream>>>(P, win, meta, queue);
   }
   const size_t smem = ((size_t)2 * (h + 2 * G::R) * P.pitch) * sizeof(float) + 16;
   int dev = 0, max_smem = 0;
@@ -872,7 +861,7 @@ static int launch_decode_bwd(const float* heat, const float* stats, const float*
   }
   LPB_CUDA(cudaFuncSetAttribute(decode_bwd_kernel<DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned grid = (unsigned)n_planes;
-  if (meta) {  // flag scan: one wave of resident CTAs
+  if (queue) {  // queue mode: one wave of resident CTAs
     int sms = 0;
     LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (grid > (unsigned)(2 * sms)) grid = (unsigned)(2 * sms);
@@ -927,17 +916,17 @@ extern "C" int lpb_decode_bwd(const float* heatmaps, const float* stats, const f
 
 extern "C" int lpb_decode_bwd_windows(const float* heatmaps, const float* stats, const float* grad_xy, int64_t n_planes, int h,
                                       int w, int ds, float temperature, float* win, int32_t* meta, float* g_overflow,
-                                      void* stream) {
+                                      int32_t* queue, void* stream) {
   using namespace lpb;
-  LPB_REQUIRE(heatmaps && stats && grad_xy && win && meta && g_overflow, "decode_bwd_windows: null pointer");
+  LPB_REQUIRE(heatmaps && stats && grad_xy && win && meta && g_overflow && queue, "decode_bwd_windows: null pointer");
   LPB_REQUIRE(h >= 1 && w >= 1 && ds >= 1 && ds <= 3, "decode_bwd_windows: bad shape h=%d w=%d ds=%d", h, w, ds);
   LPB_REQUIRE(n_planes >= 0 && n_planes < (1ll << 31), "decode_bwd_windows: bad n_planes");
   if (n_planes == 0) return LPB_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (ds) {
-    case 1: return launch_decode_bwd<1>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, g_overflow, s, win, meta);
-    case 2: return launch_decode_bwd<2>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, g_overflow, s, win, meta);
-    default: return launch_decode_bwd<3>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, g_overflow, s, win, meta);
+    case 1: return launch_decode_bwd<1>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, g_overflow, s, win, meta, queue);
+    case 2: return launch_decode_bwd<2>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, g_overflow, s, win, meta, queue);
+    default: return launch_decode_bwd<3>(heatmaps, stats, grad_xy, n_planes, h, w, temperature, g_overflow, s, win, meta, queue);
   }
 }
 

@@ -205,8 +205,9 @@ def decode_backward_windows(heatmaps, stats, grad_xy, ds, temperature):
     # only planes whose support overflows a window are ever written/read here (none for peaked heatmaps);
     # the caching allocator hands the block back without touching it
     overflow = torch.empty_like(heatmaps)
+    queue = torch.empty((b * k + 1,), device=heatmaps.device, dtype=torch.int32)
     with torch.cuda.device(heatmaps.device):
-        check(lib.lpb_decode_bwd_windows(_ptr(heatmaps), _ptr(stats), _ptr(grad_xy), b * k, h, w, ds, temperature, _ptr(win), _ptr(meta), _ptr(overflow), _stream()))
+        check(lib.lpb_decode_bwd_windows(_ptr(heatmaps), _ptr(stats), _ptr(grad_xy), b * k, h, w, ds, temperature, _ptr(win), _ptr(meta), _ptr(overflow), _ptr(queue), _stream()))
     return win, meta, overflow
 
 
