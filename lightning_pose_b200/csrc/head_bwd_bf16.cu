@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
 // =====================================================================================================
 // b3a: data gradient of the first deconv + inverse PixelShuffle:  G1 -> d features (NCHW bf16)
 // =====================================================================================================
-constexpr int B3A_THREADS = 192;  // warp 0 loader, warp 1 MMA, warps 2-5 epilogue (lane = channel)
+constexpr int B3A_THREADS = 320;  // warp 0 loader, warp 1 MMA, warps 2-9 epilogue (lane = channel, two warps per TMEM lane quarter)
 
 struct B3aParams {
   const __nv_bfloat16* G1;   // [B][10][L.rows][8] padded row layout
@@ -368,6 +368,7 @@ struct B3aParams {
   int nhalf_cols;            // TMEM columns per half (multiple of 16)
 };
 
+template <int WS2>
 __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_constant__ B3aParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Wi = P.Wi, Hi = P.Hi, Pp = Wi + 1, LEAD = Pp + 1;
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
     mbar_init(g_empty, 1);
     mbar_init(w_full, 1);
     mbar_init(t_full, 1);
-    mbar_init(t_empty, 128);
+    mbar_init(t_empty, 256);
     fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
@@ -455,34 +456,49 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
       }
     }
   } else {
-    const int q = warp & 3;
-    const int c = mt * 128 + 32 * q + lane;  // shuffled channel owned by this thread (= TMEM lane)
-    const int Ws2 = Wi / 2, HW = (Hi / 2) * Ws2;
+    // Epilogue.  Thread = shuffled channel c (TMEM lane); shuffled pixel (m, n) = (2i + di, 2j + dj) belongs to source
+    // plane 4c + 2di + dj.  A work item is (di, pair of feature rows i, i+1): two accumulator rows m = 2i + di and m + 2,
+    // i.e. 2 * WS2 consecutive elements of each of the planes dj = 0, 1 -> aligned 16-byte stores.  The two warps of a
+    // lane quarter take alternate items.
+    const int q = warp & 3, e = (warp - 2) >> 2;
+    const int c = mt * 128 + 32 * q + lane;
+    const int HW = (Hi / 2) * WS2;
+    constexpr int NCH = (2 * WS2 + 15) / 16;  // 16-column TMEM loads per accumulator row
+    const int npairs = Hh / 4;                // feature-row pairs per half
     int nb = 0;
     for (int b = slot; b < P.B; b += nslot) {
       for (int hf = 0; hf < 2; ++hf, ++nb) {
         mbar_wait(t_full, nb & 1);
         tc::fence_after_sync();
-        for (int ml = 0; ml < Hh; ++ml) {
-          const int m = hf * Hh + ml;
-          const int i = m >> 1, di = m & 1;
-          __nv_bfloat16* base = P.dfeat + ((size_t)b * 4 * P.C4 + 4 * c + 2 * di) * HW + (size_t)i * Ws2;
-          for (int nc = 0; nc < Wi; nc += 16) {  // 16 raster columns = 8 feature columns of each dj
-            float v[16];
-            tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + ml * Pp + nc, v);
-            const int jn = min(8, (Wi - nc) / 2);  // valid feature columns in this group
+        for (int item = e; item < 2 * npairs; item += 2) {
+          const int di = item & 1, ip = item >> 1;
+          const int ml = 4 * ip + di;  // first accumulator row of the item within this half
+          float v[2][NCH * 16];
 #pragma unroll
-            for (int dj = 0; dj < 2; ++dj) {
-              __nv_bfloat16* dst = base + (size_t)dj * HW + nc / 2;
+          for (int r = 0; r < 2; ++r)
 #pragma unroll
-              for (int j4 = 0; j4 < 2; ++j4) {
-                if (4 * j4 < jn) {
-                  __nv_bfloat162 lo = __floats2bfloat162_rn(v[2 * (4 * j4) + dj], v[2 * (4 * j4 + 1) + dj]);
-                  __nv_bfloat162 hi = __floats2bfloat162_rn(v[2 * (4 * j4 + 2) + dj], v[2 * (4 * j4 + 3) + dj]);
-                  *reinterpret_cast<uint2*>(dst + 4 * j4) =
-                      make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-                }
+            for (int k = 0; k < NCH; ++k) {
+              float t16[16];
+              tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (ml + 2 * r) * Pp + 16 * k, t16);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[r][16 * k + i] = t16[i];
+            }
+          const int i0 = (hf * Hh) / 2 + 2 * ip;  // first feature row of the pair
+#pragma unroll
+          for (int dj = 0; dj < 2; ++dj) {
+            __nv_bfloat16* dst = P.dfeat + ((size_t)b * 4 * P.C4 + 4 * c + 2 * di + dj) * HW + (size_t)i0 * WS2;
+#pragma unroll
+            for (int s4 = 0; s4 < (2 * WS2) / 8; ++s4) {  // 8 consecutive elements of [row r][j]
+              uint32_t pk[4];
+#pragma unroll
+              for (int e2 = 0; e2 < 4; ++e2) {
+                const int x0 = 8 * s4 + 2 * e2, x1 = x0 + 1;  // index into the 2*WS2 run
+                const float f0 = v[x0 / WS2][2 * (x0 % WS2) + dj];
+                const float f1 = v[x1 / WS2][2 * (x1 % WS2) + dj];
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
               }
+              *reinterpret_cast<uint4*>(dst + 8 * s4) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
         }
@@ -702,7 +718,8 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
   LPB_REQUIRE(g_out || win, "head_bwd_bf16: neither a dense gradient nor decode windows given");
   LPB_REQUIRE(!win || (win_meta && g_overflow), "head_bwd_bf16: windows need their meta and overflow buffers");
   LPB_REQUIRE(B >= 0 && C >= 512 && C % 512 == 0 && H >= 1 && W >= 1, "head_bwd_bf16: bad feature shape C=%d H=%d W=%d", C, H, W);
-  LPB_REQUIRE(c1 >= 1 && c1 < GB_CLS && c2 >= 1 && c2 <= GB_CLS && (W % 4) == 0, "head_bwd_bf16: unsupported channels/width");
+  LPB_REQUIRE(c1 >= 1 && c1 < GB_CLS && c2 >= 1 && c2 <= GB_CLS && (W % 4) == 0 && (H % 4) == 0 && W <= 16,
+              "head_bwd_bf16: unsupported channels / feature map (needs H %% 4 == 0, W in {4, 8, 12, 16})");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int C4 = C / 4, Hi1 = 2 * H, Wi1 = 2 * W, Hi2 = 4 * H, Wi2 = 4 * W;
   LPB_CUDA(cudaMemsetAsync(dw1, 0, sizeof(float) * (size_t)C4 * c1 * 9, s));
@@ -795,12 +812,24 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
     const int rows_alloc = (Wi1 + 2 + 2 * nhalf + 7) & ~7;
     const size_t smem = (size_t)GB_KC * rows_alloc * 16 + (size_t)4 * GB_KC * 128 * 16 + 64;
     LPB_REQUIRE(smem <= 220 * 1024, "head_bwd_bf16: layer-1 operands need %zu B shared memory", smem);
-    LPB_CUDA(cudaFuncSetAttribute(b3a_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntile = C4 / 128;
     int slots = sms / ntile;
     if (slots < 1) slots = 1;
     if (slots > B) slots = B;
-    b3a_dgrad_kernel<<<slots * ntile, B3A_THREADS, smem, s>>>(p);
+    auto run = [&](auto kern) -> int {
+      LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<slots * ntile, B3A_THREADS, smem, s>>>(p);
+      return LPB_OK;
+    };
+    int rc = LPB_ERR_UNSUPPORTED;
+    switch (W) {
+      case 4: rc = run(b3a_dgrad_kernel<4>); break;
+      case 8: rc = run(b3a_dgrad_kernel<8>); break;
+      case 12: rc = run(b3a_dgrad_kernel<12>); break;
+      case 16: rc = run(b3a_dgrad_kernel<16>); break;
+      default: set_error("head_bwd_bf16: feature width %d not in this build's epilogue set {4, 8, 12, 16}", W);
+    }
+    if (rc != LPB_OK) return rc;
   }
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;

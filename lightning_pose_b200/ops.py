@@ -185,7 +185,7 @@ def _head_forward_bf16(f, weights, biases, final_softmax, train=False):
     check(lib.lpb_head_bf16_workspace_bytes(b, c, h, w, c1, c2, C.byref(nbytes)))
     ws = torch.empty((nbytes.value,), device=f.device, dtype=torch.uint8)
     out = torch.empty((b, c2, 8 * h, 8 * w), device=f.device, dtype=torch.float32)
-    native_bwd = train and c % 512 == 0 and w % 4 == 0 and ((h * (2 * w + 1) + 15) & ~15) <= 304
+    native_bwd = train and c % 512 == 0 and w in (4, 8, 12, 16) and h % 4 == 0 and ((h * (2 * w + 1) + 15) & ~15) <= 304
     xs = None
     if native_bwd:  # row-layout copy of the shuffled features for the weight-gradient GEMM
         check(lib.lpb_head_bf16_saved_bytes(b, c, h, w, C.byref(nbytes)))
