@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
   }
   if (tid < 32) smask[tid] = 0u;
   if (P.bulk) {
-    mbar_wait(bar, tma_phase);
+    if (warp == 0) mbar_wait(bar, tma_phase);  // one warp polls; the bytes are in shared memory once the phase flips
     tma_phase ^= 1;
   }
   __syncthreads();

@@ -112,8 +112,9 @@ __global__ void pack_convt_weights_kernel(const float* __restrict__ w, const flo
 // =====================================================================================================
 // k1a: PixelShuffle + first transposed convolution
 // =====================================================================================================
-// warps 0-3 transposers, warp 4 MMA issuer (+TMEM owner), warps 5-8 epilogue, warp 9 TMA loader
-constexpr int K1A_THREADS = 320;
+// warps 0..TW-1 transposers, warp TW MMA issuer (+TMEM owner), warps TW+1..TW+4 epilogue, warp TW+5 TMA loader
+constexpr int K1A_TW = 4;                      // transposer warps
+constexpr int K1A_THREADS = 32 * (K1A_TW + 6);  // + MMA warp, 4 epilogue warps, TMA loader warp
 constexpr int K1A_ASTAGES = 2;  // K-major operand stages (A + packed weights)
 constexpr int K1A_RSTAGES = 2;  // raw NCHW stages filled by the TMA engine
 
@@ -152,16 +153,16 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
   for (int i = tid; i < K1A_ASTAGES * stage_bytes / 16; i += K1A_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&full[s], 129);
+      mbar_init(&full[s], 32 * K1A_TW + 1);
       mbar_init(&empty[s], 1);
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], 128);
+      mbar_init(&raw_empty[s], 32 * K1A_TW);
     }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 128);
     fence_mbar_init();
   }
-  if (warp == 4) tc::tmem_alloc(tmem_ptr, 512);
+  if (warp == K1A_TW) tc::tmem_alloc(tmem_ptr, 512);
   fence_proxy_async();  // generic-proxy zero fill -> visible to the async proxy (UMMA operand reads)
   tc::fence_before_sync();
   __syncthreads();
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
   for (int b = blockIdx.x; b < P.B; b += gridDim.x) ++nframes;
   const int total_it = nframes * P.nstages;
 
-  if (warp == 9) {
+  if (warp == K1A_TW + 5) {
     // ================= TMA loader: raw feature slabs run ahead, weights follow the operand slots ====
     if (lane == 0) {
       auto issue_raw = [&](int it) {
@@ -194,30 +195,52 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
                  reinterpret_cast<const unsigned char*>(P.wpk) + (size_t)st * HB_BSTAGE_BYTES, HB_BSTAGE_BYTES, &full[s]);
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < K1A_TW) {
     // ================= transposers: raw NCHW slab (smem) -> K-major rows, PixelShuffle folded in ======
+    // A task is one 8x8 bf16 transpose: 8 channels x 8 consecutive spatial positions (one 16-byte chunk per channel)
+    // of one sub-pixel class q -> 8 rows of 16 bytes.  Which tasks a thread owns, and where they read / write, is the
+    // same for every stage, so the index arithmetic (divisions by runtime sizes) is done once, up front.
     const int nchunk = P.HW / 8;  // 16-byte chunks of 8 consecutive spatial positions per channel
     const int ntasks = 4 * 4 * nchunk;
+    constexpr int MAXT = 3;
+    uint32_t t_raw[MAXT], t_a[MAXT], t_x[MAXT];
+    int t_wrap[MAXT];
+    int nt = 0;
+#pragma unroll
+    for (int k = 0; k < MAXT; ++k) {
+      const int task = tid + k * 32 * K1A_TW;
+      t_raw[k] = t_a[k] = t_x[k] = 0;
+      t_wrap[k] = 8;
+      if (task < ntasks) {
+        const int sc = task % nchunk, q = (task / nchunk) & 3, kc = task / (4 * nchunk);
+        const int sp0 = sc * 8, i0 = sp0 / P.W, jc0 = sp0 - i0 * P.W;
+        const int row0 = (2 * i0 + (q >> 1)) * g.P + 2 * jc0 + (q & 1);
+        t_raw[k] = (uint32_t)(((4 * kc * 8 + q) * P.HW + sc * 8) * 2);
+        t_a[k] = (uint32_t)((kc * g.rows_alloc + row0) * 16);
+        t_x[k] = (uint32_t)((kc * P.Lxs.rows + P.Lxs.lead + row0) * 16);
+        t_wrap[k] = P.W - jc0;  // position at which the image row wraps (W >= 8: at most once per task)
+        nt = k + 1;
+      }
+    }
+    const uint32_t chan_stride = (uint32_t)(4 * P.HW * 2);       // next shuffled channel e -> 4 source channels on
+    const uint32_t wrap_jump = (uint32_t)((2 * g.P - 2 * P.W) * 16);  // extra bytes once the position wraps to row i + 1
     for (int it = 0; it < total_it; ++it) {
       const int s = it % K1A_ASTAGES, r = it % K1A_RSTAGES;
       mbar_wait(&raw_full[r], (it / K1A_RSTAGES) & 1);
       mbar_wait(&empty[s], ((it / K1A_ASTAGES) & 1) ^ 1);
       unsigned char* As = stage_base + s * stage_bytes;
-      __nv_bfloat16* xs_st = nullptr;  // this (frame, stage)'s 4 K-chunks of the saved copy
+      unsigned char* xs_st = nullptr;  // this (frame, stage)'s 4 K-chunks of the saved copy
       if (P.xs) {
         const int b = blockIdx.x + (it / P.nstages) * gridDim.x, st = it % P.nstages;
-        xs_st = P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)P.Lxs.rows * 8;
+        xs_st = reinterpret_cast<unsigned char*>(P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)P.Lxs.rows * 8);
       }
       const unsigned char* raw = raw_base + r * raw_bytes;
-      for (int task = tid; task < ntasks; task += 128) {
-        const int sc = task % nchunk;
-        const int q = (task / nchunk) & 3;
-        const int kc = task / (4 * nchunk);
+#pragma unroll
+      for (int k = 0; k < MAXT; ++k) {
+        if (k >= nt) break;
         uint4 v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          v[e] = *reinterpret_cast<const uint4*>(raw + ((size_t)(4 * (kc * 8 + e) + q) * P.HW + sc * 8) * 2);
-        const int di = q >> 1, dj = q & 1;
+        for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const uint4*>(raw + t_raw[k] + e * chan_stride);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t wj[8];
@@ -231,11 +254,10 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
             o.y = __byte_perm(wj[2], wj[3], sel);
             o.z = __byte_perm(wj[4], wj[5], sel);
             o.w = __byte_perm(wj[6], wj[7], sel);
-            const int sp = sc * 8 + 2 * j + hl;  // spatial index i*W + jcol
-            const int i = sp / P.W, jc = sp - i * P.W;
-            const int row = (2 * i + di) * g.P + (2 * jc + dj);
-            *reinterpret_cast<uint4*>(As + ((size_t)kc * g.rows_alloc + row) * 16) = o;
-            if (xs_st) *reinterpret_cast<uint4*>(xs_st + ((size_t)kc * P.Lxs.rows + P.Lxs.lead + row) * 8) = o;
+            const int pos = 2 * j + hl;  // position within the task: spatial index sc*8 + pos
+            const uint32_t delta = (uint32_t)(pos * 32) + (pos >= t_wrap[k] ? wrap_jump : 0u);
+            *reinterpret_cast<uint4*>(As + t_a[k] + delta) = o;
+            if (xs_st) *reinterpret_cast<uint4*>(xs_st + t_x[k] + delta) = o;
           }
         }
       }
@@ -243,7 +265,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
       tc::mbar_arrive(&full[s]);
       tc::mbar_arrive(&raw_empty[r]);
     }
-  } else if (warp == 4) {
+  } else if (warp == K1A_TW) {
     // ================= MMA issuer =================
     const uint32_t idesc = tc::make_idesc_bf16_f32(128, HB_NCOLS);
     const uint32_t lbo_a = g.rows_alloc * 16, lbo_b = HB_NCOLS * 16;
@@ -338,7 +360,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem_base, 512);
+  if (warp == K1A_TW) tc::tmem_dealloc(tmem_base, 512);
 }
 
 // =====================================================================================================
@@ -606,6 +628,10 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   LPB_REQUIRE(features && w1 && b1 && w2 && b2 && out && workspace, "head_fwd_bf16: null pointer");
   LPB_REQUIRE(B >= 0 && C >= 128 && C % 128 == 0 && H >= 1 && W >= 1, "head_fwd_bf16: bad feature shape C=%d H=%d W=%d", C, H, W);
   LPB_REQUIRE((H * W) % 8 == 0, "head_fwd_bf16: H*W must be a multiple of 8 (got %d)", H * W);
+  if (!((W >= 7 || W == 4 || W == 6) && H * W <= 192)) {
+    set_error("head_fwd_bf16: feature map %dx%d outside this build's staging (W >= 7 or W in {4, 6}; H*W <= 192)", H, W);
+    return LPB_ERR_UNSUPPORTED;
+  }
   LPB_REQUIRE(c1 >= 1 && c1 < HB_CLS && c2 >= 1 && c2 <= HB_CLS, "head_fwd_bf16: channel counts %d/%d exceed %d", c1, c2, HB_CLS);
   if (B == 0) return LPB_OK;
   const HeadGeom g1 = make_geom(2 * H, 2 * W), g2 = make_half_geom(2 * H, 4 * W);  // layer 2: 4H rows in two halves

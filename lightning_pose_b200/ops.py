@@ -179,7 +179,7 @@ def _head_forward_bf16(f, weights, biases, final_softmax, train=False):
     w1, w2 = (_cuda_f32(x, "weight") for x in weights)
     b1, b2 = (_cuda_f32(x, "bias") for x in biases)
     c1, c2 = w1.shape[1], w2.shape[1]
-    if c % 128 or (h * w) % 8 or c1 >= 20 or c2 > 20 or (2 * h * (2 * w + 1) + 127) // 128 * 80 > 512:
+    if c % 128 or (h * w) % 8 or c1 >= 20 or c2 > 20 or (2 * h * (2 * w + 1) + 127) // 128 * 80 > 512 or h * w > 192 or not (w >= 7 or w in (4, 6)):
         return None
     nbytes = C.c_size_t(0)
     check(lib.lpb_head_bf16_workspace_bytes(b, c, h, w, c1, c2, C.byref(nbytes)))
