@@ -74,23 +74,54 @@ __global__ void __launch_bounds__(256) plane_dot_kernel(G2Src S, int hw, float* 
 // look-ups are rare (a 32x32 patch of a 96x96 plane) and come last.
 constexpr int G2B_THREADS = 128;
 
+// HAS_WIN: the decode windows are staged per CTA into shared memory first (the CTA's 128 input-grid pixels span at
+// most G2B_MROWS rows m, i.e. 2 * G2B_MROWS output rows; a window contributes 32 columns of each), so the main loop
+// adds them with branch-free shared-memory reads instead of divergent global gathers.
+constexpr int G2B_MROWS = 4;  // input-grid rows a CTA can touch: ceil(128 / Wi) + 1 for Wi >= 43 (host checks)
+
 template <bool HAS_G, bool HAS_P, bool HAS_WIN>
-__global__ void __launch_bounds__(G2B_THREADS) g2_build_kernel(G2Src S, int B, int C, int Hi, int Wi, int ctas_per_frame,
+__global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B, int C, int Hi, int Wi, int ctas_per_frame,
                                                                __nv_bfloat16* __restrict__ G, RowLayout L) {
-  const int b = blockIdx.x / ctas_per_frame, t = (blockIdx.x - b * ctas_per_frame) * G2B_THREADS + threadIdx.x;
+  const int b = blockIdx.x / ctas_per_frame, t0 = (blockIdx.x - b * ctas_per_frame) * G2B_THREADS, t = t0 + threadIdx.x;
   const int Wo = 2 * Wi, Ho = 2 * Hi;
-  __shared__ int4 smeta[GB_CLS];
   __shared__ float sdot[GB_CLS];
+  __shared__ int4 smeta[GB_CLS];
+  __shared__ float wtile[HAS_WIN ? GB_CLS * 2 * G2B_MROWS * 32 : 1];
+  const int m0 = t0 / Wi;
   if (threadIdx.x < GB_CLS) {
-    int4 mt = make_int4(0, 0, 0, 0);
     float d = 0.f;
+    int4 mt = make_int4(0, 0, 0, 0);
     if (threadIdx.x < C) {
       const size_t plane = (size_t)b * C + threadIdx.x;
-      if (HAS_WIN) mt = reinterpret_cast<const int4*>(S.meta)[plane];
-      if (HAS_P) d = (mt.z == 1 ? __int_as_float(mt.w) : 0.f) + (S.ddot ? S.ddot[plane] : 0.f);
+      if (S.meta) mt = reinterpret_cast<const int4*>(S.meta)[plane];
+      if (HAS_P) {
+        if (mt.z == 1) d = __int_as_float(mt.w);
+        if (S.ddot) d += S.ddot[plane];
+      }
     }
-    smeta[threadIdx.x] = mt;
     sdot[threadIdx.x] = d;
+    smeta[threadIdx.x] = mt;
+  }
+  if (HAS_WIN) {
+    __syncthreads();
+    // wtile[o][yl][lx] = win[o][2*m0 + yl - row0][lx] (0 outside the window / for planes without one)
+    // one window row (32 floats) per warp and step, all steps unrolled: the predicated loads are independent
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    constexpr int NROW = GB_CLS * 2 * G2B_MROWS, NSTEP = NROW / (G2B_THREADS / 32);
+    float stage[NSTEP];
+#pragma unroll
+    for (int k = 0; k < NSTEP; ++k) {
+      const int r = wq + k * (G2B_THREADS / 32), o = r / (2 * G2B_MROWS), yl = r - o * (2 * G2B_MROWS);
+      float v = 0.f;
+      if (o < C) {
+        const int4 mt = smeta[o];
+        const int ly = 2 * m0 + yl - mt.x;
+        if (mt.z == 1 && (unsigned)ly < 32u) v = __ldg(S.win + ((size_t)b * C + o) * 1024 + ly * 32 + lane);
+      }
+      stage[k] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < NSTEP; ++k) wtile[(wq + k * (G2B_THREADS / 32)) * 32 + lane] = stage[k];
   }
   __syncthreads();
   if (t >= Hi * Wi) return;
@@ -111,18 +142,17 @@ __global__ void __launch_bounds__(G2B_THREADS) g2_build_kernel(G2Src S, int B, i
       }
     }
     if (HAS_WIN) {
+      const float* wrow = wtile + (2 * (m - m0) + py) * 32;
 #pragma unroll
       for (int o = 0; o < GB_CLS; ++o) {
         if (o < C) {
           const int4 mt = smeta[o];
-          if (mt.z == 1) {
-            const int ly = y - mt.x, lx = x - mt.y;
-            if ((unsigned)ly < 32u && lx >= -1 && lx < 32) {
-              const float* wr = S.win + ((size_t)b * C + o) * 1024 + ly * 32;
-              if (lx >= 0) gv[o].x += __ldg(wr + lx);
-              if (lx + 1 < 32) gv[o].y += __ldg(wr + lx + 1);
-            }
-          } else if (mt.z == 2) {
+          const int lx = x - mt.y;  // window column of output pixel x; x + 1 -> lx + 1
+          const float w0 = wrow[o * (64 * G2B_MROWS) + min(max(lx, 0), 31)];
+          const float w1 = wrow[o * (64 * G2B_MROWS) + min(max(lx + 1, 0), 31)];
+          gv[o].x += (unsigned)lx < 32u ? w0 : 0.f;
+          gv[o].y += (unsigned)(lx + 1) < 32u ? w1 : 0.f;
+          if (mt.z == 2) {  // dense fallback plane (rare; uniform per CTA)
             const float2 u = __ldg(reinterpret_cast<const float2*>(S.gov + off0 + o * pstride));
             gv[o].x += u.x, gv[o].y += u.y;
           }
@@ -155,11 +185,48 @@ __global__ void __launch_bounds__(G2B_THREADS) g2_build_kernel(G2Src S, int B, i
   }
 }
 
+// Fallback for narrow images (a CTA's 128 pixels span more than G2B_MROWS rows): one warp per plane re-evaluates
+// the pixels under its window and overwrites those bf16 entries after a window-less g2_build pass.
+template <bool HAS_G, bool HAS_P>
+__global__ void __launch_bounds__(128) g2_patch_kernel(G2Src S, long long n_planes, int C, int Hi, int Wi,
+                                                      __nv_bfloat16* __restrict__ G, RowLayout L) {
+  const int lane = threadIdx.x & 31;
+  const long long plane = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (plane >= n_planes) return;
+  const int4 mt = reinterpret_cast<const int4*>(S.meta)[plane];
+  if (mt.z == 0) return;
+  const int Wo = 2 * Wi, Ho = 2 * Hi;
+  const int b = (int)(plane / C), o = (int)(plane - (long long)b * C);
+  float dot = 0.f;
+  if (HAS_P) dot = (mt.z == 1 ? __int_as_float(mt.w) : 0.f) + (S.ddot ? S.ddot[plane] : 0.f);
+  const size_t poff = (size_t)plane * Ho * Wo;
+  const bool win = mt.z == 1;
+  const int n_it = win ? 1024 : Ho * Wo;
+  for (int i = lane; i < n_it; i += 32) {
+    const float gw = __ldg((win ? S.win + (size_t)plane * 1024 : S.gov + poff) + i);
+    const int y = win ? mt.x + (i >> 5) : i / Wo, x = win ? mt.y + (i & 31) : i % Wo;
+    if (gw == 0.f || (unsigned)y >= (unsigned)Ho || (unsigned)x >= (unsigned)Wo) continue;
+    float g = gw;
+    if (HAS_G) g += __ldg(S.g_out + poff + (size_t)y * Wo + x);
+    if (HAS_P) g = __ldg(S.probs + poff + (size_t)y * Wo + x) * (g - dot);
+    const int k = (((y & 1) << 1) | (x & 1)) * GB_CLS + o;
+    G[(((size_t)b * GB_KC + (k >> 3)) * L.rows + L.lead + (size_t)(y >> 1) * L.Pp + (x >> 1)) * 8 + (k & 7)] = __float2bfloat16_rn(g);
+  }
+}
+
 template <bool HAS_G, bool HAS_P>
 static void launch_g2_build(const G2Src& S, int B, int C, int Hi, int Wi, __nv_bfloat16* G, RowLayout L, cudaStream_t s) {
   const int cpf = (Hi * Wi + G2B_THREADS - 1) / G2B_THREADS;
-  if (S.win) g2_build_kernel<HAS_G, HAS_P, true><<<(unsigned)(B * cpf), G2B_THREADS, 0, s>>>(S, B, C, Hi, Wi, cpf, G, L);
-  else g2_build_kernel<HAS_G, HAS_P, false><<<(unsigned)(B * cpf), G2B_THREADS, 0, s>>>(S, B, C, Hi, Wi, cpf, G, L);
+  const bool fits = (G2B_THREADS + Wi - 1) / Wi + 1 <= G2B_MROWS;  // rows m a CTA's pixels can span
+  if (S.win && fits) {
+    g2_build_kernel<HAS_G, HAS_P, true><<<(unsigned)(B * cpf), G2B_THREADS, 0, s>>>(S, B, C, Hi, Wi, cpf, G, L);
+    return;
+  }
+  g2_build_kernel<HAS_G, HAS_P, false><<<(unsigned)(B * cpf), G2B_THREADS, 0, s>>>(S, B, C, Hi, Wi, cpf, G, L);
+  if (S.win) {
+    const long long np = (long long)B * C;
+    g2_patch_kernel<HAS_G, HAS_P><<<(unsigned)((np + 3) / 4), 128, 0, s>>>(S, np, C, Hi, Wi, G, L);
+  }
 }
 
 // ---- weight packing for the data-gradient GEMMs ----------------------------------------------------------
@@ -538,13 +605,15 @@ struct WgParams {
   int XR;                     // X rows per K-chunk in smem (KR + Wi + 2, multiple of 8)
   int kcx, kcx_total;         // K-chunks (8 channels) per CTA group / per frame
   int Cin, Cout, ones_c;
+  int stack;                  // 1: the four shifted copies of X are stacked along N in smem -> one MMA per K step
+                              // (small channel counts: an N = 32 MMA costs as much operand fetch as an N = 128 one)
   int smem_bytes;
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Wi = P.Wi, Hi = P.Hi, Pp = Wi + 1, R = P.R, KR = P.KR, XR = P.XR;
-  const int g_bytes = GB_KC * KR * 16, x_bytes = P.kcx * XR * 16;
+  const int g_bytes = GB_KC * KR * 16, x_bytes = (P.stack ? 4 : 1) * P.kcx * XR * 16;
   unsigned char* Gs = smem;
   unsigned char* Xs = smem + 2 * g_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P.smem_bytes - 64);
@@ -581,19 +650,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       const int s = j & 1, b = u / nchunk, y0 = (u - b * nchunk) * R;
       mbar_wait(&empty[s], ((j >> 1) & 1) ^ 1);
       // one copy per K-chunk: R image rows of G; R + 1 rows of X (the row below is the shifts' halo)
-      const uint32_t gbytes = (uint32_t)(R * Pp * 16), xbytes = (uint32_t)((R + 1) * Pp * 16);
-      if (lane == 0) mbar_expect_tx(&full[s], GB_KC * gbytes + P.kcx * xbytes);
+      const uint32_t gbytes = (uint32_t)(R * Pp * 16), xbytes = P.stack ? gbytes : (uint32_t)((R + 1) * Pp * 16);
+      const int nx = (P.stack ? 4 : 1) * P.kcx;  // X copies: stacked mode loads each K-chunk once per shift, pre-shifted
+      if (lane == 0) mbar_expect_tx(&full[s], GB_KC * gbytes + nx * xbytes);
       __syncwarp();
       const size_t row0 = (size_t)P.L.lead + (size_t)y0 * Pp;
       if (lane < GB_KC)
         bulk_g2s(Gs + (size_t)s * g_bytes + (size_t)lane * KR * 16, P.G + (((size_t)b * GB_KC + lane) * P.L.rows + row0) * 8, gbytes,
                  &full[s]);
-      if (lane < P.kcx)
+      if (lane < nx) {
+        const int sh = lane / P.kcx, kc = lane - sh * P.kcx;
+        const size_t shift_rows = P.stack ? (size_t)((sh >> 1) * Pp + (sh & 1)) : 0;
         bulk_g2s(Xs + (size_t)s * x_bytes + (size_t)lane * XR * 16,
-                 P.X + (((size_t)b * P.kcx_total + (size_t)grp * P.kcx + lane) * P.L.rows + row0) * 8, xbytes, &full[s]);
+                 P.X + (((size_t)b * P.kcx_total + (size_t)grp * P.kcx + kc) * P.L.rows + row0 + shift_rows) * 8, xbytes, &full[s]);
+      }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = tc::make_idesc_bf16_f32(128, N) | (1u << 15) | (1u << 16);  // both operands MN-major
+    const uint32_t idesc = tc::make_idesc_bf16_f32(128, P.stack ? 4 * N : N) | (1u << 15) | (1u << 16);  // both operands MN-major
     const uint32_t g0 = smem_u32(Gs), x0 = smem_u32(Xs);
     int j = 0;
     for (int u = slot; u < nunits; u += nslot, ++j) {
@@ -603,6 +676,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       if (lane == 0) {
         for (int k16 = 0; k16 < KR / 16; ++k16) {
           const uint64_t gd = tc::make_smem_desc(g0 + s * g_bytes + k16 * 256, 128, KR * 16);
+          if (P.stack) {
+            tc::umma_bf16(tmem_base, gd, tc::make_smem_desc(x0 + s * x_bytes + k16 * 256, 128, XR * 16), idesc, (j | k16) != 0 ? 1u : 0u);
+            continue;
+          }
 #pragma unroll
           for (int sh = 0; sh < 4; ++sh) {
             const int shift_rows = (sh >> 1) * Pp + (sh & 1);
@@ -649,13 +726,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
 }
 
 static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, float* dW, float* dbias, int B, int Hi, int Wi,
-                        int kcx, int kcx_total, int Cin, int Cout, int ones_c, int sms, cudaStream_t s) {
+                        int kcx, int kcx_total, int Cin, int Cout, int ones_c, int stack, int sms, cudaStream_t s) {
   // image rows per unit: the largest divisor of Hi (<= 8) whose two stages fit in shared memory
   int R = 0;
   for (int r = Hi < 8 ? Hi : 8; r >= 1; --r) {
     if (Hi % r) continue;
-    const int kr = (r * (Wi + 1) + 15) & ~15, xr = (kr + Wi + 2 + 7) & ~7;
-    if ((size_t)2 * GB_KC * kr * 16 + (size_t)2 * kcx * xr * 16 + 64 <= 225 * 1024) {
+    const int kr = (r * (Wi + 1) + 15) & ~15, xr = stack ? kr : ((kr + Wi + 2 + 7) & ~7);
+    if ((size_t)2 * GB_KC * kr * 16 + (size_t)2 * (stack ? 4 : 1) * kcx * xr * 16 + 64 <= 225 * 1024) {
       R = r;
       break;
     }
@@ -672,13 +749,14 @@ static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, float* d
   p.Wi = Wi;
   p.R = R;
   p.KR = (R * (Wi + 1) + 15) & ~15;
-  p.XR = (p.KR + Wi + 2 + 7) & ~7;
+  p.XR = stack ? p.KR : ((p.KR + Wi + 2 + 7) & ~7);
+  p.stack = stack;
   p.kcx = kcx;
   p.kcx_total = kcx_total;
   p.Cin = Cin;
   p.Cout = Cout;
   p.ones_c = ones_c;
-  const size_t gb = (size_t)GB_KC * p.KR * 16, xb = (size_t)kcx * p.XR * 16;
+  const size_t gb = (size_t)GB_KC * p.KR * 16, xb = (size_t)(stack ? 4 : 1) * kcx * p.XR * 16;
   size_t body = 2 * gb + 2 * xb;
   const size_t phantom = gb + (size_t)16 * p.KR * 16;  // address range the 16-chunk A descriptor of stage 1 spans
   if (body < phantom) body = phantom;
@@ -771,7 +849,7 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
   }
   // layer 2: weight + bias gradient (bias from the all-ones channel c1 of mid), then data gradient -> G1 (+ db1)
   {
-    const int rc = launch_wgrad(mid, G2, dw2, db2, B, Hi2, Wi2, 4, 4, c1, c2, c1, sms, s);
+    const int rc = launch_wgrad(mid, G2, dw2, db2, B, Hi2, Wi2, 4, 4, c1, c2, c1, 1, sms, s);
     if (rc != LPB_OK) return rc;
   }
   {
@@ -795,7 +873,7 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
   }
   // layer 1: weight gradient from the saved shuffled features, data gradient -> d features
   {
-    const int rc = launch_wgrad(static_cast<const __nv_bfloat16*>(saved_xs), G1, dw1, nullptr, B, Hi1, Wi1, 16, C4 / 8, C4, c1, -1, sms, s);
+    const int rc = launch_wgrad(static_cast<const __nv_bfloat16*>(saved_xs), G1, dw1, nullptr, B, Hi1, Wi1, 16, C4 / 8, C4, c1, -1, 0, sms, s);
     if (rc != LPB_OK) return rc;
   }
   if (dfeat) {
