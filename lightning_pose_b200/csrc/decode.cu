@@ -480,6 +480,8 @@ struct DecodeBwdParams {
   const float* tabW;
   float* gheat;
   const int* queue;      // optional {count, plane ids...}: dense fallback units of the window path
+  float lipw;            // max row sum of |horizontal taps|
+  float wabs[W];         // max over rows / phases of |vertical tap| per offset (window kernel's row pruning)
   long long n_planes;
   int h, w, pitch, padl, bulk;
   float T;
@@ -734,6 +736,29 @@ __global__ void __launch_bounds__(128) decode_bwd_window_kernel(const __grid_con
     }
   }
   __syncwarp();
+  // Tighten the row range.  The forward's box is "a candidate within R samples" (global Lipschitz bound); with the
+  // window in shared memory the decay of the taps can be used: for a fine pixel in coarse row a,
+  //   |field| <= lipW * sum_t wabs[t] * rowmax[a - R + t]      (rowmax over the window's columns = the strips' footprint)
+  // and rows whose bound is below M - CUT/T carry weight < exp(-CUT) of the peak.  Lane r owns window row r.
+  int ra0 = A0, ra1 = A1;
+  if (P.T > 0.f) {
+    float rmx = 0.f;
+#pragma unroll 8
+    for (int cc = 0; cc < DEC_WIN; ++cc) rmx = fmaxf(rmx, fabsf(tile[lane * DEC_WP + cc]));
+    float bnd = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2 * R + 1; ++t) {
+      const int src = lane - R + t;
+      const float v = __shfl_sync(0xffffffffu, rmx, src & 31);
+      if ((unsigned)src < (unsigned)DEC_WIN) bnd = fmaf(P.wabs[t], v, bnd);
+    }
+    const bool act = lane >= R && lane < R + nrows && bnd * P.lipw >= M - DEC_CUT / P.T;
+    const unsigned am = __ballot_sync(0xffffffffu, act);
+    if (am) {
+      ra0 = A0 + (__ffs(am) - 1 - R);
+      ra1 = A0 + (31 - __clz(am) - R);
+    }
+  }
   const float c = P.T * 1.4426950408889634f;
   const float kscale = P.T / S;
   const int J0 = B0 * F, J1 = (B1 + 1) * F;
@@ -741,8 +766,8 @@ __global__ void __launch_bounds__(128) decode_bwd_window_kernel(const __grid_con
   for (int sidx = 0; sidx < nstrips; ++sidx) {
     const int jf0 = J0 + sidx * 32;
     const int tcol0 = jf0 / F - B0;  // window column of coarse column jf0/F - R
-    decode_bwd_strip<DS, false>(P, tile, gt, DEC_WP, 0, tcol0, DEC_WIN - tcol0, jf0, J1, A0, A1 + 1, M, c, kscale, xhat, yhat, gx, gy,
-                                lane);
+    decode_bwd_strip<DS, false>(P, tile, gt, DEC_WP, ra0 - A0, tcol0, DEC_WIN - tcol0, jf0, J1, ra0, ra1 + 1, M, c, kscale, xhat, yhat, gx,
+                                gy, lane);
     __syncwarp();
   }
   float dot = 0.f;
@@ -838,6 +863,12 @@ static int launch_decode_bwd(const float* heat, const float* stats, const float*
   P.tabW = tw->win;
   P.gheat = gheat;
   P.queue = queue;
+  P.lipw = tw->host.lip;
+  for (int t = 0; t < G::W; ++t) {
+    float m = 0.f;
+    for (size_t i = 0; i < (size_t)h * G::F; ++i) m = std::fmax(m, std::fabs(th->host.win[i * G::W + t]));
+    P.wabs[t] = m * (1.0f + 1e-6f);
+  }
   P.n_planes = n_planes;
   P.h = h;
   P.w = w;
