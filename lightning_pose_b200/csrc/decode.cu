@@ -14,6 +14,7 @@
 // > exp(-40) relative to the peak (rigorous bound |field| <= lip * max|h| over the tap footprint).
 // Flat (fresh-init) planes fall through to the same code with the box = whole plane.
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/lpb200.h"
 #include "lpb_common.cuh"
@@ -38,6 +39,9 @@ struct DecodeParams {
   int h, w, pitch, padl, bulk;
   int64_t n_planes;
   float T, lip, offset;
+  const int* queue;   // CTA kernel, queue mode: {count, plane ids ...} left over by the warp-per-plane kernel
+  float lipw;         // max row sum of |horizontal taps|
+  float wabs[W];      // max over rows / phases of |vertical tap| per offset (row pruning in the warp kernel)
   float phase[F][W];  // interior rows (constant bank operands)
 };
 
@@ -124,7 +128,9 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
   __syncthreads();
 
   uint32_t tma_phase = 0;
-  for (size_t plane = blockIdx.x; plane < (size_t)P.n_planes; plane += gridDim.x) {
+  const size_t nwork = P.queue ? (size_t)P.queue[0] : (size_t)P.n_planes;
+  for (size_t work = blockIdx.x; work < nwork; work += gridDim.x) {
+  const size_t plane = P.queue ? (size_t)P.queue[1 + work] : work;
   const float* __restrict__ src = P.heat + plane * (size_t)h * w;
 
   // ---- stage the plane: TMA bulk row copies into the zero-padded tile -------------------------
@@ -464,6 +470,269 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
   }
   __syncthreads();  // every read of the tile / scratch is done before the next plane is staged
   }  // persistent plane loop
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-per-plane forward for planes whose mass sits in one small box (trained networks: all of them).
+// The CTA kernel above synchronises eight warps five times per plane and more than half of its stall samples
+// are at those barriers; here one warp owns a plane end to end and only warp-level primitives are used:
+//   pass 1  stream the plane (16-byte loads), arg max |h|
+//   window  32x32 coarse pixels around the arg max -> shared memory; m_lb = exact field on the arg max's F x F block
+//   pass 2  stream the plane again (L2), hull of the candidates |h| >= theta
+//   window  re-centred on the hull +- R; rows pruned with the tap-decay bound; separable evaluation of the strips
+//           with a per-lane online softmax; exact 5x5 confidence window
+// Planes whose hull does not fit a window (diffuse / multi-modal), NaN planes and T <= 0 are appended to a queue
+// and run by the CTA kernel in queue mode, so every plane produces the same outputs either way.
+constexpr int DECW_WIN = 32, DECW_WP = 33;
+
+template <int DS>
+__device__ float eval_point_win(const float* tile, int r0w, int c0w, const float* __restrict__ tabH,
+                                const float* __restrict__ tabW, int i, int j) {
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  const float* base = tile + (i / F - R - r0w) * DECW_WP + (j / F - R - c0w);
+  float acc = 0.f;
+#pragma unroll 1
+  for (int t = 0; t < W; ++t) {
+    const float* row = base + t * DECW_WP;
+    float r = 0.f;
+#pragma unroll
+    for (int u = 0; u < W; ++u) r = fmaf(__ldg(tabW + j * W + u), row[u], r);
+    acc = fmaf(__ldg(tabH + i * W + t), r, acc);
+  }
+  return acc;
+}
+
+template <int DS>
+__device__ __forceinline__ void load_window(float* tile, const float* __restrict__ src, int h, int w, int r0w, int c0w, int lane) {
+  const int x = c0w + lane;
+  const bool xin = x >= 0 && x < w;
+#pragma unroll 8
+  for (int r = 0; r < DECW_WIN; ++r) {
+    const int y = r0w + r;
+    tile[r * DECW_WP + lane] = (xin && y >= 0 && y < h) ? __ldg(src + (size_t)y * w + x) : 0.f;
+  }
+}
+
+template <int DS>
+__global__ void __launch_bounds__(128) decode_fwd_warp_kernel(const __grid_constant__ DecodeParams<DS> P, int* __restrict__ queue) {
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  __shared__ float tile_s[4][DECW_WIN * DECW_WP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long plane = (long long)blockIdx.x * 4 + warp;
+  if (plane >= P.n_planes) return;
+  const int h = P.h, w = P.w, w4 = w >> 2, n4 = h * w4;
+  const float* __restrict__ src = P.heat + (size_t)plane * h * w;
+  const float4* __restrict__ src4 = reinterpret_cast<const float4*>(src);
+  float* tile = tile_s[warp];
+  auto to_queue = [&]() {
+    if (lane == 0) queue[1 + atomicAdd(queue, 1)] = (int)plane;
+  };
+
+  // ---- pass 1: arg max of |h| ----------------------------------------------------------------------------
+  float best = -1.f;
+  int bidx = 0;
+#pragma unroll 8
+  for (int idx = lane; idx < n4; idx += 32) {
+    const float4 x = __ldg(src4 + idx);
+    const float m4 = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
+    if (m4 > best) {
+      best = m4;
+      bidx = idx;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ob > best || (ob == best && oi < bidx)) {
+      best = ob;
+      bidx = oi;
+    }
+  }
+  if (!(best >= 0.f) || !(P.T > 0.f)) {  // NaN plane or no temperature: the CTA kernel's full evaluation
+    to_queue();
+    return;
+  }
+  const int besta = bidx / w4;
+  int bestb = (bidx - besta * w4) * 4;
+  {
+    const float4 x = __ldg(src4 + bidx);
+    bestb += (fabsf(x.x) == best) ? 0 : ((fabsf(x.y) == best) ? 1 : ((fabsf(x.z) == best) ? 2 : 3));
+  }
+  // ---- lower bound of the field maximum: exact values on the arg max's F x F block ---------------------
+  int r0w = besta - DECW_WIN / 2, c0w = bestb - DECW_WIN / 2;
+  load_window<DS>(tile, src, h, w, r0w, c0w, lane);
+  __syncwarp();
+  float lb = -3.0e38f;
+  if (lane < F * F) lb = eval_point_win<DS>(tile, r0w, c0w, P.tabH, P.tabW, besta * F + lane / F, bestb * F + lane % F);
+  const float mlb = warp_max(lb);
+  const float thr = mlb - DEC_CUT / P.T;
+  const float theta = thr / P.lip;
+
+  // ---- pass 2: hull of the candidates (|h| >= theta), 4-column granularity like the CTA kernel -----------
+  int amin = h, amax = -1, bmin = w, bmax = -1;
+  {
+    int a = 0, g = lane;  // idx = a * w4 + g
+    while (g >= w4) {
+      g -= w4;
+      ++a;
+    }
+#pragma unroll 4
+    for (int idx = lane; idx < n4; idx += 32) {
+      const float4 x = __ldg(src4 + idx);
+      const bool c = (fabsf(x.x) >= theta) || (fabsf(x.y) >= theta) || (fabsf(x.z) >= theta) || (fabsf(x.w) >= theta);
+      if (c) {
+        amin = min(amin, a);
+        amax = max(amax, a);
+        bmin = min(bmin, 4 * g);
+        bmax = max(bmax, min(4 * g + 3, w - 1));
+      }
+      g += 32;
+      while (g >= w4) {
+        g -= w4;
+        ++a;
+      }
+    }
+  }
+  amin = warp_min_i(amin);
+  amax = warp_max_i(amax);
+  bmin = warp_min_i(bmin);
+  bmax = warp_max_i(bmax);
+  const int A0 = max(amin - R, 0), A1 = min(amax + R, h - 1);
+  const int B0 = max(bmin - R, 0), B1 = min(bmax + R, w - 1);
+  const int nrows = A1 - A0 + 1, ncols = B1 - B0 + 1;
+  // one spare row / column on each side: the confidence window may step one coarse pixel outside the box
+  if (amax < 0 || nrows > DECW_WIN - 2 * R - 2 || ncols > DECW_WIN - 2 * R - 2) {
+    to_queue();
+    return;
+  }
+  r0w = A0 - R - 1;
+  c0w = B0 - R - 1;
+  __syncwarp();
+  load_window<DS>(tile, src, h, w, r0w, c0w, lane);
+  __syncwarp();
+
+  // ---- rows that can carry weight (tap-decay bound, see decode_bwd_window_kernel); lane r owns window row r ----
+  int ra0 = A0, ra1 = A1;
+  {
+    float rmx = 0.f;
+#pragma unroll 8
+    for (int cc = 0; cc < DECW_WIN; ++cc) rmx = fmaxf(rmx, fabsf(tile[lane * DECW_WP + cc]));
+    float bnd = 0.f;
+#pragma unroll
+    for (int t = 0; t < W; ++t) {
+      const int sl = lane - R + t;
+      const float v = __shfl_sync(0xffffffffu, rmx, sl & 31);
+      if ((unsigned)sl < (unsigned)DECW_WIN) bnd = fmaf(P.wabs[t], v, bnd);
+    }
+    const int arow = r0w + lane;  // coarse row of window row `lane`
+    const unsigned am = __ballot_sync(0xffffffffu, arow >= A0 && arow <= A1 && bnd * P.lipw >= thr);
+    if (am) {
+      ra0 = r0w + (__ffs(am) - 1);
+      ra1 = r0w + (31 - __clz(am));
+    }
+  }
+
+  // ---- strips of 32 fine columns over rows [ra0, ra1]: separable evaluation + per-lane online softmax -------
+  const float c = P.T * 1.4426950408889634f;
+  float M = mlb, S = 0.f, SX = 0.f, SY = 0.f;
+  const int J0 = B0 * F, J1 = (B1 + 1) * F;
+  for (int jf0 = J0; jf0 < J1; jf0 += 32) {
+    const int jf = jf0 + lane;
+    const bool ok = jf < J1;
+    const int jc = ok ? jf : (J1 - 1);
+    float wc[W];
+#pragma unroll
+    for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
+    const float* colbase = tile + (jc / F - R - c0w);  // add (a - R - r0w + t) * WP for coarse row a - R + t
+    const int tr0 = ra0 - R - r0w;
+    float tmp[W + 1];
+#pragma unroll
+    for (int t = 0; t < W; ++t) tmp[t] = dot_w<W>(colbase + (tr0 + t) * DECW_WP, wc);
+    float m = M, mc = M * c, s_it = 0.f, sy_it = 0.f;
+    const float kill = ok ? 0.f : -3.0e38f;
+    auto accumulate = [&](const float* v, float yrow) {
+      float vm = v[0];
+#pragma unroll
+      for (int p = 1; p < F; ++p) vm = fmaxf(vm, v[p]);
+      vm += kill;
+      if (__any_sync(0xffffffffu, vm > m)) {
+        const float mn = fmaxf(m, vm);
+        const float sc = fast_exp2((m - mn) * c);
+        s_it *= sc;
+        sy_it *= sc;
+        m = mn;
+        mc = mn * c;
+      }
+      float rs = 0.f, pw = 0.f;
+#pragma unroll
+      for (int p = 0; p < F; ++p) {
+        const float e = fast_exp2(fmaf(v[p], c, -mc) + kill);
+        rs += e;
+        if (p > 0) pw = fmaf(e, (float)p, pw);
+      }
+      s_it += rs;
+      sy_it = fmaf(yrow, rs, sy_it) + pw;
+    };
+    float yrow = (float)(ra0 * F);
+    for (int a = ra0; a <= ra1; ++a, yrow += (float)F) {
+      float v[F];
+      column_pass<DS>(P, a, h, tmp, v);
+      accumulate(v, yrow);
+      if (a < ra1) {
+#pragma unroll
+        for (int t = 0; t < W - 1; ++t) tmp[t] = tmp[t + 1];
+        tmp[W - 1] = dot_w<W>(colbase + (tr0 + (a - ra0) + 1 + 2 * R) * DECW_WP, wc);
+      }
+    }
+    {
+      const float Mn = fmaxf(M, m);
+      const float a1 = fast_exp2((M - Mn) * c), a2 = fast_exp2((m - Mn) * c);
+      S = fmaf(s_it, a2, S * a1);
+      SX = fmaf((float)jf * s_it, a2, SX * a1);
+      SY = fmaf(sy_it, a2, SY * a1);
+      M = Mn;
+    }
+  }
+  {
+    const float Mw = warp_max(M);
+    const float sc = fast_exp2((M - Mw) * c);
+    S = warp_sum(S * sc);
+    SX = warp_sum(SX * sc);
+    SY = warp_sum(SY * sc);
+    M = Mw;
+  }
+  const float xhat = SX / S, yhat = SY / S;
+
+  // ---- confidence: softmax mass of the (2r+1)^2 window around (trunc y, trunc x) -----------------
+  constexpr int CW = 2 * DEC_CONF_R + 1;
+  float cw = 0.f;
+  if (lane < CW * CW) {
+    const int i = (int)yhat + lane / CW - DEC_CONF_R;
+    const int j = (int)xhat + lane % CW - DEC_CONF_R;
+    const int tr = i / F - R - r0w, tc = j / F - R - c0w;  // footprint inside the window by construction; guard anyway
+    if (i >= 0 && i < h * F && j >= 0 && j < w * F && tr >= 0 && tr + W <= DECW_WIN && tc >= 0 && tc + W <= DECW_WIN) {
+      const float v = eval_point_win<DS>(tile, r0w, c0w, P.tabH, P.tabW, i, j);
+      cw = fast_exp2((v - M) * c) / S;
+    }
+  }
+  cw = warp_sum(cw);
+  if (lane == 0) {
+    P.xy[2 * plane + 0] = xhat - P.offset;
+    P.xy[2 * plane + 1] = yhat - P.offset;
+    P.conf[plane] = cw;
+    if (P.stats) {
+      float* st = P.stats + 8 * plane;
+      st[0] = M;
+      st[1] = S;
+      st[2] = xhat;
+      st[3] = yhat;
+      st[4] = (float)A0;
+      st[5] = (float)A1;
+      st[6] = (float)B0;
+      st[7] = (float)B1;
+    }
+  }
 }
 
 // d loss / d h = U_H^T G U_W with G[i,j] = T * p[i,j] * ((j - xhat) gx + (i - yhat) gy), p the
@@ -842,7 +1111,25 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
   LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   LPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_fwd_kernel<DS>, DEC_THREADS, smem));
   const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);  // persistent CTAs: one wave
-  decode_fwd_kernel<DS><<<(unsigned)(n_planes < resident ? n_planes : resident), DEC_THREADS, smem, stream>>>(P);
+  P.queue = nullptr;
+  P.lipw = tw->host.lip;
+  for (int t = 0; t < G::W; ++t) {
+    float m = 0.f;
+    for (size_t i = 0; i < (size_t)h * G::F; ++i) m = std::fmax(m, std::fabs(th->host.win[i * G::W + t]));
+    P.wabs[t] = m * (1.0f + 1e-6f);
+  }
+  if (P.bulk && getenv("LPB_DECODE_CTA_ONLY") == nullptr) {
+    // warp-per-plane first; what it cannot take (diffuse / multi-modal / NaN planes) is queued for the CTA kernel
+    int* queue = nullptr;
+    LPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&queue), sizeof(int) * (size_t)(n_planes + 1), stream));
+    LPB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int), stream));
+    decode_fwd_warp_kernel<DS><<<(unsigned)((n_planes + 3) / 4), 128, 0, stream>>>(P, queue);
+    P.queue = queue;
+    decode_fwd_kernel<DS><<<(unsigned)(n_planes < resident ? n_planes : resident), DEC_THREADS, smem, stream>>>(P);
+    LPB_CUDA(cudaFreeAsync(queue, stream));
+  } else {
+    decode_fwd_kernel<DS><<<(unsigned)(n_planes < resident ? n_planes : resident), DEC_THREADS, smem, stream>>>(P);
+  }
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
 }
