@@ -177,7 +177,7 @@ class HotPath:
         self.teps = torch.full((K_PTS,), 20.0, device=device)
         self.w_unsup = 1.0 / (2.0 * np.exp(5.0))
         if not fwd_only:
-            self.opt = torch.optim.Adam(self.head.parameters(), lr=1e-5, fused=True)
+            self.opt = torch.optim.Adam(self.head.parameters(), lr=1e-5, fused=True, capturable=True)
             self.reducer = FlatGradAllReducer(self.head.parameters(), n_scalars=4) if world > 1 else None
 
     def step(self, feats: torch.Tensor):
@@ -207,6 +207,29 @@ class HotPath:
                 return return_scalars
             self.opt.step()
         return torch.stack(scalars)
+
+
+class GraphedStep:
+    """The whole training step (forward, backward, all-reduce, Adam) captured once into a CUDA graph and replayed:
+    the step is ~60 short launches, so launch latency is a visible share of it.  The input tensor is static (the
+    resident feature buffer); the returned scalars live in the graph's pool."""
+
+    def __init__(self, hp: "HotPath", feats: torch.Tensor):
+        self.feats = feats
+        side = torch.cuda.Stream(device=feats.device)
+        side.wait_stream(torch.cuda.current_stream(feats.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                hp.step(feats)
+        torch.cuda.current_stream(feats.device).wait_stream(side)
+        torch.cuda.synchronize(feats.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = hp.step(feats)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out
 
 
 def time_steps(fn, steps, warmup, barrier=None):
@@ -272,8 +295,18 @@ def run_ours(args):
     n_frames = feats.shape[0]
     barrier = (lambda: dist.barrier()) if dist else None
 
+    step_fn = lambda: hp.step(feats)
+    graphed = False
+    if not args.no_graph:
+        try:
+            step_fn = GraphedStep(hp, feats)
+            graphed = True
+        except Exception as exc:  # a failed capture leaves the process in an undefined state: start over without it
+            sys.stderr.write(f"bench: CUDA-graph capture failed ({type(exc).__name__}: {exc}); re-running with --no-graph\n")
+            sys.stderr.flush()
+            os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
     with ClockSampler(local) as clk:
-        ms = time_steps(lambda: hp.step(feats), args.steps, args.warmup, barrier)
+        ms = time_steps(step_fn, args.steps, args.warmup, barrier)
     t = torch.tensor([ms], device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -371,6 +404,7 @@ def run_ours(args):
             "backward": "all native: loss stack, remap, sparse soft-argmax windows, target+mse, fused softmax-backward/G2 front end, tcgen05 dgrad+wgrad of both transposed convolutions; torch library: fused Adam on the head parameters",
             "frames_per_step_per_gpu": n_frames, "regime": ("trained-like synthetic response (unimodal Gaussian-like heatmaps; planted features + bilinear per-keypoint deconvs, see bench.make_problem); fresh_init_regime = reference initialiser"
                                                                                   if args.regime == "trained" else "fresh init (reference initialiser, flat heatmaps)"),
+            "launch": "whole step replayed from one CUDA graph" if graphed else "eager launches",
             "l2_policy": f"inputs larger than L2 ({feats.numel() * esz / 2**20:.0f} MiB of features per step)", "parallelism": f"dp{world}",
         },
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": feats.numel() * esz, "d2h_bytes_per_step": 16},
@@ -484,6 +518,7 @@ def main():
     ap.add_argument("--no-flat", action="store_true", help="skip the secondary fresh-init (flat heatmap) regime")
     ap.add_argument("--fwd-only", action="store_true", help="time the forward pass only (default: full training step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
