@@ -369,7 +369,8 @@ def run_ours(args):
     fwd_only_value = None
     if not args.fwd_only:
         hp_fwd = HotPath(prob, dev, True)
-        ms_f = time_steps(lambda: hp_fwd.step(feats), args.steps, 2)
+        fwd_fn = GraphedStep(hp_fwd, feats) if graphed else (lambda: hp_fwd.step(feats))
+        ms_f = time_steps(fwd_fn, args.steps, 2)
         fwd_only_value = {"value": n_frames * args.steps / (ms_f / 1e3), "unit": "frames/s", "ms_per_step": ms_f / args.steps}
     flat = None
     if not args.no_flat:

@@ -313,12 +313,9 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
       for (int t = 0; t < g.tiles; ++t) {
         float d[HB_NCOLS];
 #pragma unroll
-        for (int cc = 0; cc < HB_NCOLS / 16; ++cc) {
-          float v[16];
-          tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + t * HB_NCOLS + cc * 16, v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) d[cc * 16 + i] = v[i];
-        }
+        for (int cc = 0; cc < HB_NCOLS / 16; ++cc)
+          tc::tmem_ld16_async(tmem_base + ((uint32_t)(32 * q) << 16) + t * HB_NCOLS + cc * 16, &d[cc * 16]);
+        tc::tmem_ld_wait();
         const int row = t * 128 + 32 * q + lane;
         const int m = row / g.P, n = row - m * g.P;
         if (m < g.Hi && n < g.Wi) {
@@ -507,12 +504,9 @@ __global__ void __launch_bounds__(K1B_THREADS, 2) k1b_convt_softmax_kernel(const
             // aligned: read [32e, 32e+48) and pick with compile-time register indices
             float d[48];
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-              float v[16];
-              tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + tt * HB_NCOLS + 32 * e + cc * 16, v);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) d[cc * 16 + i] = v[i];
-            }
+            for (int cc = 0; cc < 3; ++cc)
+              tc::tmem_ld16_async(tmem_base + ((uint32_t)(32 * q) << 16) + tt * HB_NCOLS + 32 * e + cc * 16, &d[cc * 16]);
+            tc::tmem_ld_wait();
             const int row = t * 128 + 32 * q + lane;
             const int ml = row / g.P, n = row - ml * g.P;
             const bool valid = (ml < P.Hh) && (n < Wi);

@@ -376,12 +376,8 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
         for (int t = 0; t < B2D_TILES; ++t) {
           float d[32];
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            float v[16];
-            tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + t * 32 + cc * 16, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) d[cc * 16 + i] = v[i];
-          }
+          for (int cc = 0; cc < 2; ++cc) tc::tmem_ld16_async(tmem_base + ((uint32_t)(32 * q) << 16) + t * 32 + cc * 16, &d[cc * 16]);
+          tc::tmem_ld_wait();
           const int row = t * 128 + 32 * q + lane;
           const int ml = row / Pp, n = row - ml * Pp;
           if (ml < nrow && n < Wi) {
@@ -544,12 +540,9 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
 #pragma unroll
           for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-              float t16[16];
-              tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (ml + 2 * r) * Pp + 16 * k, t16);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[r][16 * k + i] = t16[i];
-            }
+            for (int k = 0; k < NCH; ++k)
+              tc::tmem_ld16_async(tmem_base + ((uint32_t)(32 * q) << 16) + (ml + 2 * r) * Pp + 16 * k, &v[r][16 * k]);
+          tc::tmem_ld_wait();
           const int i0 = (hf * Hh) / 2 + 2 * ip;  // first feature row of the pair
 #pragma unroll
           for (int dj = 0; dj < 2; ++dj) {

@@ -11,5 +11,5 @@ if ! grep -q " passed" gpurun_out/pytest_gpu.log || grep -q "failed" gpurun_out/
 echo "== bench train"; timeout 400 python bench.py --steps 10 --warmup 3 ${BENCH_ARGS:-} 2>&1 | tail -3 | tee gpurun_out/bench.log
 if [[ "${QUICK:-0}" == "1" ]]; then exit 0; fi
 echo "== ncu launch list (train step)"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_train.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-flat > gpurun_out/ncu_list_train.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_train.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-flat --no-graph > gpurun_out/ncu_list_train.log 2>&1
 tail -1 gpurun_out/ncu_list_train.log | cut -c1-200
