@@ -25,6 +25,7 @@ namespace lpb {
 constexpr int DEC_THREADS = 256;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr float DEC_CUT = 40.0f;  // dropped pixels have weight < exp(-40) = 4e-18 of the peak pixel
+constexpr int DEC_MAX_PARTS = 8;  // CTAs a queued (dense) plane can be split over
 constexpr int DEC_CONF_R = 2;     // floor(1.25 * 2), lightning_pose/data/heatmaps.py:111
 
 template <int DS>
@@ -40,6 +41,8 @@ struct DecodeParams {
   int64_t n_planes;
   float T, lip, offset;
   const int* queue;   // CTA kernel, queue mode: {count, plane ids ...} left over by the warp-per-plane kernel
+  int* qcounter;      // [n_planes] arrival counters (zeroed) and
+  float* qscratch;    // [n_planes][DEC_MAX_PARTS][4] partial softmax states of a plane split over several CTAs
   float lipw;         // max row sum of |horizontal taps|
   float wabs[W];      // max over rows / phases of |vertical tap| per offset (row pruning in the warp kernel)
   float phase[F][W];  // interior rows (constant bank operands)
@@ -99,7 +102,7 @@ __device__ __forceinline__ void column_pass(const DecodeParams<DS>& P, int a, in
 }
 
 template <int DS>
-__global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_constant__ DecodeParams<DS> P) {
+__global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kernel(const __grid_constant__ DecodeParams<DS> P) {
   constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
   constexpr int CPS = 32 / F;  // coarse columns per 32-fine-column strip
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -128,9 +131,15 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
   __syncthreads();
 
   uint32_t tma_phase = 0;
-  const size_t nwork = P.queue ? (size_t)P.queue[0] : (size_t)P.n_planes;
+  // queue mode: the few planes the warp kernel left over are each split over NP CTAs (their work items are dealt
+  // round-robin; partial softmax states meet in global scratch, the last CTA to arrive merges and finishes)
+  const int qcount = P.queue ? P.queue[0] : 0;
+  const int NP = (P.queue && qcount > 0) ? min(DEC_MAX_PARTS, max(1, (int)gridDim.x / qcount)) : 1;
+  const size_t nwork = P.queue ? (size_t)qcount * NP : (size_t)P.n_planes;
   for (size_t work = blockIdx.x; work < nwork; work += gridDim.x) {
-  const size_t plane = P.queue ? (size_t)P.queue[1 + work] : work;
+  const size_t slot = work / NP;
+  const int part = (int)(work - slot * NP);
+  const size_t plane = P.queue ? (size_t)P.queue[1 + slot] : work;
   const float* __restrict__ src = P.heat + plane * (size_t)h * w;
 
   // ---- stage the plane: TMA bulk row copies into the zero-padded tile -------------------------
@@ -324,7 +333,9 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
   const float c = P.T * 1.4426950408889634f;
   float M = mlb, S = 0.f, SX = 0.f, SY = 0.f;
 
-  for (int item = warp; item < nitems; item += DEC_WARPS) {
+  for (int itw = warp;; itw += DEC_WARPS) {
+    const int item = itw * NP + part;
+    if (item >= nitems) break;
     const unsigned own = __ballot_sync(0xffffffffu, item >= istart && item < istart + nmine);
     const int sl = __ffs(own) - 1;  // strip index
     unsigned rm = __shfl_sync(0xffffffffu, my_mask, sl);
@@ -438,6 +449,36 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
     SX = fmaf(red[16 + 4 * k + 2], sc, SX);
     SY = fmaf(red[16 + 4 * k + 3], sc, SY);
   }
+  bool finisher = true;
+  if (NP > 1) {  // cross-CTA merge of the parts of this plane
+    float* part_state = P.qscratch + (slot * DEC_MAX_PARTS + part) * 4;
+    if (tid == 0) {
+      part_state[0] = M;
+      part_state[1] = S;
+      part_state[2] = SX;
+      part_state[3] = SY;
+      __threadfence();
+      redi[0] = atomicAdd(P.qcounter + slot, 1);
+    }
+    __syncthreads();
+    finisher = redi[0] == NP - 1;
+    if (finisher) {
+      __threadfence();
+      const volatile float* ps = P.qscratch + slot * DEC_MAX_PARTS * 4;
+      M = ps[0];
+      for (int k = 1; k < NP; ++k) M = fmaxf(M, ps[4 * k]);
+      S = 0.f;
+      SX = 0.f;
+      SY = 0.f;
+      for (int k = 0; k < NP; ++k) {
+        const float sc = fast_exp2((ps[4 * k] - M) * c);
+        S = fmaf(ps[4 * k + 1], sc, S);
+        SX = fmaf(ps[4 * k + 2], sc, SX);
+        SY = fmaf(ps[4 * k + 3], sc, SY);
+      }
+    }
+  }
+  if (finisher) {
   const float xhat = SX / S, yhat = SY / S;
 
   // ---- confidence: softmax mass of the (2r+1)^2 window around (trunc y, trunc x) -----------------
@@ -468,6 +509,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_fwd_kernel(const __grid_co
       st[7] = (float)B1;
     }
   }
+  }  // finisher
   __syncthreads();  // every read of the tile / scratch is done before the next plane is staged
   }  // persistent plane loop
 }
@@ -1112,6 +1154,8 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
   LPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_fwd_kernel<DS>, DEC_THREADS, smem));
   const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);  // persistent CTAs: one wave
   P.queue = nullptr;
+  P.qcounter = nullptr;
+  P.qscratch = nullptr;
   P.lipw = tw->host.lip;
   for (int t = 0; t < G::W; ++t) {
     float m = 0.f;
@@ -1120,11 +1164,14 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
   }
   if (P.bulk && getenv("LPB_DECODE_CTA_ONLY") == nullptr) {
     // warp-per-plane first; what it cannot take (diffuse / multi-modal / NaN planes) is queued for the CTA kernel
-    int* queue = nullptr;
-    LPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&queue), sizeof(int) * (size_t)(n_planes + 1), stream));
-    LPB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int), stream));
+    int* queue = nullptr;  // [1 + n queue][n counters][n * 8 * 4 floats of partial states]
+    const size_t qints = (size_t)(2 * n_planes + 1) + (size_t)n_planes * DEC_MAX_PARTS * 4;
+    LPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&queue), sizeof(int) * qints, stream));
+    LPB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int) * (size_t)(2 * n_planes + 1), stream));
     decode_fwd_warp_kernel<DS><<<(unsigned)((n_planes + 3) / 4), 128, 0, stream>>>(P, queue);
     P.queue = queue;
+    P.qcounter = queue + 1 + n_planes;
+    P.qscratch = reinterpret_cast<float*>(queue + 1 + 2 * n_planes);
     decode_fwd_kernel<DS><<<(unsigned)(n_planes < resident ? n_planes : resident), DEC_THREADS, smem, stream>>>(P);
     LPB_CUDA(cudaFreeAsync(queue, stream));
   } else {
