@@ -74,3 +74,53 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), f"{f} references the oracle"
+
+
+def header_prototypes():
+    """name -> number of parameters, parsed from the (comment-stripped) header."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(lpb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_ctypes_table_matches_header_arity():
+    """Every ctypes signature has exactly as many arguments as the C prototype it binds."""
+    from lightning_pose_b200 import _lib
+
+    protos = header_prototypes()
+    assert sorted(protos) == header_symbols()
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert len(argtypes) == protos[name], f"{name}: ctypes has {len(argtypes)} arguments, header has {protos[name]}"
+
+
+def test_head_training_entry_points_validate_without_gpu():
+    """The backward-side ABI (sizes, null checks) is callable without a GPU; nothing computes."""
+    from lightning_pose_b200 import _lib
+
+    n = ctypes.c_size_t(0)
+    # saved shuffled features: B x (C/32) K-chunks x padded rows x 16 bytes (row layout: (2H)(2W+1) + 2(2W+2) rows, /8 up)
+    assert _lib.lib.lpb_head_bf16_saved_bytes(3, 2048, 12, 12, ctypes.byref(n)) == 0
+    rows = (24 * 25 + 2 * 26 + 7) // 8 * 8
+    assert n.value == 3 * 64 * rows * 16
+    assert _lib.lib.lpb_head_bwd_bf16_workspace_bytes(3, 2048, 12, 12, 17, 17, ctypes.byref(n)) == 0
+    rows2 = (48 * 49 + 2 * 50 + 7) // 8 * 8
+    assert n.value >= 3 * 10 * (rows + rows2) * 16
+    rc = _lib.lib.lpb_head_bwd_bf16(None, None, None, None, None, None, None, 1, 2048, 12, 12, None, 17, None, 17,
+                                    None, None, None, None, None, None, None)
+    assert rc == -1 and b"null pointer" in _lib.lib.lpb_last_error()
+    rc = _lib.lib.lpb_decode_bwd_windows(None, None, None, 1, 8, 8, 2, 1000.0, None, None, None, None, None)
+    assert rc == -1 and b"null pointer" in _lib.lib.lpb_last_error()
+
+
+def test_fused_head_node_refuses_cpu_tensors():
+    from lightning_pose_b200.models.heads.heatmap import HeatmapHead
+
+    head = HeatmapHead("resnet50", 64, 5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        head.forward_with_keypoints(torch.rand(1, 64, 2, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        head.forward_with_keypoints(torch.rand(1, 64, 2, 2).bfloat16())
