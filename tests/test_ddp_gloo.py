@@ -55,3 +55,27 @@ def test_flat_allreduce_two_ranks_gloo():
         out = m.dict()
         mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _teardown_worker(rank, world, port, out):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out[rank] = True  # reached the end of the "run"; _teardown never returns (os._exit(0) without destructors)
+    bench._teardown(dist, rank, world)
+    out[rank] = False
+
+
+@pytest.mark.timeout(120)
+def test_bench_teardown_two_ranks_gloo():
+    """bench.py's end-of-run rendezvous (store counter, rank 0 leaves last, exit code 0 on every rank): the multi-rank
+    run must end cleanly without destroying the process group under the captured CUDA graph."""
+    world = 2
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_teardown_worker, args=(world, _free_port(), out), nprocs=world, join=True)  # raises on a non-zero exit
+        assert dict(out) == {0: True, 1: True}
