@@ -154,3 +154,66 @@ def test_losses_golden(golden):
         {"heatmap_mse": (O.heatmap_mse_loss(targ, pred), 0.0),
          "temporal": (O.temporal_loss(T(g["temporal2_in_kp"]), T(g["temporal2_in_conf"]), 20.0, 0.05), 5.0)}, 0.3)
     close(tot, g["factory_out_total"])
+
+
+# ---- more of the reference's own numerical unit tests, restated as known answers for the oracle ---------------
+def test_kat_confidence_window_exact_sums():
+    """tests/data/test_heatmaps.py:457-563: the window sum is the exact sum of the (2r+1)^2 patch around
+    (trunc y, trunc x), r = floor(1.25 * 2) = 2, zero beyond the plane's border."""
+    p = torch.zeros(1, 2, 12, 12)
+    p[0, 0, 5, 6] = 0.25
+    p[0, 0, 7, 8] = 0.5      # inside the 5x5 window centred on (y=5, x=6): rows 3..7, cols 4..8
+    p[0, 0, 8, 6] = 0.125    # row 8: outside
+    p[0, 1, 0, 0] = 0.75     # corner: window reaches beyond the plane, missing part counts as zero
+    p[0, 1, 2, 2] = 0.0625
+    p[0, 1, 3, 0] = 1.0      # row 3: outside the window centred on (0, 0)
+    locs = torch.tensor([[[6.9, 5.2], [0.4, 0.9]]])  # (x, y); trunc -> (6, 5) and (0, 0)
+    close(O.confidence_window_sum(p, locs), [[0.75, 0.8125]])
+
+
+def test_kat_heatmap_losses_zero_at_equality_and_monotone():
+    """tests/losses/test_losses.py:137-217, :449-480: MSE / KL / JS vanish for identical heatmaps and grow as the
+    prediction is rolled away from the target."""
+    g = torch.Generator().manual_seed(0)
+    targ = O.gaussian_targets(torch.rand(3, 4, 2, generator=g) * 40 + 12, 64, 64, (32, 32))
+    for fn in (O.heatmap_mse_loss, O.heatmap_kl_loss, O.heatmap_js_loss):
+        assert abs(float(fn(targ, targ.clone()))) < 1e-6
+        vals = [float(fn(targ, torch.roll(targ, s, dims=-1))) for s in (1, 2, 4)]
+        assert vals[0] > 1e-6 and vals[0] < vals[1] < vals[2]
+
+
+def test_kat_temporal_per_keypoint_epsilon():
+    """tests/losses/test_losses.py:343-392: analytic values with a scalar and with a per-keypoint epsilon."""
+    kp = torch.zeros(3, 4)          # T=3 frames, K=2 keypoints
+    kp[1] = torch.tensor([3.0, 4.0, 0.0, 0.0])   # keypoint 0 moves by 5 then by 5 back; keypoint 1 rests
+    close(O.temporal_loss(kp), 2.5)                                   # mean(5, 0, 5, 0)
+    close(O.temporal_loss(kp, epsilon=1.0), 2.0)                      # mean(4, 0, 4, 0)
+    close(O.temporal_loss(kp, epsilon=[4.0, 0.0]), 0.5)               # mean(1, 0, 1, 0)
+    conf = torch.tensor([[0.9, 0.9], [0.01, 0.9], [0.9, 0.9]])        # frame 1 of keypoint 0 is low confidence
+    close(O.temporal_loss(kp, conf, epsilon=0.0, prob_threshold=0.05), 0.0)  # both of its differences are masked
+
+
+def test_kat_pca_zero_inside_subspace_and_positive_outside():
+    """tests/losses/test_losses.py:289-311: points inside the kept subspace reproject onto themselves (loss 0);
+    moving along a discarded direction gives the distance, rectified by epsilon."""
+    g = torch.Generator().manual_seed(1)
+    q, _ = torch.linalg.qr(torch.randn(6, 6, generator=g))
+    kept, disc = q[:2], q[2:]
+    mean = torch.randn(6, generator=g)
+    inside = mean[None] + torch.randn(5, 2, generator=g) @ kept
+    close(O.pca_loss(inside, mean, kept, 0.0), 0.0, atol=1e-6)
+    off = inside + 2.0 * disc[0][None]
+    err = O.pca_reprojection_error(off, mean, kept)                    # (N, 3): norm of the residual per (x, y) pair
+    close((err**2).sum(1), torch.full((5,), 4.0), atol=1e-5)           # the residual is exactly 2 * disc[0]
+    assert float(O.pca_loss(off, mean, kept, 0.0)) > float(O.pca_loss(off, mean, kept, 0.5)) > 0.0
+    close(O.pca_loss(off, mean, kept, 10.0), 0.0)
+
+
+def test_kat_factory_anneal_exemption():
+    """tests/losses/test_factory.py:213-263: the anneal weight multiplies every loss except heatmap_{mse,kl,js}."""
+    one = torch.tensor(1.0)
+    losses = {"heatmap_mse": (one, 0.0), "temporal": (one, 0.0), "pca_singleview": (2 * one, np.log(2.0))}
+    w = O.loss_weight(0.0)  # 1 / (2 * exp(0)) = 0.5
+    close(O.combine_losses(losses, 1.0), w + w + 2 * O.loss_weight(np.log(2.0)))
+    close(O.combine_losses(losses, 0.0), w)           # only the heatmap loss survives anneal_weight = 0
+    close(O.combine_losses(losses, 0.25), w + 0.25 * (w + 2 * O.loss_weight(np.log(2.0))))
