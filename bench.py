@@ -89,7 +89,8 @@ def _inverse_pixel_shuffle(xs: torch.Tensor) -> torch.Tensor:
 
 
 def make_problem(n_clips: int, seed: int, device, regime: str = "trained"):
-    """Seeded synthetic inputs of BASELINE configs[1] (no datasets / checkpoints are reachable).
+    """Seeded synthetic inputs of BASELINE configs[1] (no datasets / checkpoints are reachable).  Plain tensors only:
+    both arms (ours, the reference on the CPU) build their own head from ``head_params``.
 
     regime "trained": what the semi-supervised phase of training sees - unimodal, Gaussian-like heatmaps
       (peak ~0.1, sigma ~1.25 heatmap px, cf. SURVEY 8(d) "peaked").  Built by construction, since the head is
@@ -98,14 +99,15 @@ def make_problem(n_clips: int, seed: int, device, regime: str = "trained"):
     regime "fresh": the reference's own initialiser (xavier-uniform gain 0.01, zero bias) on randn*0.5 features
       -> flat heatmaps, for which the soft-argmax has to evaluate the whole 384x384 field.
     """
-    from lightning_pose_b200.models.heads.heatmap import HeatmapHead
-
     g = torch.Generator().manual_seed(seed)
     n_lab, n_unl = n_clips * B_LABELED, n_clips * T_UNLABELED
     n_frames = n_lab + n_unl
     torch.manual_seed(seed)
-    head = HeatmapHead("resnet50", FEAT_C, K_PTS)  # reference initialiser
     c4, hs = FEAT_C // 4, 2 * FEAT_HW
+    # reference initialiser (models/heads/heatmap.py:74-83): xavier-uniform gain 0.01, zero bias
+    w1 = torch.nn.init.xavier_uniform_(torch.empty(c4, K_PTS, 3, 3), gain=0.01)
+    w2 = torch.nn.init.xavier_uniform_(torch.empty(K_PTS, K_PTS, 3, 3), gain=0.01)
+    b1, b2 = torch.zeros(K_PTS), torch.zeros(K_PTS)
     # keypoints in heatmap pixels: labeled uniform, unlabeled = per-clip random walk
     kp_hm = torch.empty(n_frames, K_PTS, 2)
     kp_hm[:n_lab] = torch.rand(n_lab, K_PTS, 2, generator=g) * 80 + 8
@@ -115,14 +117,10 @@ def make_problem(n_clips: int, seed: int, device, regime: str = "trained"):
     if regime == "trained":
         tri = torch.tensor([[0.25, 0.5, 0.25], [0.5, 1.0, 0.5], [0.25, 0.5, 0.25]])
         group = torch.arange(c4) % K_PTS
-        with torch.no_grad():
-            d1, d2 = list(head.upsampling_layers)[1:]
-            w1 = torch.randn(d1.weight.shape, generator=g) * 1e-3
-            w1[torch.arange(c4), group] += tri / (c4 // K_PTS)
-            w2 = torch.randn(d2.weight.shape, generator=g) * 1e-3
-            w2[torch.arange(K_PTS), torch.arange(K_PTS)] += tri
-            d1.weight.copy_(w1)
-            d2.weight.copy_(w2)
+        w1 = torch.randn(w1.shape, generator=g) * 1e-3
+        w1[torch.arange(c4), group] += tri / (c4 // K_PTS)
+        w2 = torch.randn(w2.shape, generator=g) * 1e-3
+        w2[torch.arange(K_PTS), torch.arange(K_PTS)] += tri
         centre = torch.arange(hs, dtype=torch.float32) * 4 + 1.5  # heatmap position of a shuffled pixel
         for i in range(0, n_frames, 64):  # bounded temp memory
             kp = kp_hm[i : i + 64]
@@ -147,28 +145,38 @@ def make_problem(n_clips: int, seed: int, device, regime: str = "trained"):
     mean = lat.mean(0)
     _, _, vt = torch.linalg.svd(lat - mean, full_matrices=False)
     pca = {"mean": mean, "kept": vt[:6].contiguous(), "eps": 5.0}
-    return {"head": head, "feats": feats, "kp_lab": kp_lab, "vis": vis, "tf": tf, "bbox": bbox, "pca": pca, "n_clips": n_clips}
+    return {"head_params": (w1, b1, w2, b2), "feats": feats, "kp_lab": kp_lab, "vis": vis, "tf": tf, "bbox": bbox, "pca": pca, "n_clips": n_clips}
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+BACKBONE_PARAMS = 23_508_032  # ResNet-50 trunk (94.4 MB of fp32 gradients per step with the head's 80,971)
+
+
 class HotPath:
     # our own kernel launches per step (library kernels of torch are not counted)
-    # per head call: 2 weight packs + 2 pad clears + k1a + k1b + decode (warp kernel + queued CTA kernel) = 8
-    # (two calls: labeled, unlabeled); + target+mse (2) + remap + unsup losses
-    LAUNCHES_FWD = 2 * 8 + 2 + 1 + 1
+    # per head call: 2 weight packs + 1 pad clear (mid) + k1a + k1b + decode (warp kernel + queued CTA kernel) = 7
+    # (+1 pad clear for the saved operand copy when training); two calls: labeled, unlabeled;
+    # + target+mse (2) + remap + unsup losses
+    LAUNCHES_FWD = 2 * 7 + 2 + 1 + 1
     # unsup bwd, remap bwd, target+mse bwd; per head backward: 2 packs + 2 pad clears + plane dots + G2 front end
     # + wgrad2 + dgrad2 + wgrad1 + dgrad1 = 10 (x2), + decode windows and its dense-fallback launch (unlabeled)
-    LAUNCHES_BWD = 3 + 2 * 10 + 2
+    LAUNCHES_BWD = 2 + 3 + 2 * 10 + 2
 
-    def __init__(self, prob, device, fwd_only: bool, world: int = 1):
+    def __init__(self, prob, device, fwd_only: bool, world: int = 1, ddp_payload_floats: int = 0):
         from lightning_pose_b200 import ops
         from lightning_pose_b200.ddp import FlatGradAllReducer
+        from lightning_pose_b200.models.heads.heatmap import HeatmapHead
 
         self.ops, self.dev, self.fwd_only = ops, device, fwd_only
         self.n_clips = prob["n_clips"]
-        self.head = prob["head"].to(device)
+        self.head = HeatmapHead("resnet50", FEAT_C, K_PTS)
+        d1, d2 = list(self.head.upsampling_layers)[1:]
+        with torch.no_grad():
+            w1, b1, w2, b2 = prob["head_params"]
+            d1.weight.copy_(w1), d1.bias.copy_(b1), d2.weight.copy_(w2), d2.bias.copy_(b2)
+        self.head = self.head.to(device)
         self.kp_lab = prob["kp_lab"].to(device)
         self.vis = prob["vis"].to(device)
         self.tf = prob["tf"].to(device)
@@ -176,18 +184,19 @@ class HotPath:
         self.sv = ops.PcaParams(np.arange(K_PTS, dtype=np.int32), K_PTS, 0, None, prob["pca"]["mean"], prob["pca"]["kept"], prob["pca"]["eps"], device)
         self.teps = torch.full((K_PTS,), 20.0, device=device)
         self.w_unsup = 1.0 / (2.0 * np.exp(5.0))
+        self.reducer = None
         if not fwd_only:
             self.opt = torch.optim.Adam(self.head.parameters(), lr=1e-5, fused=True, capturable=True)
-            self.reducer = FlatGradAllReducer(self.head.parameters(), n_scalars=4) if world > 1 else None
+            if world > 1:
+                self.reducer = FlatGradAllReducer(self.head.parameters(), n_scalars=4, extra_floats=ddp_payload_floats)
 
-    def step(self, feats: torch.Tensor):
+    def forward_backward(self, feats: torch.Tensor):
         ops, n = self.ops, self.n_clips
         nl = n * B_LABELED
         # the reference runs the labeled and the unlabeled batch through the model separately
         # (heatmap_tracker.py:163-179, :299-340): two feature tensors, two head calls
         f_lab, f_unl = feats[:nl].detach(), feats[nl:].detach()
         if not self.fwd_only:
-            self.opt.zero_grad(set_to_none=True)
             f_lab.requires_grad_(True)  # d loss / d features feeds the backbone's backward
             f_unl.requires_grad_(True)
         with torch.set_grad_enabled(not self.fwd_only):
@@ -201,10 +210,20 @@ class HotPath:
         scalars = [total.detach(), l_sup.detach(), per_clip[:, 0].mean().detach(), per_clip[:, 1].mean().detach()]
         if not self.fwd_only:
             total.backward()
+        return scalars
+
+    def step(self, feats: torch.Tensor):
+        if not self.fwd_only:
             if self.reducer is not None:
-                return_scalars = self.reducer.step(scalars)  # ONE all-reduce: head gradients + logged scalars
+                self.reducer.begin_step()  # gradients accumulate straight into the flat buffer; backbone bucket starts
+            else:
+                self.opt.zero_grad(set_to_none=True)
+        scalars = self.forward_backward(feats)
+        if not self.fwd_only:
+            if self.reducer is not None:
+                out = self.reducer.finish_step(scalars)  # head bucket (+ logged scalars) after the backward
                 self.opt.step()
-                return return_scalars
+                return out
             self.opt.step()
         return torch.stack(scalars)
 
@@ -252,6 +271,18 @@ def _teardown(dist, rank: int, world: int) -> None:
     os._exit(0)
 
 
+def _wait_for_rank0(dist, timeout_s: float = 900.0) -> None:
+    """Ranks != 0 idle (no GPU work, no collective) until rank 0 has finished its single-GPU breakdown, so that nothing
+    tears down or competes for the NVSwitch / host while rank 0 is still timing kernels."""
+    try:
+        store = dist.distributed_c10d._get_default_store()
+        deadline = time.time() + timeout_s
+        while int(store.add("lpb_rank0_done", 0)) < 1 and time.time() < deadline:
+            time.sleep(0.05)
+    except Exception:
+        pass
+
+
 def time_steps(fn, steps, warmup, barrier=None):
     for _ in range(warmup):
         fn()
@@ -269,26 +300,86 @@ def time_steps(fn, steps, warmup, barrier=None):
     return e0.elapsed_time(e1)
 
 
-def kernel_breakdown(hp: "HotPath", feats, reps=5):
-    """Per-stage device time (CUDA events on the launching stream) for the roofline line."""
+class L2Flusher:
+    """Writes a buffer larger than the 126 MB L2 between timed repetitions of a single stage."""
+
+    def __init__(self, dev, mib: int = 256):
+        self.buf = torch.empty(mib * 2**20 // 4, dtype=torch.float32, device=dev)
+        self.k = 0
+
+    def __call__(self):
+        self.k += 1
+        self.buf.fill_(float(self.k & 7))
+
+
+def time_stage(fn, flush, reps=20, warmup=3):
+    """Mean device time of ``fn`` (CUDA events on the launching stream), L2 flushed before every repetition; the
+    flush itself is outside the event pair."""
+    for _ in range(warmup):
+        fn()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    torch.cuda.synchronize()
+    for e0, e1 in evs:
+        flush()
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize()
+    ts = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+    return float(np.mean(ts)), float(ts[len(ts) // 2])
+
+
+# algorithmic HBM bytes per frame (SURVEY 8(d), K = 17, 384^2, ds = 2; DESIGN.md section 4 restates them)
+HM_BYTES = K_PTS * HM * HM * 4          # one frame of fp32 heatmaps: 626,688
+KP_BYTES = K_PTS * 12                   # x, y, confidence
+
+
+def kernel_breakdown(hp: "HotPath", feats, reps=20):
+    """Per-stage device time for the roofline line: every forward AND backward stage of the step, each timed alone
+    with the L2 flushed before every repetition.  Returns {stage: {ms, ms_median, algorithmic_bytes, gbs}}."""
     ops, n = hp.ops, hp.n_clips
-    nf = feats.shape[0]
+    nf, nl = feats.shape[0], hp.n_clips * B_LABELED
+    nu = nf - nl
+    fb = FEAT_C * FEAT_HW * FEAT_HW * feats.element_size()  # feature bytes per frame
+    flush = L2Flusher(feats.device)
+    out = {}
+
+    def add(name, fn, nbytes, what):
+        ms, med = time_stage(fn, flush, reps)
+        out[name] = {"ms": ms, "ms_median": med, "algorithmic_bytes": nbytes, "gbs": nbytes / ms / 1e6, "what": what}
+
     with torch.no_grad():
         hm = hp.head(feats)
         kp, cf = ops.decode_softargmax(hm, 2, 1000.0)
-        stages = {
-            "head_fwd(convT1+convT2+softmax)": (lambda: hp.head(feats), nf * (FEAT_C * FEAT_HW * FEAT_HW * feats.element_size() + K_PTS * HM * HM * 4)),
-            "decode_fwd": (lambda: ops.decode_softargmax(hm, 2, 1000.0), nf * (K_PTS * HM * HM * 4 + K_PTS * 12)),
-            "target+mse_fwd": (lambda: ops.heatmap_mse_from_keypoints(hp.kp_lab, hm[: n * B_LABELED], IMG, IMG, visibility=hp.vis),
-                               n * B_LABELED * (K_PTS * HM * HM * 4 + K_PTS * 12)),
-            "unsup_losses_fwd": (lambda: ops.unsup_losses(kp[n * B_LABELED :].reshape(n, T_UNLABELED, -1), cf[n * B_LABELED :].reshape(n, T_UNLABELED, -1),
-                                                          temporal_eps=hp.teps, prob_threshold=0.05, pca_singleview=hp.sv),
-                                 n * T_UNLABELED * K_PTS * 12),
-        }
-        out = {}
-        for name, (fn, nbytes) in stages.items():
-            ms = time_steps(fn, reps, 2) / reps
-            out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / ms / 1e6}
+        add("head_fwd", lambda: hp.head(feats), nf * (fb + HM_BYTES), "K1: features -> normalised heatmaps (k1a + k1b, inference form)")
+        add("decode_fwd", lambda: ops.decode_softargmax(hm, 2, 1000.0), nf * (HM_BYTES + KP_BYTES), "K2: heatmaps -> (x, y, confidence)")
+        add("target_mse_fwd", lambda: ops.heatmap_mse_from_keypoints(hp.kp_lab, hm[:nl], IMG, IMG, visibility=hp.vis),
+            nl * (HM_BYTES + KP_BYTES), "K3: fused Gaussian targets + heatmap MSE (labeled frames)")
+        add("unsup_losses_fwd", lambda: ops.unsup_losses(kp[nl:].reshape(n, T_UNLABELED, -1), cf[nl:].reshape(n, T_UNLABELED, -1),
+                                                       temporal_eps=hp.teps, prob_threshold=0.05, pca_singleview=hp.sv),
+            nu * KP_BYTES, "K4: remapped keypoints -> temporal + PCA losses")
+    if not hp.fwd_only:
+        params = list(hp.head.parameters())
+        # labeled branch: dense heatmap-loss gradient -> G2 front end -> wgrad/dgrad of both deconvs
+        f_lab = feats[:nl].detach().requires_grad_(True)
+        hm_lab, _, _ = hp.head.forward_with_keypoints(f_lab)
+        l_sup = ops.heatmap_mse_from_keypoints(hp.kp_lab, hm_lab, IMG, IMG, visibility=hp.vis)
+        g_hm = torch.autograd.grad(l_sup, hm_lab, retain_graph=True)[0]
+        add("target_mse_bwd", lambda: torch.autograd.grad(l_sup, hm_lab, retain_graph=True), nl * 2 * HM_BYTES,
+            "K3 backward: heatmaps -> d heatmaps (dense)")
+        add("head_bwd_labeled", lambda: torch.autograd.grad(hm_lab, [f_lab] + params, g_hm, retain_graph=True),
+            nl * (2 * HM_BYTES + 2 * fb), "K1 backward, dense form: (heatmaps, d heatmaps, features) -> d features + weight gradients")
+        # unlabeled branch: keypoint gradient -> sparse decode windows -> G2 front end -> wgrad/dgrad
+        f_unl = feats[nl:].detach().requires_grad_(True)
+        _hm_u, kp_u, cf_u = hp.head.forward_with_keypoints(f_unl)
+        kp_r = ops.remap_keypoints(kp_u, hp.tf, hp.bbox, IMG, IMG)
+        per_clip = ops.unsup_losses(kp_r.reshape(n, T_UNLABELED, 2 * K_PTS), cf_u.reshape(n, T_UNLABELED, K_PTS),
+                                    temporal_eps=hp.teps, prob_threshold=0.05, pca_singleview=hp.sv)
+        l_uns = per_clip[:, :2].sum()
+        g_kp = torch.autograd.grad(l_uns, kp_u, retain_graph=True)[0]
+        add("unsup_losses_bwd", lambda: torch.autograd.grad(l_uns, kp_u, retain_graph=True), nu * 2 * KP_BYTES, "K4 backward (+ remap)")
+        add("head_bwd_unlabeled", lambda: torch.autograd.grad(kp_u, [f_unl] + params, g_kp, retain_graph=True),
+            nu * (HM_BYTES + 2 * fb), "K2 + K1 backward, sparse form: decode windows + (heatmaps, features) -> d features + weight gradients")
     return out
 
 
@@ -307,7 +398,8 @@ def run_ours(args):
     import lightning_pose_b200  # noqa: F401  (fails loudly without the CUDA library)
 
     prob = make_problem(args.clips, seed=1234 + rank, device=dev, regime=args.regime)
-    hp = HotPath(prob, dev, args.fwd_only, world)
+    payload = int(args.ddp_payload_mb * 1e6 / 4) if (world > 1 and not args.fwd_only) else 0
+    hp = HotPath(prob, dev, args.fwd_only, world, ddp_payload_floats=payload)
     tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     feats_host = prob["feats"].to(tdt).pin_memory()
     feats = feats_host.to(dev, non_blocking=True)
@@ -381,16 +473,21 @@ def run_ours(args):
 
     if rank != 0:
         if dist:
+            _wait_for_rank0(dist)  # stay quiet while rank 0 times its single-GPU stages
             _teardown(dist, rank, world)
         return
     pk, pk_src = peaks()
-    br = kernel_breakdown(hp, feats)
+    # single-GPU stage timings: a fresh single-rank HotPath (no collective inside), peers idle
+    hp_b = HotPath(prob, dev, args.fwd_only) if world > 1 else hp
+    br = kernel_breakdown(hp_b, feats)
     fwd_only_value = None
     if not args.fwd_only:
         hp_fwd = HotPath(prob, dev, True)
         fwd_fn = GraphedStep(hp_fwd, feats) if graphed else (lambda: hp_fwd.step(feats))
-        ms_f = time_steps(fwd_fn, args.steps, 2)
-        fwd_only_value = {"value": n_frames * args.steps / (ms_f / 1e3), "unit": "frames/s", "ms_per_step": ms_f / args.steps}
+        ms_f = time_steps(fwd_fn, args.steps, 3)
+        fwd_alg = n_frames * (FEAT_C * FEAT_HW * FEAT_HW * esz + HM_BYTES + KP_BYTES)  # SURVEY 8(d) "fused path total, training fwd"
+        fwd_only_value = {"value": n_frames * args.steps / (ms_f / 1e3), "unit": "frames/s", "ms_per_step": ms_f / args.steps,
+                          "algorithmic_bytes_per_step": fwd_alg, "frac_hbm": fwd_alg * args.steps / ms_f / 1e6 / pk["hbm_gbs"]}
     flat = None
     if not args.no_flat:
         # secondary regime: the reference's own initialiser (xavier gain 0.01) on randn features -> flat heatmaps ->
@@ -399,19 +496,19 @@ def run_ours(args):
         hp_f = HotPath(prob_f, dev, args.fwd_only)
         feats_f = prob_f["feats"].to(tdt).to(dev)
         nst = max(2, args.steps // 2)
-        ms_flat = time_steps(lambda: hp_f.step(feats_f), nst, 2)
+        ms_flat = time_steps(lambda: hp_f.step(feats_f), nst, 3)
         flat = {"value": n_frames * nst / (ms_flat / 1e3), "unit": "frames/s",
                 "regime": "fresh init: reference initialiser (xavier gain 0.01) on randn*0.5 features; flat heatmaps, dense decode",
-                "stages": {k: round(v["ms"], 4) for k, v in kernel_breakdown(hp_f, feats_f, reps=3).items()}}
+                "stages": {k: round(v["ms"], 4) for k, v in kernel_breakdown(hp_f, feats_f, reps=5).items()}}
         del hp_f, feats_f, prob_f
-    # roofline: the single kernel with the largest share of the step that is callable on its own (the head stage
-    # is several launches; its two GEMM kernels are listed per launch in profiles/)
-    dom = "decode_fwd"
+    # roofline: the stage with the largest measured share of the step
+    dom = max(br, key=lambda k: br[k]["ms"])
     traffic = None
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as fh:
-            per_plane = json.load(fh).get(dom, {}).get("dram_bytes_per_plane")
-            traffic = per_plane * n_frames * K_PTS if per_plane else None  # ncu --set full capture, scaled to this launch
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
+            per_frame = json.load(fh).get(dom, {}).get("dram_bytes_per_frame")
+            nfr = {"head_fwd": n_frames, "decode_fwd": n_frames, "head_bwd_unlabeled": n_frames - hp.n_clips * B_LABELED}.get(dom, hp.n_clips * B_LABELED)
+            traffic = per_frame * nfr if per_frame else None  # ncu --set full capture (profiles/), scaled to this launch
     except Exception:
         pass
     line = {
@@ -420,20 +517,25 @@ def run_ours(args):
         "dtype": args.dtype, "data": "synthetic",
         "config": {
             "workload": f"BASELINE configs[1] hot path on ResNet-50 features (B,2048,12,12): {args.clips} clips/step/GPU x (16 labeled + 32 unlabeled) frames, "
-                        f"K=17, heatmaps 96x96, decode field 384x384; pass = {'forward' if args.fwd_only else 'forward + backward + Adam step on the head (+ one flat all-reduce when N>1)'}",
+                        f"K=17, heatmaps 96x96, decode field 384x384; pass = {'forward' if args.fwd_only else 'forward + backward + Adam step on the head (+ gradient all-reduce when N>1)'}",
             "backward": "all native: loss stack, remap, sparse soft-argmax windows, target+mse, fused softmax-backward/G2 front end, tcgen05 dgrad+wgrad of both transposed convolutions; torch library: fused Adam on the head parameters",
             "frames_per_step_per_gpu": n_frames, "regime": ("trained-like synthetic response (unimodal Gaussian-like heatmaps; planted features + bilinear per-keypoint deconvs, see bench.make_problem); fresh_init_regime = reference initialiser"
                                                                                   if args.regime == "trained" else "fresh init (reference initialiser, flat heatmaps)"),
             "launch": "whole step replayed from one CUDA graph" if graphed else "eager launches",
-            "l2_policy": f"inputs larger than L2 ({feats.numel() * esz / 2**20:.0f} MiB of features per step)", "parallelism": f"dp{world}",
+            "l2_policy": f"step: inputs larger than L2 ({feats.numel() * esz / 2**20:.0f} MiB of features per step); stages: L2 flushed (256 MiB write) before each of 20 timed repetitions",
+            "parallelism": f"dp{world}",
+            "ddp": (f"2 NCCL all-reduces per step: a {payload * 4 / 1e6:.1f} MB synthetic backbone-gradient bucket (stands in for ResNet-50's {BACKBONE_PARAMS:,} parameters, which this "
+                    "head-only step does not produce) on a side stream overlapped with the head's backward, then the head bucket (80,971 gradients written in place by autograd + 4 logged scalars)"
+                    if hp.reducer is not None else "none (N=1)"),
         },
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": feats.numel() * esz, "d2h_bytes_per_step": 16},
         "gpu_launches": (HotPath.LAUNCHES_FWD + (0 if args.fwd_only else HotPath.LAUNCHES_BWD)) * args.steps,
         "clocks": clk.summary(),
-        "roofline": {"bound": "hbm", "kernel": "decode_fwd: decode_fwd_warp_kernel (+ decode_fwd_kernel in queue mode for the planes it hands over)", "achieved": br[dom]["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": f"{dom}: {br[dom]['what']}", "achieved": br[dom]["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": br[dom]["gbs"] / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
-                     "algorithmic_bytes_per_launch": br[dom]["algorithmic_bytes"], "launch_ms": br[dom]["ms"]},
-        "stages": {k: {"ms": round(v["ms"], 4), "GBps": round(v["gbs"], 1), "frac_hbm": round(v["gbs"] / pk["hbm_gbs"], 4)} for k, v in br.items()},
+                     "algorithmic_bytes_per_launch": br[dom]["algorithmic_bytes"], "launch_ms": br[dom]["ms"],
+                     "selection": "arg-max of the per-stage device times below (each stage timed alone, 20 reps, L2 flushed)"},
+        "stages": {k: {"ms": round(v["ms"], 4), "ms_median": round(v["ms_median"], 4), "GBps": round(v["gbs"], 1), "frac_hbm": round(v["gbs"] / pk["hbm_gbs"], 4)} for k, v in br.items()},
     }
     if fwd_only_value is not None:
         line["forward_only"] = fwd_only_value
@@ -444,83 +546,72 @@ def run_ours(args):
     print(json.dumps(line))
     sys.stdout.flush()
     if dist:
+        try:
+            dist.distributed_c10d._get_default_store().add("lpb_rank0_done", 1)
+        except Exception:
+            pass
         _teardown(dist, rank, world)
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the CPU oracle (restated reference path) on the host cores
+# reference arm: the reference's own CPU code (oracle/ref_arm.py -> oracle/ref_loader.py) on the host cores.
+# Nothing on this path imports lightning_pose_b200.
 # ------------------------------------------------------------------------------------------------
 def cpu_threads() -> int:
     """torch CPU ops on these small tensors stop scaling (and regress) beyond ~32 threads; override with LPB_CPU_THREADS."""
     return int(os.environ.get("LPB_CPU_THREADS", min(os.cpu_count() or 1, 32)))
 
 
-def cpu_step(prob, train: bool = True):
-    """The same step on the CPU oracle (restated reference path): forward, and with ``train`` the autograd
-    backward into the features and the head parameters (the reference trains through exactly these torch ops)."""
-    from oracle import lp_oracle as O
-
-    n = prob["n_clips"]
-    deconvs = list(prob["head"].upsampling_layers)[1:]
-    feats = prob["feats"].detach().requires_grad_(train)
-    with torch.set_grad_enabled(train):
-        hm = O.head_forward(feats, [d.weight for d in deconvs], [d.bias for d in deconvs])
-        targ = O.gaussian_targets(prob["kp_lab"], IMG, IMG, (HM, HM), visibility=prob["vis"])
-        l_sup = O.heatmap_mse_loss(targ, hm[: n * B_LABELED])
-        kp, cf = O.decode_softargmax(hm, 2, 1000.0)
-        kp_unl = O.model_to_frame(O.undo_affine(kp[n * B_LABELED :], prob["tf"]), prob["bbox"], IMG, IMG)
-        tot = 0.5 * l_sup
-        for c in range(n):
-            sl = slice(c * T_UNLABELED, (c + 1) * T_UNLABELED)
-            tot = tot + (O.temporal_loss(kp_unl[sl], cf[n * B_LABELED :][sl].detach(), 20.0, 0.05)
-                         + O.pca_loss(O.pca_format_singleview(kp_unl[sl]), prob["pca"]["mean"], prob["pca"]["kept"], prob["pca"]["eps"])) / (2.0 * np.exp(5.0))
-    if train:
-        for d in deconvs:
-            d.weight.grad = d.bias.grad = None
-        tot.backward()
-    return tot.detach()
+def _cpu_model() -> str:
+    try:
+        return [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        return "?"
 
 
 def cpu_reference(seed, clips, reps, train=True):
+    from oracle.ref_arm import ReferenceStep
+
     torch.set_num_threads(cpu_threads())
     prob = make_problem(clips, seed=seed, device="cpu", regime="trained")
-    cpu_step(prob, train)  # warm-up
+    step = ReferenceStep(prob, IMG, HM, B_LABELED, T_UNLABELED)
+    step(train)  # warm-up
     t0 = time.perf_counter()
     for _ in range(reps):
-        cpu_step(prob, train)
+        step(train)
     dt = (time.perf_counter() - t0) / reps
     frames = clips * (B_LABELED + T_UNLABELED)
-    model = "?"
-    try:
-        model = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
-    except Exception:
-        pass
-    return {"value": frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{clips} clip(s) = {frames} frames of the same workload, {'forward+backward' if train else 'forward'} pass, torch CPU oracle (oracle/lp_oracle.py), {model}",
+    code = "the reference's own files (oracle/_ref via oracle/ref_loader.py; kornia restated)" if step.kind == "reference" else "torch CPU restatement (oracle/lp_oracle.py)"
+    return {"value": frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": step.kind,
+            "sample": f"{clips} clip(s) = {frames} frames of the same workload, {'forward+backward' if train else 'forward'} pass, fp32, {code}, {_cpu_model()}",
             "seconds_per_sample": dt}
 
 
 def run_reference(args):
     if int(os.environ.get("RANK", 0)) != 0:
         return
+    from oracle.ref_arm import ReferenceStep
+
     torch.set_num_threads(cpu_threads())
     clips = 1
     prob = make_problem(clips, seed=1234, device="cpu", regime=args.regime)
+    step = ReferenceStep(prob, IMG, HM, B_LABELED, T_UNLABELED)
     train = not args.fwd_only
     for _ in range(min(args.warmup, 1)):
-        cpu_step(prob, train)
+        step(train)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(prob, train)
+        step(train)
     dt = time.perf_counter() - t0
     frames = clips * (B_LABELED + T_UNLABELED)
     value = frames * args.steps / dt
+    code = "the reference's own files executed unmodified (oracle/_ref, oracle/ref_loader.py; kornia restated)" if step.kind == "reference" else "torch CPU restatement of the reference path (oracle/lp_oracle.py)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1] hot path, bounded sample: {clips} clip/step x (16 labeled + 32 unlabeled) frames, {'forward+backward' if train else 'forward'} pass, CPU"},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{frames} frames/step, torch CPU restatement of the reference path (oracle/lp_oracle.py)"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": step.kind,
+                         "sample": f"{frames} frames/step, {code}, {_cpu_model()}"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -539,6 +630,8 @@ def main():
     ap.add_argument("--fwd-only", action="store_true", help="time the forward pass only (default: full training step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a captured CUDA graph")
+    ap.add_argument("--ddp-payload-mb", type=float, default=BACKBONE_PARAMS * 4 / 1e6,
+                    help="N>1: size of the synthetic backbone-gradient bucket all-reduced every step (0 = head gradients only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -107,15 +107,32 @@ int lpb_head_fwd_f32(const float* features, int B, int C, int H, int W, const fl
                      int c1, const float* w2, const float* b2, int c2, int final_softmax, float* out,
                      void* workspace, void* stream);
 
-/* bf16 tensor-core path (tcgen05 / TMEM), two-deconv heads (ResNet family): features bf16 NCHW, fp32
- * master weights (rounded to bf16 on device, as autocast does), fp32 accumulate, fp32 heatmaps.
- * C % 128 == 0, H*W % 8 == 0, c1, c2 <= 20.  Returns LPB_ERR_UNSUPPORTED for shapes outside this
- * build's tiling (callers then use lpb_head_fwd_f32 on up-cast features). */
+/* The same stack one layer at a time (any number of deconvs: n_layers = log2(stride) - downsample_factor - 1,
+ * heads/heatmap.py:192-193), with its native backward -- the fp32 reference precision path trains through these.
+ *   lpb_convt_fwd_f32   in [B, Cin(*4 if shuffle), Hi(/2), Wi(/2)] -> out [B, Cout, 2Hi, 2Wi]; shuffle != 0 folds
+ *                       PixelShuffle(2) into the load (Hi, Wi are the conv-input = shuffled sizes)
+ *   lpb_plane_softmax_f32  in-place spatial softmax (T = 1) of [n_planes, hw]
+ *   lpb_convt_bwd_f32   autograd of lpb_convt_fwd_f32: grad_in (same shape as `in`, may be NULL), grad_w [Cin,Cout,3,3],
+ *                       grad_bias [Cout] (may be NULL); all overwritten. */
+int lpb_convt_fwd_f32(const float* in, int B, int Cin, int Hi, int Wi, int shuffle, const float* w, const float* bias,
+                      int Cout, float* out, void* stream);
+int lpb_plane_softmax_f32(float* x, int64_t n_planes, int hw, void* stream);
+int lpb_convt_bwd_f32(const float* in, const float* grad_out, int B, int Cin, int Hi, int Wi, int shuffle, const float* w,
+                      int Cout, float* grad_in, float* grad_w, float* grad_bias, void* stream);
+
+/* bf16 tensor-core path (tcgen05 / TMEM): features bf16 NCHW, fp32 master weights (rounded to bf16 on device, as
+ * autocast does), fp32 accumulate, fp32 heatmaps.  One-deconv heads (ViT family, heads/heatmap.py:192-193: pass
+ * w2 = b2 = NULL, c2 = 0) and two-deconv heads (ResNet family); C % 128 == 0, H*W % 8 == 0, c1, c2 <= 20 (c1 < 20 for
+ * two deconvs).  Two kernel families serve it: whole-frame-in-TMEM kernels for two-deconv heads on feature maps up to
+ * 12x12 ("fast path"), and banded kernels for everything else (one-deconv heads, 16x16 / 24x24 ... maps).
+ * lpb_head_bf16_plan reports which one a shape takes: plan[0] = 1 fast path, 0 banded (then saved_xs is REQUIRED by
+ * lpb_head_fwd_bf16: it is the pixel-shuffled operand itself); LPB_ERR_UNSUPPORTED if neither fits. */
+int lpb_head_bf16_plan(int C, int H, int W, int c1, int c2, int* plan);
 int lpb_head_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes);
 int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int W, const float* w1, const float* b1, int c1,
                       const float* w2, const float* b2, int c2, int final_softmax, float* out, void* saved_xs,
                       void* workspace, void* stream);
-/* saved_xs: NULL for inference.  For training pass a device buffer of lpb_head_bf16_saved_bytes() bytes; it
+/* saved_xs: on the fast path NULL for inference; for training (and always on the banded path) a device buffer of lpb_head_bf16_saved_bytes() bytes; it
  * receives the pixel-shuffled features in the padded row layout the weight-gradient GEMM reads, and must stay
  * alive (together with `workspace`, which holds the activations between the two deconvs) until
  * lpb_head_bwd_bf16. */
@@ -130,7 +147,8 @@ int lpb_head_bf16_saved_bytes(int B, int C, int H, int W, size_t* bytes);
  * probs: the head output itself when the head ends in the spatial softmax (its backward is applied on the fly),
  *   NULL when the head returns logits.
  * dfeat [B, C, H, W] bf16 or NULL (frozen backbone); dw1 [C/4, c1, 3, 3], db1 [c1], dw2 [c1, c2, 3, 3],
- * db2 [c2] fp32 (overwritten).  workspace: lpb_head_bwd_bf16_workspace_bytes(). */
+ * db2 [c2] fp32 (overwritten).  One-deconv heads: w2 = dw2 = db2 = NULL, c2 = 0 (output [B, c1, 4H, 4W]).
+ * Feature maps: H even, W in {4, 8, 12, 16, 24, 32}.  workspace: lpb_head_bwd_bf16_workspace_bytes(). */
 int lpb_head_bwd_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes);
 int lpb_head_bwd_bf16(const float* g_out, const float* probs, const float* win, const int32_t* win_meta,
                       const float* g_overflow, const void* saved_xs, const void* fwd_workspace, int B, int C, int H,
@@ -187,6 +205,12 @@ int lpb_heatmap_mse_from_keypoints_bwd(const float* keypoints, const int32_t* vi
 int lpb_temporal_heatmap_loss_fwd(const float* heatmaps, const float* confidences, int64_t T, int K, int h, int w,
                                   int kind, const float* eps, float prob_threshold, float* out, float* workspace,
                                   void* stream);
+/* autograd of the call above w.r.t. heatmaps (the reference trains through it: temporal_heatmap_mse / _kl are
+ * unsupervised losses, losses/factory.py:73-91).  workspace = the forward's (per-pair differences); grad_out [1];
+ * grad_heatmaps [T,K,h,w] is overwritten. */
+int lpb_temporal_heatmap_loss_bwd(const float* heatmaps, const float* confidences, const float* workspace, int64_t T,
+                                  int K, int h, int w, int kind, const float* eps, float prob_threshold,
+                                  const float* grad_out, float* grad_heatmaps, void* stream);
 
 /* ---- unsupervised losses on the (T, K, 2) keypoint tensor -------------------------------------
  * replaces TemporalLoss.__call__ and PCALoss.__call__ (+ KeypointPCA._format_data / reproject /

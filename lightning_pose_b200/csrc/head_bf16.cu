@@ -23,6 +23,7 @@
 #include <type_traits>
 
 #include "../../include/lpb200.h"
+#include "head_rows.cuh"
 #include "lpb_common.cuh"
 #include "row_layout.cuh"
 #include "tcgen05.cuh"
@@ -597,7 +598,46 @@ __host__ inline HeadGeom make_half_geom(int Hh, int Wi) {
 
 }  // namespace lpb
 
-// workspace layout: [packed w1][packed w2][mid activations (padded row layout)]
+// ---- which kernels serve a shape ---------------------------------------------------------------------------
+// fast path (k1a + k1b): two-deconv heads whose whole frame fits the TMEM / shared-memory tiling above;
+// generic path (head_rows_bf16.cu): everything else -- one-deconv heads, larger feature maps.
+static bool head_fast_path(int C, int H, int W, int c2, int max_smem) {
+  using namespace lpb;
+  if (c2 <= 0) return false;
+  if (!((W >= 7 || W == 4 || W == 6) && H * W <= 192)) return false;
+  const HeadGeom g1 = make_geom(2 * H, 2 * W), g2 = make_half_geom(2 * H, 4 * W);
+  if (g1.tiles * HB_NCOLS > 512) return false;
+  return (int64_t)k1a_smem_bytes(g1, H * W) <= max_smem && (int64_t)k1b_smem_bytes(g2) <= max_smem;
+}
+
+static int device_limits(int* max_smem, int* sms) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    *max_smem = 227 * 1024;  // sm_100a (also what a CPU-only caller sizing buffers should assume)
+    *sms = 148;
+  }
+  return 0;
+}
+
+// plan[0] = 1: fast path (saved_xs optional: training only); 0: generic path (saved_xs REQUIRED: it is the operand)
+extern "C" int lpb_head_bf16_plan(int C, int H, int W, int c1, int c2, int* plan) {
+  using namespace lpb;
+  LPB_REQUIRE(plan, "head_bf16_plan: null pointer");
+  LPB_REQUIRE(C >= 128 && C % 128 == 0 && H >= 1 && W >= 1 && (H * W) % 8 == 0 && c1 >= 1 && c2 >= 0, "head_bf16_plan: bad shape");
+  LPB_REQUIRE(c2 == 0 ? c1 <= HB_CLS : (c1 < HB_CLS && c2 <= HB_CLS), "head_bf16_plan: channel counts %d/%d exceed %d", c1, c2, HB_CLS);
+  int max_smem, sms;
+  device_limits(&max_smem, &sms);
+  plan[0] = head_fast_path(C, H, W, c2, max_smem) ? 1 : 0;
+  if (!plan[0] && ((size_t)32 * H * W * 2 > 200 * 1024 || (c2 > 0 ? 4 : 2) * W + 1 > 384)) {
+    set_error("head_bf16_plan: feature map %dx%d too large for this build", H, W);
+    return LPB_ERR_UNSUPPORTED;
+  }
+  return LPB_OK;
+}
+
+// workspace layout: [packed w1][packed w2][mid activations (padded row layout; two-deconv heads only)]
 extern "C" int lpb_head_bf16_saved_bytes(int B, int C, int H, int W, size_t* bytes) {
   using namespace lpb;
   LPB_REQUIRE(bytes && B >= 0 && C >= 32 && C % 32 == 0 && H >= 1 && W >= 1, "head_bf16_saved_bytes: bad arguments");
@@ -608,9 +648,9 @@ extern "C" int lpb_head_bf16_saved_bytes(int B, int C, int H, int W, size_t* byt
 extern "C" int lpb_head_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes) {
   using namespace lpb;
   LPB_REQUIRE(bytes, "head_bf16_workspace_bytes: null pointer");
-  LPB_REQUIRE(B >= 0 && C >= 128 && C % 128 == 0 && H >= 1 && W >= 1 && c1 >= 1 && c2 >= 1, "head_bf16_workspace_bytes: bad shape");
+  LPB_REQUIRE(B >= 0 && C >= 128 && C % 128 == 0 && H >= 1 && W >= 1 && c1 >= 1 && c2 >= 0, "head_bf16_workspace_bytes: bad shape");
   const size_t w1 = (size_t)(C / 4 / HB_KSTAGE) * HB_BSTAGE_BYTES, w2 = HB_BSTAGE_BYTES;
-  const size_t mid = (size_t)B * 4 * make_row_layout(4 * H, 4 * W).rows * 16;
+  const size_t mid = c2 > 0 ? (size_t)B * 4 * make_row_layout(4 * H, 4 * W).rows * 16 : 0;
   *bytes = w1 + w2 + mid;
   return LPB_OK;
 }
@@ -619,29 +659,15 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
                                  const float* w2, const float* b2, int c2, int final_softmax, float* out, void* saved_xs,
                                  void* workspace, void* stream) {
   using namespace lpb;
-  LPB_REQUIRE(features && w1 && b1 && w2 && b2 && out && workspace, "head_fwd_bf16: null pointer");
+  LPB_REQUIRE(features && w1 && b1 && out && workspace, "head_fwd_bf16: null pointer");
+  LPB_REQUIRE(c2 == 0 || (w2 && b2), "head_fwd_bf16: a two-deconv head needs w2 and b2");
   LPB_REQUIRE(B >= 0 && C >= 128 && C % 128 == 0 && H >= 1 && W >= 1, "head_fwd_bf16: bad feature shape C=%d H=%d W=%d", C, H, W);
   LPB_REQUIRE((H * W) % 8 == 0, "head_fwd_bf16: H*W must be a multiple of 8 (got %d)", H * W);
-  if (!((W >= 7 || W == 4 || W == 6) && H * W <= 192)) {
-    set_error("head_fwd_bf16: feature map %dx%d outside this build's staging (W >= 7 or W in {4, 6}; H*W <= 192)", H, W);
-    return LPB_ERR_UNSUPPORTED;
-  }
-  LPB_REQUIRE(c1 >= 1 && c1 < HB_CLS && c2 >= 1 && c2 <= HB_CLS, "head_fwd_bf16: channel counts %d/%d exceed %d", c1, c2, HB_CLS);
+  LPB_REQUIRE(c2 == 0 ? (c1 >= 1 && c1 <= HB_CLS) : (c1 >= 1 && c1 < HB_CLS && c2 >= 1 && c2 <= HB_CLS),
+              "head_fwd_bf16: channel counts %d/%d exceed %d", c1, c2, HB_CLS);
   if (B == 0) return LPB_OK;
-  const HeadGeom g1 = make_geom(2 * H, 2 * W), g2 = make_half_geom(2 * H, 4 * W);  // layer 2: 4H rows in two halves
-  if (g1.tiles * HB_NCOLS > 512) {
-    set_error("head_fwd_bf16: %d M-tiles of layer 1 exceed TMEM (feature map %dx%d too large for this build)", g1.tiles, H, W);
-    return LPB_ERR_UNSUPPORTED;
-  }
-  int dev = 0, max_smem = 0, sms = 0;
-  LPB_CUDA(cudaGetDevice(&dev));
-  LPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t s1 = k1a_smem_bytes(g1, H * W), s2 = k1b_smem_bytes(g2);
-  if ((int64_t)s1 > max_smem || (int64_t)s2 > max_smem) {
-    set_error("head_fwd_bf16: needs %zu / %zu B shared memory (> %d)", s1, s2, max_smem);
-    return LPB_ERR_UNSUPPORTED;
-  }
+  int max_smem = 0, sms = 0;
+  device_limits(&max_smem, &sms);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nst = C / 4 / HB_KSTAGE;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
@@ -649,12 +675,58 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   __nv_bfloat16* wp1 = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* wp2 = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)nst * HB_BSTAGE_BYTES);
   __nv_bfloat16* mid = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES);
-  launch_zero_row_pads(mid, Lmid, (long long)B * 4, stream);
-  if (saved_xs) launch_zero_row_pads(static_cast<__nv_bfloat16*>(saved_xs), Lxs, (long long)B * (C / 32), stream);
   pack_convt_weights_kernel<<<64, 256, 0, s>>>(w1, nullptr, C / 4, c1, nst, wp1, nullptr, 0);
   // layer 2: bias rides on the constant-one channel c1 of the mid activations (only needed without softmax:
   // a per-plane constant does not change a softmax)
-  pack_convt_weights_kernel<<<8, 256, 0, s>>>(w2, final_softmax ? nullptr : b2, c1, c2, 1, wp2, nullptr, 0);
+  if (c2 > 0) {
+    pack_convt_weights_kernel<<<8, 256, 0, s>>>(w2, final_softmax ? nullptr : b2, c1, c2, 1, wp2, nullptr, 0);
+    launch_zero_row_pads(mid, Lmid, (long long)B * 4, stream);
+  }
+  if (!head_fast_path(C, H, W, c2, max_smem)) {
+    // ---- generic path: shuffle rows -> banded GEMM(s) ----
+    LPB_REQUIRE(saved_xs, "head_fwd_bf16: this shape takes the banded kernels (lpb_head_bf16_plan = 0): pass the "
+                          "lpb_head_bf16_saved_bytes() buffer as saved_xs");
+    __nv_bfloat16* xs = static_cast<__nv_bfloat16*>(saved_xs);
+    int rc = launch_rows_shuffle(static_cast<const __nv_bfloat16*>(features), B, C, H, W, xs, s);
+    if (rc != LPB_OK) return rc;
+    ConvtRowsParams p{};
+    p.X = xs;
+    p.L = Lxs;
+    p.wpk = wp1;
+    p.bias = b1;
+    p.nst = nst;
+    p.B = B;
+    p.cout = c1;
+    p.out = out;
+    if (c2 == 0) {
+      p.mode = final_softmax ? CONVT_ROWS_SOFTMAX : CONVT_ROWS_PLANES;
+      rc = launch_convt_rows(p, sms, s);
+      if (rc != LPB_OK) return rc;
+    } else {
+      p.mode = CONVT_ROWS_MID;
+      p.mid = mid;
+      p.Lout = Lmid;
+      rc = launch_convt_rows(p, sms, s);
+      if (rc != LPB_OK) return rc;
+      ConvtRowsParams p2{};
+      p2.X = mid;
+      p2.L = Lmid;
+      p2.wpk = wp2;
+      p2.bias = nullptr;  // folded into the GEMM through the ones channel (see the pack above)
+      p2.nst = 1;
+      p2.B = B;
+      p2.cout = c2;
+      p2.out = out;
+      p2.mode = final_softmax ? CONVT_ROWS_SOFTMAX : CONVT_ROWS_PLANES;
+      rc = launch_convt_rows(p2, sms, s);
+      if (rc != LPB_OK) return rc;
+    }
+    LPB_CUDA(cudaGetLastError());
+    return LPB_OK;
+  }
+  const HeadGeom g1 = make_geom(2 * H, 2 * W), g2 = make_half_geom(2 * H, 4 * W);  // layer 2: 4H rows in two halves
+  const size_t s1 = k1a_smem_bytes(g1, H * W), s2 = k1b_smem_bytes(g2);
+  if (saved_xs) launch_zero_row_pads(static_cast<__nv_bfloat16*>(saved_xs), Lxs, (long long)B * (C / 32), stream);
   K1aParams pa;
   pa.feat = static_cast<const __nv_bfloat16*>(features);
   pa.wpk = wp1;

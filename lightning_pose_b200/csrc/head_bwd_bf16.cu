@@ -263,8 +263,7 @@ __global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, int Cin, 
 // b2d: data gradient of the second deconv:  G2 -> d mid, emitted as G1 (+ bias gradient of layer 1)
 // =====================================================================================================
 constexpr int B2D_THREADS = 192;  // warp 0 loader, warp 1 MMA, warps 2-5 epilogue
-constexpr int B2D_ROWS = 7;       // image rows per chunk (7 * 49 = 343 raster rows -> 3 M-tiles)
-constexpr int B2D_TILES = 3;
+constexpr int B2D_TILES = 3;       // M-tiles per chunk: R2 = 384 / (Wi + 1) image rows (7 * 49 = 343 raster rows at Wi = 48)
 
 struct B2dParams {
   const __nv_bfloat16* G2;    // [B][10][L2.rows][8] padded row layout
@@ -273,6 +272,7 @@ struct B2dParams {
   RowLayout L2, L1;
   float* db1;                 // [c1] accumulated with atomics (pre-zeroed)
   int B, Hi, Wi, c1;
+  int R2;                     // image rows per chunk
 };
 
 __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_constant__ B2dParams P) {
@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  const int B2D_ROWS = P.R2;
   const int nchunk = (Hi + B2D_ROWS - 1) / B2D_ROWS;
 
   if (warp == 0) {
@@ -321,8 +322,9 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
         const int y0 = ck * B2D_ROWS;
         mbar_wait(a_empty, (it & 1) ^ 1);
         // per K-chunk ONE copy: the zero entry before image row y0-1, that row, and the chunk's rows (zero columns
-        // included); rows above the image / below it come from the layout's zero lead / trail rows
-        const uint32_t nbytes = (uint32_t)((1 + (B2D_ROWS + 1) * Pp) * 16);
+        // included); the row above the image comes from the layout's zero lead rows.  A short last chunk copies only its
+        // own rows (stale rows further down feed accumulator rows the epilogue skips).
+        const uint32_t nbytes = (uint32_t)((1 + (min(B2D_ROWS, Hi - y0) + 1) * Pp) * 16);
         if (lane < GB_KC) {
           if (lane == 0) mbar_expect_tx(a_full, GB_KC * nbytes);
           __syncwarp((1u << GB_KC) - 1);
@@ -425,37 +427,42 @@ constexpr int B3A_THREADS = 320;  // warp 0 loader, warp 1 MMA, warps 2-9 epilog
 struct B3aParams {
   const __nv_bfloat16* G1;   // [B][10][L.rows][8] padded row layout
   RowLayout L;
-  const __nv_bfloat16* wpk;  // [C4/128][4][10][128][8]
+  const __nv_bfloat16* wpk;  // [ceil(C4/128)][4][10][128][8]
   __nv_bfloat16* dfeat;      // [B][4*C4][(Hi/2)*(Wi/2)]
   int B, C4, Hi, Wi;         // shuffled-image geometry (Hi = 2H, Wi = 2W)
-  int nhalf_cols;            // TMEM columns per half (multiple of 16)
+  int Hh;                    // image rows per band (multiple of 4)
+  int ncols;                 // TMEM columns per band = Hh * (Wi + 1) rounded up to 16 (<= 304)
 };
 
+// A frame is processed in bands of Hh image rows (the accumulator of a band, N = Hh * (Wi + 1) pixels, must fit TMEM next
+// to nothing else; the band's gradient rows plus the halo row above are double-buffered in shared memory).
 template <int WS2>
 __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_constant__ B3aParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Wi = P.Wi, Hi = P.Hi, Pp = Wi + 1, LEAD = Pp + 1;
-  const int Hh = Hi / 2;  // image rows per half
-  const int rows_alloc = (LEAD + 2 * P.nhalf_cols + 7) & ~7;
+  const int Hh = P.Hh, nbands = (Hi + Hh - 1) / Hh;
+  const int rows_alloc = (LEAD + P.ncols + 7) & ~7;
   const int g_bytes = GB_KC * rows_alloc * 16;
   const int w_bytes = 4 * GB_KC * 128 * 16;
-  unsigned char* Gs = smem;
-  unsigned char* Ws = smem + g_bytes;
+  unsigned char* Gs = smem;                 // [2 stages][10][rows_alloc][16 B]
+  unsigned char* Ws = smem + 2 * g_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(Ws + w_bytes);
-  uint64_t* g_full = bars;
-  uint64_t* g_empty = bars + 1;
-  uint64_t* w_full = bars + 2;
-  uint64_t* t_full = bars + 3;
-  uint64_t* t_empty = bars + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* g_full = bars;       // [2]
+  uint64_t* g_empty = bars + 2;  // [2]
+  uint64_t* w_full = bars + 4;
+  uint64_t* t_full = bars + 5;
+  uint64_t* t_empty = bars + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ntile = P.C4 / 128;
+  const int ntile = (P.C4 + 127) / 128;
   const int mt = blockIdx.x % ntile, slot = blockIdx.x / ntile, nslot = gridDim.x / ntile;
 
-  for (int i = tid; i < g_bytes / 16; i += B3A_THREADS) reinterpret_cast<uint4*>(Gs)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * g_bytes / 16; i += B3A_THREADS) reinterpret_cast<uint4*>(Gs)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    mbar_init(g_full, 1);
-    mbar_init(g_empty, 1);
+    for (int st = 0; st < 2; ++st) {
+      mbar_init(&g_full[st], 1);
+      mbar_init(&g_empty[st], 1);
+    }
     mbar_init(w_full, 1);
     mbar_init(t_full, 1);
     mbar_init(t_empty, 256);
@@ -467,8 +474,8 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  const int n0 = P.nhalf_cols > 256 ? 160 : P.nhalf_cols;  // first MMA's N; the rest goes into a second MMA
-  const int n1 = P.nhalf_cols - n0;
+  const int n0 = P.ncols > 256 ? 160 : P.ncols;  // first MMA's N; the rest goes into a second MMA
+  const int n1 = P.ncols - n0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -476,36 +483,42 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
       bulk_g2s(Ws, reinterpret_cast<const unsigned char*>(P.wpk) + (size_t)mt * w_bytes, (uint32_t)w_bytes, w_full);
     }
     int it = 0;
-    for (int b = slot; b < P.B; b += nslot, ++it) {
-      mbar_wait(g_empty, (it & 1) ^ 1);
-      // the smem operand IS the padded row layout (same lead): one copy per K-chunk
-      const uint32_t nbytes = (uint32_t)((LEAD + Hi * Pp) * 16);
-      if (lane < GB_KC) {
-        if (lane == 0) mbar_expect_tx(g_full, GB_KC * nbytes);
-        __syncwarp((1u << GB_KC) - 1);
-        bulk_g2s(Gs + (size_t)lane * rows_alloc * 16, P.G1 + (((size_t)b * GB_KC + lane) * P.L.rows) * 8, nbytes, g_full);
+    for (int b = slot; b < P.B; b += nslot)
+      for (int band = 0; band < nbands; ++band, ++it) {
+        const int st = it & 1, y0 = band * Hh, hb = min(Hh, Hi - y0);
+        mbar_wait(&g_empty[st], ((it >> 1) & 1) ^ 1);
+        // one copy per K-chunk: the zero entry before image row y0 - 1, that row (zero lead rows of the layout when
+        // y0 = 0), and the band's rows, zero columns included
+        const uint32_t nbytes = (uint32_t)((1 + (hb + 1) * Pp) * 16);
+        if (lane < GB_KC) {
+          if (lane == 0) mbar_expect_tx(&g_full[st], GB_KC * nbytes);
+          __syncwarp((1u << GB_KC) - 1);
+          bulk_g2s(Gs + (size_t)st * g_bytes + (size_t)lane * rows_alloc * 16,
+                   P.G1 + (((size_t)b * GB_KC + lane) * P.L.rows + P.L.lead + (size_t)(y0 - 1) * Pp - 1) * 8, nbytes, &g_full[st]);
+        }
       }
-    }
   } else if (warp == 1) {
     const uint32_t idesc0 = tc::make_idesc_bf16_f32(128, n0);
     const uint32_t idesc1 = n1 > 0 ? tc::make_idesc_bf16_f32(128, n1) : 0u;
     const uint32_t lbo_g = rows_alloc * 16, lbo_w = 128 * 16;
-    const uint32_t g0 = smem_u32(Gs), w0 = smem_u32(Ws);
+    const uint32_t w0 = smem_u32(Ws);
     mbar_wait(w_full, 0);
-    int it = 0, nb = 0;
-    for (int b = slot; b < P.B; b += nslot, ++it) {
-      mbar_wait(g_full, it & 1);
-      for (int hf = 0; hf < 2; ++hf, ++nb) {
-        mbar_wait(t_empty, (nb & 1) ^ 1);
+    int it = 0;
+    for (int b = slot; b < P.B; b += nslot)
+      for (int band = 0; band < nbands; ++band, ++it) {
+        const int st = it & 1;
+        mbar_wait(&g_full[st], (it >> 1) & 1);
+        mbar_wait(t_empty, (it & 1) ^ 1);
         tc::fence_after_sync();
         if (lane == 0) {
+          const uint32_t g0 = smem_u32(Gs + (size_t)st * g_bytes);
 #pragma unroll
           for (int sh = 0; sh < 4; ++sh) {
             const int shift_rows = (sh >> 1) * Pp + (sh & 1);
 #pragma unroll
             for (int k16 = 0; k16 < GB_K / 16; ++k16) {
               const uint32_t ww = w0 + ((sh * GB_KC + 2 * k16) * 128) * 16;
-              const uint32_t gg = g0 + (2 * k16) * lbo_g + (LEAD + hf * Hh * Pp - shift_rows) * 16;
+              const uint32_t gg = g0 + (2 * k16) * lbo_g + (LEAD - shift_rows) * 16;
               const uint64_t wd = tc::make_smem_desc(ww, lbo_w, 128);
               tc::umma_bf16(tmem_base, wd, tc::make_smem_desc(gg, lbo_g, 128), idesc0, (sh | k16) != 0 ? 1u : 0u);
               if (n1 > 0)
@@ -513,11 +526,10 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
             }
           }
           tc::umma_commit(t_full);
-          if (hf == 1) tc::umma_commit(g_empty);
+          tc::umma_commit(&g_empty[st]);
         }
         __syncwarp();
       }
-    }
   } else {
     // Epilogue.  Thread = shuffled channel c (TMEM lane); shuffled pixel (m, n) = (2i + di, 2j + dj) belongs to source
     // plane 4c + 2di + dj.  A work item is (di, pair of feature rows i, i+1): two accumulator rows m = 2i + di and m + 2,
@@ -527,15 +539,16 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
     const int c = mt * 128 + 32 * q + lane;
     const int HW = (Hi / 2) * WS2;
     constexpr int NCH = (2 * WS2 + 15) / 16;  // 16-column TMEM loads per accumulator row
-    const int npairs = Hh / 4;                // feature-row pairs per half
-    int nb = 0;
-    for (int b = slot; b < P.B; b += nslot) {
-      for (int hf = 0; hf < 2; ++hf, ++nb) {
-        mbar_wait(t_full, nb & 1);
+    int it = 0;
+    for (int b = slot; b < P.B; b += nslot)
+      for (int band = 0; band < nbands; ++band, ++it) {
+        const int y0 = band * Hh, hb = min(Hh, Hi - y0);
+        const int npairs = hb / 4;  // feature-row pairs in this band
+        mbar_wait(t_full, it & 1);
         tc::fence_after_sync();
         for (int item = e; item < 2 * npairs; item += 2) {
           const int di = item & 1, ip = item >> 1;
-          const int ml = 4 * ip + di;  // first accumulator row of the item within this half
+          const int ml = 4 * ip + di;  // first accumulator row of the item within this band
           float v[2][NCH * 16];
 #pragma unroll
           for (int r = 0; r < 2; ++r)
@@ -543,29 +556,30 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
             for (int k = 0; k < NCH; ++k)
               tc::tmem_ld16_async(tmem_base + ((uint32_t)(32 * q) << 16) + (ml + 2 * r) * Pp + 16 * k, &v[r][16 * k]);
           tc::tmem_ld_wait();
-          const int i0 = (hf * Hh) / 2 + 2 * ip;  // first feature row of the pair
+          if (c < P.C4) {
+            const int i0 = y0 / 2 + 2 * ip;  // first feature row of the pair
 #pragma unroll
-          for (int dj = 0; dj < 2; ++dj) {
-            __nv_bfloat16* dst = P.dfeat + ((size_t)b * 4 * P.C4 + 4 * c + 2 * di + dj) * HW + (size_t)i0 * WS2;
+            for (int dj = 0; dj < 2; ++dj) {
+              __nv_bfloat16* dst = P.dfeat + ((size_t)b * 4 * P.C4 + 4 * c + 2 * di + dj) * HW + (size_t)i0 * WS2;
 #pragma unroll
-            for (int s4 = 0; s4 < (2 * WS2) / 8; ++s4) {  // 8 consecutive elements of [row r][j]
-              uint32_t pk[4];
+              for (int s4 = 0; s4 < (2 * WS2) / 8; ++s4) {  // 8 consecutive elements of [row r][j]
+                uint32_t pk[4];
 #pragma unroll
-              for (int e2 = 0; e2 < 4; ++e2) {
-                const int x0 = 8 * s4 + 2 * e2, x1 = x0 + 1;  // index into the 2*WS2 run
-                const float f0 = v[x0 / WS2][2 * (x0 % WS2) + dj];
-                const float f1 = v[x1 / WS2][2 * (x1 % WS2) + dj];
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-                pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  const int x0 = 8 * s4 + 2 * e2, x1 = x0 + 1;  // index into the 2*WS2 run
+                  const float f0 = v[x0 / WS2][2 * (x0 % WS2) + dj];
+                  const float f1 = v[x1 / WS2][2 * (x1 % WS2) + dj];
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                  pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                *reinterpret_cast<uint4*>(dst + 8 * s4) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
-              *reinterpret_cast<uint4*>(dst + 8 * s4) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
         }
         tc::fence_before_sync();
         tc::mbar_arrive(t_empty);
       }
-    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -766,17 +780,46 @@ static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, float* d
   return LPB_OK;
 }
 
+// bias gradient of a one-deconv head: column sums of the gradient rows, folded over the four classes
+__global__ void __launch_bounds__(256) rows_colsum_kernel(const __nv_bfloat16* __restrict__ G, RowLayout L, int B, int cout,
+                                                          float* __restrict__ db) {
+  // one CTA per (frame, K-chunk): thread = (row stripe, e)
+  const int b = blockIdx.x / GB_KC, kc = blockIdx.x - b * GB_KC;
+  const __nv_bfloat16* slab = G + ((size_t)b * GB_KC + kc) * (size_t)L.rows * 8;
+  const int e = threadIdx.x & 7;
+  float acc = 0.f;
+  for (int r = L.lead + (threadIdx.x >> 3); r < L.lead + L.Hi * L.Pp; r += 32) acc += __bfloat162float(slab[(size_t)r * 8 + e]);
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int i = threadIdx.x; i < 256; i += 8) t += red[i];
+    const int k = kc * 8 + threadIdx.x, o = k % GB_CLS;
+    if (o < cout && t != 0.f) atomicAdd(db + o, t);
+  }
+}
+
+// largest rows-per-band Hh (multiple of 4) whose accumulator fits the b3a TMEM tiling
+static int b3a_band_rows(int Hi1, int Wi1) {
+  int hh = (304 / (Wi1 + 1)) & ~3;
+  if (hh > Hi1) hh = Hi1;
+  return hh;
+}
+
 }  // namespace lpb
 
-// workspace: [W1 dgrad pack][W2 dgrad pack][G2][G1][plane dots]   (G2 / G1: padded row layouts, row_layout.cuh)
+// workspace: [W1 dgrad pack][W2 dgrad pack][G2][G1][plane dots]   (G2 / G1: padded row layouts, row_layout.cuh);
+// a one-deconv head (c2 = 0) has no W2 pack and no G2: its output gradient is G1 directly
 extern "C" int lpb_head_bwd_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, size_t* bytes) {
   using namespace lpb;
   LPB_REQUIRE(bytes, "head_bwd_bf16_workspace_bytes: null pointer");
-  LPB_REQUIRE(B >= 0 && C >= 512 && C % 512 == 0 && H >= 1 && W >= 1 && c1 >= 1 && c2 >= 1, "head_bwd_bf16_workspace_bytes: bad shape");
-  const size_t w1 = (size_t)(C / 4 / 128) * 4 * GB_KC * 128 * 16, w2 = (size_t)4 * GB_KC * 32 * 16;
-  const size_t g2 = (size_t)B * GB_KC * make_row_layout(4 * H, 4 * W).rows * 16;
+  LPB_REQUIRE(B >= 0 && C >= 128 && C % 128 == 0 && H >= 1 && W >= 1 && c1 >= 1 && c2 >= 0, "head_bwd_bf16_workspace_bytes: bad shape");
+  const int C4 = C / 4;
+  const size_t w1 = (size_t)((C4 + 127) / 128) * 4 * GB_KC * 128 * 16, w2 = (size_t)4 * GB_KC * 32 * 16;
+  const size_t g2 = c2 > 0 ? (size_t)B * GB_KC * make_row_layout(4 * H, 4 * W).rows * 16 : 0;
   const size_t g1 = (size_t)B * GB_KC * make_row_layout(2 * H, 2 * W).rows * 16;
-  *bytes = w1 + w2 + g2 + g1 + (((size_t)B * c2 * 4 + 255) & ~(size_t)255);
+  *bytes = w1 + w2 + g2 + g1 + (((size_t)B * (c2 > 0 ? c2 : c1) * 4 + 255) & ~(size_t)255);
   return LPB_OK;
 }
 
@@ -785,21 +828,29 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
                                  int W, const float* w1, int c1, const float* w2, int c2, void* dfeat, float* dw1, float* db1,
                                  float* dw2, float* db2, void* workspace, void* stream) {
   using namespace lpb;
-  LPB_REQUIRE(saved_xs && fwd_workspace && w1 && w2 && dw1 && db1 && dw2 && db2 && workspace, "head_bwd_bf16: null pointer");
+  const bool two = c2 > 0;
+  LPB_REQUIRE(saved_xs && fwd_workspace && w1 && dw1 && db1 && workspace, "head_bwd_bf16: null pointer");
+  LPB_REQUIRE(!two || (w2 && dw2 && db2), "head_bwd_bf16: a two-deconv head needs w2, dw2, db2");
   LPB_REQUIRE(g_out || win, "head_bwd_bf16: neither a dense gradient nor decode windows given");
   LPB_REQUIRE(!win || (win_meta && g_overflow), "head_bwd_bf16: windows need their meta and overflow buffers");
-  LPB_REQUIRE(B >= 0 && C >= 512 && C % 512 == 0 && H >= 1 && W >= 1, "head_bwd_bf16: bad feature shape C=%d H=%d W=%d", C, H, W);
-  LPB_REQUIRE(c1 >= 1 && c1 < GB_CLS && c2 >= 1 && c2 <= GB_CLS && (W % 4) == 0 && (H % 4) == 0 && W <= 16,
-              "head_bwd_bf16: unsupported channels / feature map (needs H %% 4 == 0, W in {4, 8, 12, 16})");
+  LPB_REQUIRE(B >= 0 && C >= 128 && C % 128 == 0 && H >= 1 && W >= 1, "head_bwd_bf16: bad feature shape C=%d H=%d W=%d", C, H, W);
+  LPB_REQUIRE(two ? (c1 >= 1 && c1 < GB_CLS && c2 <= GB_CLS) : (c1 >= 1 && c1 <= GB_CLS), "head_bwd_bf16: channel counts %d/%d exceed %d", c1, c2, GB_CLS);
+  if ((W % 4) != 0 || (H % 2) != 0 || !(W == 4 || W == 8 || W == 12 || W == 16 || W == 24 || W == 32)) {
+    set_error("head_bwd_bf16: feature map %dx%d outside this build's epilogue set (H even, W in {4, 8, 12, 16, 24, 32})", H, W);
+    return LPB_ERR_UNSUPPORTED;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int C4 = C / 4, Hi1 = 2 * H, Wi1 = 2 * W, Hi2 = 4 * H, Wi2 = 4 * W;
+  const int kout = two ? c2 : c1;
   LPB_CUDA(cudaMemsetAsync(dw1, 0, sizeof(float) * (size_t)C4 * c1 * 9, s));
-  LPB_CUDA(cudaMemsetAsync(dw2, 0, sizeof(float) * (size_t)c1 * c2 * 9, s));
   LPB_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * c1, s));
-  LPB_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * c2, s));
+  if (two) {
+    LPB_CUDA(cudaMemsetAsync(dw2, 0, sizeof(float) * (size_t)c1 * c2 * 9, s));
+    LPB_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * c2, s));
+  }
   if (B == 0) return LPB_OK;
-  const int nhalf = ((Hi1 / 2) * (Wi1 + 1) + 15) & ~15;
-  if (nhalf > 304 || (Hi1 & 1)) {
+  const int Hh = b3a_band_rows(Hi1, Wi1);
+  if (Hh < 4) {
     set_error("head_bwd_bf16: feature map %dx%d outside this build's TMEM tiling", H, W);
     return LPB_ERR_UNSUPPORTED;
   }
@@ -808,44 +859,50 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
   LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const RowLayout L2 = make_row_layout(Hi2, Wi2), L1 = make_row_layout(Hi1, Wi1);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
-  const size_t w1b = (size_t)(C4 / 128) * 4 * GB_KC * 128 * 16, w2b = (size_t)4 * GB_KC * 32 * 16;
+  const int ntile1 = (C4 + 127) / 128;
+  const size_t w1b = (size_t)ntile1 * 4 * GB_KC * 128 * 16, w2b = (size_t)4 * GB_KC * 32 * 16;
+  const size_t g2b = two ? (size_t)B * GB_KC * L2.rows * 16 : 0, g1b = (size_t)B * GB_KC * L1.rows * 16;
   __nv_bfloat16* wp1 = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* wp2 = reinterpret_cast<__nv_bfloat16*>(ws + w1b);
   __nv_bfloat16* G2 = reinterpret_cast<__nv_bfloat16*>(ws + w1b + w2b);
-  __nv_bfloat16* G1 = reinterpret_cast<__nv_bfloat16*>(ws + w1b + w2b + (size_t)B * GB_KC * L2.rows * 16);
+  __nv_bfloat16* G1 = reinterpret_cast<__nv_bfloat16*>(ws + w1b + w2b + g2b);
+  float* ddot = reinterpret_cast<float*>(ws + w1b + w2b + g2b + g1b);
   // the forward pass's mid activations (head_bf16.cu workspace layout: [packed w1][packed w2][mid])
   const size_t fwd_mid_off = (size_t)(C4 / 32 + 1) * (4 * 4 * 80 * 16);
   const __nv_bfloat16* mid = reinterpret_cast<const __nv_bfloat16*>(static_cast<const unsigned char*>(fwd_workspace) + fwd_mid_off);
 
-  pack_dgrad_weights_kernel<<<128, 256, 0, s>>>(w1, C4, c1, C4 / 128, 128, wp1, nullptr, 0);
-  pack_dgrad_weights_kernel<<<8, 256, 0, s>>>(w2, c1, c2, 1, 32, wp2, nullptr, 0);
-  launch_zero_row_pads(G2, L2, (long long)B * GB_KC, stream);
+  pack_dgrad_weights_kernel<<<128, 256, 0, s>>>(w1, C4, c1, ntile1, 128, wp1, nullptr, 0);
+  if (two) {
+    pack_dgrad_weights_kernel<<<8, 256, 0, s>>>(w2, c1, c2, 1, 32, wp2, nullptr, 0);
+    launch_zero_row_pads(G2, L2, (long long)B * GB_KC, stream);
+  }
   launch_zero_row_pads(G1, L1, (long long)B * GB_KC, stream);
   {
+    // gradient front end on the head's OUTPUT grid: G2 for a two-deconv head, G1 for a one-deconv head
+    const int Hio = two ? Hi2 : Hi1, Wio = two ? Wi2 : Wi1;
+    __nv_bfloat16* Gout = two ? G2 : G1;
+    const RowLayout Lo = two ? L2 : L1;
     G2Src src;
     src.g_out = g_out;
     src.probs = probs;
     src.win = win;
     src.meta = win ? win_meta : nullptr;
     src.gov = g_overflow;
-    float* ddot = reinterpret_cast<float*>(ws + w1b + w2b + (size_t)B * GB_KC * L2.rows * 16 + (size_t)B * GB_KC * L1.rows * 16);
     src.ddot = nullptr;
     if (probs) {
-      LPB_REQUIRE(((4 * Hi2 * Wi2) % 4) == 0, "head_bwd_bf16: plane size");
-      plane_dot_kernel<<<(unsigned)(B * c2), 256, 0, s>>>(src, 4 * Hi2 * Wi2, ddot);
+      LPB_REQUIRE(((4 * Hio * Wio) % 4) == 0, "head_bwd_bf16: plane size");
+      plane_dot_kernel<<<(unsigned)(B * kout), 256, 0, s>>>(src, 4 * Hio * Wio, ddot);
       src.ddot = ddot;
     }
-    if (g_out && probs) launch_g2_build<true, true>(src, B, c2, Hi2, Wi2, G2, L2, s);
-    else if (g_out) launch_g2_build<true, false>(src, B, c2, Hi2, Wi2, G2, L2, s);
-    else if (probs) launch_g2_build<false, true>(src, B, c2, Hi2, Wi2, G2, L2, s);
-    else launch_g2_build<false, false>(src, B, c2, Hi2, Wi2, G2, L2, s);
+    if (g_out && probs) launch_g2_build<true, true>(src, B, kout, Hio, Wio, Gout, Lo, s);
+    else if (g_out) launch_g2_build<true, false>(src, B, kout, Hio, Wio, Gout, Lo, s);
+    else if (probs) launch_g2_build<false, true>(src, B, kout, Hio, Wio, Gout, Lo, s);
+    else launch_g2_build<false, false>(src, B, kout, Hio, Wio, Gout, Lo, s);
   }
-  // layer 2: weight + bias gradient (bias from the all-ones channel c1 of mid), then data gradient -> G1 (+ db1)
-  {
+  if (two) {
+    // layer 2: weight + bias gradient (bias from the all-ones channel c1 of mid), then data gradient -> G1 (+ db1)
     const int rc = launch_wgrad(mid, G2, dw2, db2, B, Hi2, Wi2, 4, 4, c1, c2, c1, 1, sms, s);
     if (rc != LPB_OK) return rc;
-  }
-  {
     B2dParams p;
     p.G2 = G2;
     p.wpk = wp2;
@@ -857,16 +914,22 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
     p.Hi = Hi2;
     p.Wi = Wi2;
     p.c1 = c1;
+    p.R2 = (B2D_TILES * 128) / (Wi2 + 1);
+    if (p.R2 > Hi2) p.R2 = Hi2;
     const int rows_alloc = (Wi2 + 2 + B2D_TILES * 128 + 7) & ~7;
     const size_t smem = (size_t)GB_KC * rows_alloc * 16 + (size_t)4 * GB_KC * 32 * 16 + 64;
-    LPB_REQUIRE(smem <= 113 * 1024 && (B2D_ROWS * (Wi2 + 1)) <= B2D_TILES * 128, "head_bwd_bf16: layer-2 width %d too large", Wi2);
+    LPB_REQUIRE(smem <= 113 * 1024 && p.R2 >= 1, "head_bwd_bf16: layer-2 width %d too large", Wi2);
     LPB_CUDA(cudaFuncSetAttribute(b2d_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = B < 2 * sms ? B : 2 * sms;
     b2d_dgrad_kernel<<<grid, B2D_THREADS, smem, s>>>(p);
+  } else {
+    rows_colsum_kernel<<<(unsigned)(B * GB_KC), 256, 0, s>>>(G1, L1, B, c1, db1);
   }
   // layer 1: weight gradient from the saved shuffled features, data gradient -> d features
   {
-    const int rc = launch_wgrad(static_cast<const __nv_bfloat16*>(saved_xs), G1, dw1, nullptr, B, Hi1, Wi1, 16, C4 / 8, C4, c1, -1, 0, sms, s);
+    const int nkc = C4 / 8;  // multiple of 4
+    const int kcx = nkc % 16 == 0 ? 16 : (nkc % 12 == 0 ? 12 : (nkc % 8 == 0 ? 8 : 4));
+    const int rc = launch_wgrad(static_cast<const __nv_bfloat16*>(saved_xs), G1, dw1, nullptr, B, Hi1, Wi1, kcx, nkc, C4, c1, -1, 0, sms, s);
     if (rc != LPB_OK) return rc;
   }
   if (dfeat) {
@@ -879,17 +942,17 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
     p.C4 = C4;
     p.Hi = Hi1;
     p.Wi = Wi1;
-    p.nhalf_cols = nhalf;
-    const int rows_alloc = (Wi1 + 2 + 2 * nhalf + 7) & ~7;
-    const size_t smem = (size_t)GB_KC * rows_alloc * 16 + (size_t)4 * GB_KC * 128 * 16 + 64;
-    LPB_REQUIRE(smem <= 220 * 1024, "head_bwd_bf16: layer-1 operands need %zu B shared memory", smem);
-    const int ntile = C4 / 128;
-    int slots = sms / ntile;
+    p.Hh = Hh;
+    p.ncols = (Hh * (Wi1 + 1) + 15) & ~15;
+    const int rows_alloc = (Wi1 + 2 + p.ncols + 7) & ~7;
+    const size_t smem = (size_t)2 * GB_KC * rows_alloc * 16 + (size_t)4 * GB_KC * 128 * 16 + 128;
+    LPB_REQUIRE(smem <= 225 * 1024, "head_bwd_bf16: layer-1 operands need %zu B shared memory", smem);
+    int slots = sms / ntile1;
     if (slots < 1) slots = 1;
     if (slots > B) slots = B;
     auto run = [&](auto kern) -> int {
       LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<slots * ntile, B3A_THREADS, smem, s>>>(p);
+      kern<<<slots * ntile1, B3A_THREADS, smem, s>>>(p);
       return LPB_OK;
     };
     int rc = LPB_ERR_UNSUPPORTED;
@@ -898,7 +961,9 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
       case 8: rc = run(b3a_dgrad_kernel<8>); break;
       case 12: rc = run(b3a_dgrad_kernel<12>); break;
       case 16: rc = run(b3a_dgrad_kernel<16>); break;
-      default: set_error("head_bwd_bf16: feature width %d not in this build's epilogue set {4, 8, 12, 16}", W);
+      case 24: rc = run(b3a_dgrad_kernel<24>); break;
+      case 32: rc = run(b3a_dgrad_kernel<32>); break;
+      default: set_error("head_bwd_bf16: feature width %d not in this build's epilogue set", W);
     }
     if (rc != LPB_OK) return rc;
   }

@@ -241,6 +241,45 @@ __global__ void __launch_bounds__(HL_THREADS) temporal_heatmap_final_kernel(cons
   if (threadIdx.x == 0) out[0] = acc / (float)((T - 1) * K);
 }
 
+// backward of the two kernels above: one CTA per plane (t, k).  With a = h[t], b = h[t+1]:
+//   MSE  d = mean((a-b)^2):                 dd/da = 2(a-b)/hw,          dd/db = -2(a-b)/hw
+//   KL   d = sum p (log p - log q), q = a + 1e-10, p = b + 1e-10:   dd/da = -p/q,   dd/db = log p - log q + 1
+// a pair (t, k) carries gradient iff neither confidence is below the threshold (the reference zeroes those
+// entries in place, losses.py:789) and d > eps_k (F.relu, :761); the mean runs over all (T-1)*K entries (:851).
+__global__ void __launch_bounds__(HL_THREADS) temporal_heatmap_bwd_kernel(const float* __restrict__ hm,
+                                                                          const float* __restrict__ conf,
+                                                                          const float* __restrict__ ws, int T, int K,
+                                                                          int hw, int kind, const float* __restrict__ eps,
+                                                                          float thr, const float* __restrict__ gout,
+                                                                          float* __restrict__ grad) {
+  const int t = blockIdx.x / K, k = blockIdx.x - t * K;
+  const float scale = __ldg(gout) / (float)((T - 1) * K);
+  auto active = [&](int tt) {  // pair (tt, tt + 1)
+    if (tt < 0 || tt >= T - 1) return false;
+    if (conf[(size_t)tt * K + k] < thr || conf[(size_t)(tt + 1) * K + k] < thr) return false;
+    return ws[(size_t)tt * K + k] - eps[k] > 0.f;
+  };
+  const bool fwd = active(t), bwd = active(t - 1);  // this plane is `a` of pair t and `b` of pair t - 1
+  const float* __restrict__ cur = hm + ((size_t)t * K + k) * hw;
+  const float* __restrict__ nxt = fwd ? hm + ((size_t)(t + 1) * K + k) * hw : cur;
+  const float* __restrict__ prv = bwd ? hm + ((size_t)(t - 1) * K + k) * hw : cur;
+  float* __restrict__ g = grad + ((size_t)t * K + k) * hw;
+  const float inv_hw = 1.0f / (float)hw;
+  for (int i = threadIdx.x; i < hw; i += HL_THREADS) {
+    const float x = __ldg(cur + i);
+    float acc = 0.f;
+    if (fwd) {
+      const float y = __ldg(nxt + i);
+      acc += kind == LPB_HM_MSE ? 2.f * (x - y) * inv_hw : -(y + 1e-10f) / (x + 1e-10f);
+    }
+    if (bwd) {
+      const float z = __ldg(prv + i);
+      acc += kind == LPB_HM_MSE ? -2.f * (z - x) * inv_hw : logf(x + 1e-10f) - logf(z + 1e-10f) + 1.f;
+    }
+    g[i] = acc * scale;
+  }
+}
+
 // ---- coordinate remap ---------------------------------------------------------------------------
 __global__ void remap_kernel(const float* __restrict__ in, int64_t n, int K, const float* __restrict__ tf, int per_frame,
                              int num_views, const float* __restrict__ bbox, int bbox_row_off, float inv_mh, float inv_mw,
@@ -757,6 +796,20 @@ extern "C" int lpb_temporal_heatmap_loss_fwd(const float* heatmaps, const float*
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   temporal_heatmap_pair_kernel<<<(unsigned)((T - 1) * K), HL_THREADS, 0, s>>>(heatmaps, K, h * w, kind, workspace);
   temporal_heatmap_final_kernel<<<1, HL_THREADS, 0, s>>>(workspace, confidences, (int)T, K, eps, prob_threshold, out);
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}
+
+extern "C" int lpb_temporal_heatmap_loss_bwd(const float* heatmaps, const float* confidences, const float* workspace,
+                                             int64_t T, int K, int h, int w, int kind, const float* eps,
+                                             float prob_threshold, const float* grad_out, float* grad_heatmaps,
+                                             void* stream) {
+  using namespace lpb;
+  LPB_REQUIRE(heatmaps && confidences && workspace && eps && grad_out && grad_heatmaps, "temporal_heatmap_loss_bwd: null pointer");
+  LPB_REQUIRE(T >= 2 && K >= 1 && h >= 1 && w >= 1 && (kind == LPB_HM_MSE || kind == LPB_HM_KL) && T * K < (1ll << 31),
+              "temporal_heatmap_loss_bwd: bad shape/kind");
+  temporal_heatmap_bwd_kernel<<<(unsigned)(T * K), HL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      heatmaps, confidences, workspace, (int)T, K, h * w, kind, eps, prob_threshold, grad_out, grad_heatmaps);
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
 }

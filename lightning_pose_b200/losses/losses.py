@@ -218,7 +218,15 @@ class PCALoss(Loss):
         return self.pca.compute_reprojection_error(data_arr=predictions)
 
     def kernel_params(self, num_keypoints: int) -> ops.PcaParams:
-        return self.pca.kernel_params(num_keypoints, float(self.epsilon))
+        """Device-side parameter block, built once per keypoint count: no host sync (``float(epsilon)``) and no
+        pageable upload in the step, so the unsupervised loss launch is CUDA-graph capturable."""
+        cache = self.__dict__.setdefault("_kernel_params", {})
+        eps = self.epsilon
+        key = (int(num_keypoints), id(eps))
+        if key not in cache:
+            cache.clear()
+            cache[key] = self.pca.kernel_params(num_keypoints, float(eps))
+        return cache[key]
 
     def __call__(
         self, keypoints_pred: torch.Tensor, stage: Literal["train", "val", "test"] | None = None, **kwargs: Any

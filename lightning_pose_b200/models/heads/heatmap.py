@@ -62,52 +62,45 @@ def run_subpixelmaxima(
     return ops.decode_softargmax(heatmaps, int(downsample_factor), float(temperature))
 
 
-def _conv_backward(features, params, n, g_logits, need_dfeat):
-    """Head shapes outside the tensor-core tiling and the fp32 head: transposed-conv dgrad/wgrad through the
-    framework's conv ops ("backward")."""
-    cdt = torch.bfloat16 if features.dtype == torch.bfloat16 else torch.float32  # same precision as the forward
-    with torch.enable_grad():
-        f = features.detach().to(cdt).requires_grad_(need_dfeat)
-        ps = [p.detach().float().requires_grad_(True) for p in params]
-        x = torch.nn.functional.pixel_shuffle(f, 2)
-        for wt, bs in zip(ps[:n], ps[n:]):
-            x = torch.nn.functional.conv_transpose2d(x, wt.to(cdt), bs.to(cdt), stride=2, padding=1, output_padding=1)
-        ins = ([f] if need_dfeat else []) + ps
-        grads = torch.autograd.grad(x, ins, g_logits.to(cdt))
-    gf = grads[0] if need_dfeat else None
-    gp = grads[1:] if need_dfeat else grads
-    return (gf, *gp)
+def _needs_grad(features: torch.Tensor, params) -> bool:
+    """Whether a backward can follow (decided outside the autograd node: grad mode is off inside ``forward``).
+    Inference skips everything the backward would need (saved operand copies, inter-layer activations)."""
+    return torch.is_grad_enabled() and (features.requires_grad or any(p.requires_grad for p in params))
 
 
 class _HeadFunction(torch.autograd.Function):
     """Fused head, optionally with the soft-argmax decode riding along (``decode = (ds, temperature)``).
 
-    Forward: tcgen05 head (+ decode kernel).  Backward: ONE native pass.  The gradient w.r.t. the heatmaps is
-    never materialised for the decode branch: the sparse decode windows, a dense heatmap-loss gradient if there
-    is one, and the softmax backward are all folded into the kernel that writes the deconv-gradient operand.
-    Outputs: heatmaps [, keypoints (B, 2K), confidences (B, K)].
+    Forward: tcgen05 head for bf16 features (one- or two-deconv heads inside the tensor-core tiling), the fp32
+    CUDA-core kernels otherwise (+ decode kernel).  Backward: native in both cases.  On the tcgen05 path the gradient
+    w.r.t. the heatmaps is never materialised for the decode branch: the sparse decode windows, a dense heatmap-loss
+    gradient if there is one, and the softmax backward are all folded into the kernel that writes the
+    deconv-gradient operand.  Outputs: heatmaps [, keypoints (B, 2K), confidences (B, K)].
     """
 
     @staticmethod
-    def forward(ctx, features, final_softmax, decode, *params):
+    def forward(ctx, features, final_softmax, decode, train, *params):
         n = len(params) // 2
         weights, biases = list(params[:n]), list(params[n:])
-        saved = None
-        out = None
-        if features.dtype == torch.bfloat16 and n == 2 and features.is_cuda:
-            res = ops._head_forward_bf16(features.contiguous(), weights, biases, final_softmax, train=True)
-            if res is not None:
-                out, saved = res
-        if out is None:
-            out = ops.head_forward(features, weights, biases, final_softmax)
+        saved = acts = None
+        if features.dtype == torch.bfloat16 and features.is_cuda and ops.head_bf16_supported(
+                tuple(features.shape), [w.shape[1] for w in weights], train=train):
+            res = ops._head_forward_bf16(features.contiguous(), weights, biases, final_softmax, train=train)
+            out, saved = res if train else (res, None)
+        elif train:
+            out, acts = ops.head_forward_f32(features, weights, biases, final_softmax, keep_activations=True)
+        else:
+            out = ops.head_forward_f32(features, weights, biases, final_softmax)
         ctx.set_materialize_grads(False)
         ctx.final_softmax, ctx.n, ctx.saved, ctx.decode = final_softmax, n, saved, decode
+        ctx.n_acts = len(acts) if acts is not None else 0
+        extra = list(acts) if acts is not None else []
         if decode is None:
-            ctx.save_for_backward(features, out, *params)
+            ctx.save_for_backward(features, out, *params, *extra)
             return out
         ds, temperature = decode
         xy, conf, stats = ops._decode_fwd(out, int(ds), float(temperature))
-        ctx.save_for_backward(features, out, *params, stats)
+        ctx.save_for_backward(features, out, *params, *extra, stats)
         ctx.mark_non_differentiable(conf)
         return out, xy.reshape(-1, out.shape[1] * 2), conf
 
@@ -115,12 +108,13 @@ class _HeadFunction(torch.autograd.Function):
     def backward(ctx, g, g_xy=None, g_conf=None):
         tensors = list(ctx.saved_tensors)
         stats = tensors.pop() if ctx.decode is not None else None
+        acts = [tensors.pop() for _ in range(ctx.n_acts)][::-1]
         features, out, *params = tensors
         n = ctx.n
         weights, biases = params[:n], params[n:]
         need_dfeat = ctx.needs_input_grad[0]
         if g is None and g_xy is None:
-            return (None,) * (3 + 2 * n)
+            return (None,) * (4 + 2 * n)
         if g is not None:
             g = g.contiguous().float()
         if ctx.saved is not None:
@@ -128,19 +122,22 @@ class _HeadFunction(torch.autograd.Function):
             if g_xy is not None:
                 windows = ops.decode_backward_windows(out, stats, g_xy.contiguous().float(), int(ctx.decode[0]), float(ctx.decode[1]))
             dfeat, dw1, db1, dw2, db2 = ops.head_backward_bf16(
-                g, ctx.saved, tuple(features.shape), weights[0], weights[1], need_dfeat=need_dfeat,
+                g, ctx.saved, tuple(features.shape), weights[0], weights[1] if n == 2 else None, need_dfeat=need_dfeat,
                 probs=out if ctx.final_softmax else None, windows=windows,
             )
-            ctx.saved = None
-            return (dfeat, None, None, dw1.to(weights[0].dtype), dw2.to(weights[1].dtype), db1.to(biases[0].dtype), db2.to(biases[1].dtype))
-        # generic path: dense decode gradient, softmax backward kernel, library conv backward
+            dws, dbs = ([dw1, dw2], [db1, db2]) if n == 2 else ([dw1], [db1])
+            return (dfeat, None, None, None, *[d.to(w.dtype) for d, w in zip(dws, weights)], *[d.to(b.dtype) for d, b in zip(dbs, biases)])
+        # fp32 path: dense decode gradient, softmax backward, then the deconvs' own backward kernels, last layer first
         if g_xy is not None:
             gd = ops._decode_bwd(out, stats, g_xy.contiguous().float(), int(ctx.decode[0]), float(ctx.decode[1]))
             g = gd if g is None else g + gd
         if ctx.final_softmax:  # d softmax: p * (g - sum(g * p)) per plane
             g = ops.plane_softmax_backward(out, g)
-        gf, *gp = _conv_backward(features, params, n, g, need_dfeat)
-        return (gf, None, None, *gp)
+        dws, dbs = [None] * n, [None] * n
+        for i in range(n - 1, -1, -1):
+            g, dws[i], dbs[i] = ops.convt_backward_f32(acts[i], g, weights[i], shuffle=(i == 0), need_dx=(i > 0 or need_dfeat))
+        gf = g.to(features.dtype) if need_dfeat else None
+        return (gf, None, None, None, *[d.to(w.dtype) for d, w in zip(dws, weights)], *[d.to(b.dtype) for d, b in zip(dbs, biases)])
 
 
 class HeatmapHead(nn.Module):
@@ -183,7 +180,7 @@ class HeatmapHead(nn.Module):
     def forward(self, features: torch.Tensor) -> torch.Tensor:
         deconvs = self._deconvs()
         params = [d.weight for d in deconvs] + [d.bias for d in deconvs]
-        return _HeadFunction.apply(features, bool(self.final_softmax), None, *params)
+        return _HeadFunction.apply(features, bool(self.final_softmax), None, _needs_grad(features, params), *params)
 
     def forward_with_keypoints(self, features: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """``forward`` + ``run_subpixelmaxima`` as one autograd node: (heatmaps, keypoints, confidences).
@@ -194,7 +191,7 @@ class HeatmapHead(nn.Module):
         deconvs = self._deconvs()
         params = [d.weight for d in deconvs] + [d.bias for d in deconvs]
         decode = (int(self.downsample_factor), float(self.temperature))
-        return _HeadFunction.apply(features, bool(self.final_softmax), decode, *params)
+        return _HeadFunction.apply(features, bool(self.final_softmax), decode, _needs_grad(features, params), *params)
 
     def run_subpixelmaxima(self, heatmaps: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         return run_subpixelmaxima(heatmaps, self.downsample_factor, self.temperature)

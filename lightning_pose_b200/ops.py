@@ -18,6 +18,10 @@ __all__ = [
     "generate_heatmaps",
     "evaluate_heatmaps_at_location",
     "head_forward",
+    "head_forward_f32",
+    "head_bf16_supported",
+    "convt_forward_f32",
+    "convt_backward_f32",
     "head_backward_bf16",
     "decode_backward_windows",
     "remap_keypoints",
@@ -169,31 +173,53 @@ def evaluate_heatmaps_at_location(heatmaps, locs, radius: int = 2):
 # =====================================================================================
 # heatmap head
 # =====================================================================================
+_BWD_WIDTHS = (4, 8, 12, 16, 24, 32)
+
+
+def head_bf16_supported(shape, channels, train: bool) -> bool:
+    """Whether the tcgen05 kernels cover this head: feature shape (B, C, H, W), deconv output channels (c1[, c2])."""
+    _, c, h, w = shape
+    n = len(channels)
+    if n not in (1, 2) or c % 128 or (h * w) % 8:
+        return False
+    if (n == 1 and channels[0] > 20) or (n == 2 and (channels[0] >= 20 or channels[1] > 20)):
+        return False
+    plan = C.c_int(0)
+    if lib.lpb_head_bf16_plan(c, h, w, channels[0], channels[1] if n == 2 else 0, C.byref(plan)) != 0:
+        return False
+    if train and (h % 2 or w not in _BWD_WIDTHS or (304 // (2 * w + 1)) < 4):
+        return False
+    return True
+
+
 def _head_forward_bf16(f, weights, biases, final_softmax, train=False):
-    """tcgen05 path; returns None when the shape is outside the tensor-core tiling of this build.
+    """tcgen05 path (one- or two-deconv heads); the caller checks ``head_bf16_supported`` first.
 
     ``train=True`` returns ``(out, saved)`` where ``saved`` carries what ``head_backward_bf16`` needs
-    (the forward workspace with the inter-layer activations, and the row-layout copy of the shuffled features).
+    (the row-layout copy of the shuffled features and the forward workspace with the inter-layer activations).
     """
     b, c, h, w = f.shape
-    w1, w2 = (_cuda_f32(x, "weight") for x in weights)
-    b1, b2 = (_cuda_f32(x, "bias") for x in biases)
-    c1, c2 = w1.shape[1], w2.shape[1]
-    if c % 128 or (h * w) % 8 or c1 >= 20 or c2 > 20 or (2 * h * (2 * w + 1) + 127) // 128 * 80 > 512 or h * w > 192 or not (w >= 7 or w in (4, 6)):
-        return None
+    n = len(weights)
+    w1 = _cuda_f32(weights[0], "weight")
+    b1 = _cuda_f32(biases[0], "bias")
+    w2 = _cuda_f32(weights[1], "weight") if n == 2 else None
+    b2 = _cuda_f32(biases[1], "bias") if n == 2 else None
+    c1, c2 = w1.shape[1], (w2.shape[1] if n == 2 else 0)
+    plan = C.c_int(0)
+    check(lib.lpb_head_bf16_plan(c, h, w, c1, c2, C.byref(plan)))
     nbytes = C.c_size_t(0)
     check(lib.lpb_head_bf16_workspace_bytes(b, c, h, w, c1, c2, C.byref(nbytes)))
     ws = torch.empty((nbytes.value,), device=f.device, dtype=torch.uint8)
-    out = torch.empty((b, c2, 8 * h, 8 * w), device=f.device, dtype=torch.float32)
-    native_bwd = train and c % 512 == 0 and w in (4, 8, 12, 16) and h % 4 == 0 and ((h * (2 * w + 1) + 15) & ~15) <= 304
+    up = 8 if n == 2 else 4
+    out = torch.empty((b, c2 if n == 2 else c1, up * h, up * w), device=f.device, dtype=torch.float32)
     xs = None
-    if native_bwd:  # row-layout copy of the shuffled features for the weight-gradient GEMM
+    if train or plan.value == 0:  # row-layout copy of the shuffled features: the banded path's operand / the wgrad's input
         check(lib.lpb_head_bf16_saved_bytes(b, c, h, w, C.byref(nbytes)))
         xs = torch.empty((nbytes.value,), device=f.device, dtype=torch.uint8)
     with torch.cuda.device(f.device):
         check(lib.lpb_head_fwd_bf16(_ptr(f), b, c, h, w, _ptr(w1), _ptr(b1), c1, _ptr(w2), _ptr(b2), c2, int(bool(final_softmax)), _ptr(out), _ptr(xs), _ptr(ws), _stream()))
     if train:
-        return out, ((xs, ws) if native_bwd else None)
+        return out, (xs, ws)
     return out
 
 
@@ -212,27 +238,29 @@ def decode_backward_windows(heatmaps, stats, grad_xy, ds, temperature):
 
 
 def head_backward_bf16(g_out, saved, feat_shape, w1, w2, need_dfeat=True, probs=None, windows=None):
-    """Gradients of the bf16 head (tcgen05): returns (dfeat bf16 | None, dw1, db1, dw2, db2).
+    """Gradients of the bf16 head (tcgen05): returns (dfeat bf16 | None, dw1, db1, dw2 | None, db2 | None).
 
     ``g_out``: dense gradient w.r.t. the head output or None; ``probs``: the head output when it ends in the
     spatial softmax (its backward is fused in), None for a logits head; ``windows``: result of
-    ``decode_backward_windows`` or None.
+    ``decode_backward_windows`` or None; ``w2`` None for a one-deconv head.
     """
     xs, fws = saved
     b, c, h, w = feat_shape
     g = _cuda_f32(g_out, "g_out") if g_out is not None else None
     if g is None and windows is None:
         raise ValueError("head_backward_bf16 needs a dense gradient and/or decode windows")
-    w1, w2 = _cuda_f32(w1, "w1"), _cuda_f32(w2, "w2")
-    c1, c2 = w1.shape[1], w2.shape[1]
+    w1 = _cuda_f32(w1, "w1")
+    w2 = _cuda_f32(w2, "w2") if w2 is not None else None
+    c1, c2 = w1.shape[1], (w2.shape[1] if w2 is not None else 0)
     dev = w1.device
     nbytes = C.c_size_t(0)
     check(lib.lpb_head_bwd_bf16_workspace_bytes(b, c, h, w, c1, c2, C.byref(nbytes)))
     ws = torch.empty((nbytes.value,), device=dev, dtype=torch.uint8)
     dfeat = torch.empty((b, c, h, w), device=dev, dtype=torch.bfloat16) if need_dfeat else None
-    dw1, dw2 = torch.empty_like(w1), torch.empty_like(w2)
+    dw1 = torch.empty_like(w1)
     db1 = torch.empty((c1,), device=dev, dtype=torch.float32)
-    db2 = torch.empty((c2,), device=dev, dtype=torch.float32)
+    dw2 = torch.empty_like(w2) if w2 is not None else None
+    db2 = torch.empty((c2,), device=dev, dtype=torch.float32) if w2 is not None else None
     win, meta, ov = windows if windows is not None else (None, None, None)
     with torch.cuda.device(dev):
         check(lib.lpb_head_bwd_bf16(_ptr(g), _ptr(probs), _ptr(win), _ptr(meta), _ptr(ov), _ptr(xs), _ptr(fws), b, c, h, w, _ptr(w1), c1, _ptr(w2), c2,
@@ -240,41 +268,73 @@ def head_backward_bf16(g_out, saved, feat_shape, w1, w2, need_dfeat=True, probs=
     return dfeat, dw1, db1, dw2, db2
 
 
-def head_forward(features, weights, biases, final_softmax=True):
-    """PixelShuffle(2) + ConvTranspose2d stack (1 or 2 layers) + spatial softmax; forward only.
+# ---- fp32 precision path: one transposed convolution at a time (any number of layers), native backward ----------
+def convt_forward_f32(x, weight, bias, shuffle: bool):
+    """[PixelShuffle(2) +] ConvTranspose2d(k3, s2, p1, op1) in fp32 on CUDA cores."""
+    x = _cuda_f32(x, "input")
+    wt = _cuda_f32(weight, "weight")
+    bs = _cuda_f32(bias, "bias") if bias is not None else None
+    b, c, h, w = x.shape
+    cin, hi, wi = (c // 4, 2 * h, 2 * w) if shuffle else (c, h, w)
+    if wt.shape[0] != cin:
+        raise ValueError(f"weight expects {wt.shape[0]} input channels, got {cin}")
+    out = torch.empty((b, wt.shape[1], 2 * hi, 2 * wi), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(lib.lpb_convt_fwd_f32(_ptr(x), b, cin, hi, wi, int(shuffle), _ptr(wt), _ptr(bs), wt.shape[1], _ptr(out), _stream()))
+    return out
 
-    bf16 features take the tcgen05 tensor-core kernels (fp32 accumulate, fp32 heatmaps); fp32 features
-    take the full-precision CUDA-core kernels.  Training uses ``HeatmapHead`` which adds the backward.
+
+def convt_backward_f32(x, grad_out, weight, shuffle: bool, need_dx: bool = True, need_db: bool = True):
+    """Autograd of ``convt_forward_f32``: (dx | None, dw, db | None)."""
+    x = _cuda_f32(x, "input")
+    g = _cuda_f32(grad_out, "grad_out")
+    wt = _cuda_f32(weight, "weight")
+    b, c, h, w = x.shape
+    cin, hi, wi = (c // 4, 2 * h, 2 * w) if shuffle else (c, h, w)
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty_like(wt)
+    db = torch.empty((wt.shape[1],), device=x.device, dtype=torch.float32) if need_db else None
+    with torch.cuda.device(x.device):
+        check(lib.lpb_convt_bwd_f32(_ptr(x), _ptr(g), b, cin, hi, wi, int(shuffle), _ptr(wt), wt.shape[1], _ptr(dx), _ptr(dw), _ptr(db), _stream()))
+    return dx, dw, db
+
+
+def plane_softmax_(x: torch.Tensor) -> torch.Tensor:
+    """In-place spatial softmax (T = 1) over each (b, k) plane of a contiguous fp32 tensor."""
+    b, k, h, w = x.shape
+    with torch.cuda.device(x.device):
+        check(lib.lpb_plane_softmax_f32(_ptr(x), b * k, h * w, _stream()))
+    return x
+
+
+def head_forward_f32(features, weights, biases, final_softmax=True, keep_activations=False):
+    """fp32 head: PixelShuffle(2) + any number of deconvs + spatial softmax.  Returns ``out`` or, with
+    ``keep_activations``, ``(out, inputs_of_each_layer)`` for ``convt_backward_f32``."""
+    x = _cuda_f32(features, "features")
+    acts = []
+    for i, (wt, bs) in enumerate(zip(weights, biases)):
+        acts.append(x)
+        x = convt_forward_f32(x, wt, bs, shuffle=(i == 0))
+    if final_softmax:
+        plane_softmax_(x)
+    return (x, acts) if keep_activations else x
+
+
+def head_forward(features, weights, biases, final_softmax=True):
+    """PixelShuffle(2) + ConvTranspose2d stack + spatial softmax; forward only.
+
+    bf16 features take the tcgen05 tensor-core kernels (fp32 accumulate, fp32 heatmaps) when the head is a one- or
+    two-deconv head the tiling covers; everything else takes the full-precision CUDA-core kernels.  Training uses
+    ``HeatmapHead`` which adds the backward.
     """
     if not isinstance(features, torch.Tensor) or not features.is_cuda:
         raise RuntimeError("lpb200: `features` must be a CUDA tensor (this package has no CPU fallback)")
-    if len(weights) not in (1, 2):
-        raise NotImplementedError(f"head with {len(weights)} deconv layers")
-    if features.dtype == torch.bfloat16 and len(weights) == 2 and all(b is not None for b in biases):
-        out = _head_forward_bf16(features.contiguous(), weights, biases, final_softmax)
-        if out is not None:
-            return out
-    f = _cuda_f32(features, "features")
-    b, c, h, w = f.shape
-    w1 = _cuda_f32(weights[0], "w1")
-    b1 = _cuda_f32(biases[0], "b1") if biases[0] is not None else None
-    c1 = w1.shape[1]
-    if len(weights) == 2:
-        w2 = _cuda_f32(weights[1], "w2")
-        b2 = _cuda_f32(biases[1], "b2") if biases[1] is not None else None
-        c2 = w2.shape[1]
-        k, ho, wo = c2, 8 * h, 8 * w
-    else:
-        w2 = b2 = None
-        c2 = 0
-        k, ho, wo = c1, 4 * h, 4 * w
-    out = torch.empty((b, k, ho, wo), device=f.device, dtype=torch.float32)
-    nbytes = C.c_size_t(0)
-    check(lib.lpb_head_workspace_bytes(b, c, h, w, c1, c2, C.byref(nbytes)))
-    ws = torch.empty((max(nbytes.value, 4) // 4,), device=f.device, dtype=torch.float32)
-    with torch.cuda.device(f.device):
-        check(lib.lpb_head_fwd_f32(_ptr(f), b, c, h, w, _ptr(w1), _ptr(b1), c1, _ptr(w2), _ptr(b2), c2, int(bool(final_softmax)), _ptr(out), _ptr(ws), _stream()))
-    return out
+    if len(weights) < 1:
+        raise ValueError("head needs at least one deconv layer")
+    if features.dtype == torch.bfloat16 and all(b is not None for b in biases) and head_bf16_supported(
+            tuple(features.shape), [w.shape[1] for w in weights], train=False):
+        return _head_forward_bf16(features.contiguous(), weights, biases, final_softmax)
+    return head_forward_f32(features, weights, biases, final_softmax)
 
 
 # =====================================================================================
@@ -314,8 +374,11 @@ def remap_keypoints(keypoints, transforms, bbox, model_height, model_width, is_m
     if transforms is not None and transforms.shape[-1] == 3:
         tf = _cuda_f32(transforms, "transforms")
         if not is_multiview and tf.dim() == 3:
-            per_frame = 1
-            if tf.shape[0] != n:
+            if tf.shape[0] == 1:  # a lone (1, 2, 3) transform is tiled over the frames (data/utils.py:193-200)
+                tf = tf[0].contiguous()
+            elif tf.shape[0] == n:
+                per_frame = 1
+            else:
                 raise ValueError(f"per-frame transforms {tuple(tf.shape)} vs {n} frames")
     bb = _cuda_f32(bbox, "bbox")
     if out is not None and kp.requires_grad:
@@ -403,16 +466,39 @@ def heatmap_mse_from_keypoints(keypoints, preds, height, width, sigma=1.25, visi
     return _HeatmapMseFromKeypoints.apply(kp, vis, p, float(height), float(width), float(sigma))
 
 
+class _TemporalHeatmapLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hm, cf, eps, kind, prob_threshold):
+        t, k, h, w = hm.shape
+        out = torch.empty((1,), device=hm.device, dtype=torch.float32)
+        ws = torch.empty((max(t - 1, 1) * k,), device=hm.device, dtype=torch.float32)
+        with torch.cuda.device(hm.device):
+            check(lib.lpb_temporal_heatmap_loss_fwd(_ptr(hm), _ptr(cf), t, k, h, w, kind, _ptr(eps), float(prob_threshold), _ptr(out), _ptr(ws), _stream()))
+        ctx.save_for_backward(hm, cf, eps, ws)
+        ctx.meta = (kind, float(prob_threshold))
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        hm, cf, eps, ws = ctx.saved_tensors
+        kind, thr = ctx.meta
+        t, k, h, w = hm.shape
+        gh = torch.empty_like(hm)
+        gg = g.reshape(1).contiguous().float()
+        with torch.cuda.device(hm.device):
+            check(lib.lpb_temporal_heatmap_loss_bwd(_ptr(hm), _ptr(cf), _ptr(ws), t, k, h, w, kind, _ptr(eps), thr, _ptr(gg), _ptr(gh), _stream()))
+        return gh, None, None, None, None
+
+
 def temporal_heatmap_loss(heatmaps, confidences, kind: str, epsilon: torch.Tensor, prob_threshold: float):
+    """TemporalHeatmapLoss (mse | kl) over consecutive frames; differentiable in ``heatmaps``."""
     hm = _cuda_f32(heatmaps, "heatmaps_pred")
-    cf = _cuda_f32(confidences, "confidences")
-    t, k, h, w = hm.shape
+    cf = _cuda_f32(confidences, "confidences").detach()
+    k = hm.shape[1]
     eps = _cuda_f32(epsilon.to(hm.device).reshape(-1).expand(k) if epsilon.numel() in (1, k) else epsilon, "epsilon")
-    out = torch.empty((1,), device=hm.device, dtype=torch.float32)
-    ws = torch.empty((max(t - 1, 1) * k,), device=hm.device, dtype=torch.float32)
-    with torch.cuda.device(hm.device):
-        check(lib.lpb_temporal_heatmap_loss_fwd(_ptr(hm), _ptr(cf), t, k, h, w, _KIND[kind], _ptr(eps), float(prob_threshold), _ptr(out), _ptr(ws), _stream()))
-    return out[0]
+    if hm.shape[0] < 2:
+        raise ValueError("temporal heatmap loss needs at least two frames")
+    return _TemporalHeatmapLoss.apply(hm, cf, eps, _KIND[kind], float(prob_threshold))
 
 
 # =====================================================================================

@@ -1,7 +1,8 @@
 """Stub loader that executes the reference's OWN hot-path files from /root/reference.  TEST INFRA.
 
-Only usable in the authoring container (``/root/reference`` does not exist on the GPU box), and
-only from ``oracle/gen_golden.py`` / ``tests/test_reference_live.py`` (skipped when absent).
+In the authoring container the files are executed where they lie under ``/root/reference``; on the GPU box (no
+``/root/reference``) from the staged copy ``oracle/_ref`` that ``oracle/build_ref.py`` produces (a git-ignored build
+output).  Used by ``oracle/gen_golden.py``, ``oracle/ref_arm.py`` (the CPU arm of ``bench.py``) and the tests.
 
 The reference cannot be imported as a package here (``omegaconf``, ``kornia``, ``lightning`` ...
 are not installed, no network).  Its hot-path files load unmodified once
@@ -9,7 +10,7 @@ are not installed, no network).  Its hot-path files load unmodified once
     sub-packages, so ``import lightning_pose.data.heatmaps`` resolves to the real file;
   * ``kornia`` is replaced by the six restated functions in ``oracle/lp_oracle.py``;
   * ``omegaconf`` / ``lightning.pytorch`` / three data-layer modules are placeholder names.
-Nothing is copied: the reference sources are executed where they lie.
+The sources are executed as they are (no edits); see oracle/build_ref.py for the staged copy.
 """
 from __future__ import annotations
 
@@ -18,7 +19,10 @@ import os
 import sys
 import types
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # oracle/build_ref.py (GPU box)
 REF_ROOT = os.environ.get("LP_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "lightning_pose")) and os.path.isdir(os.path.join(_STAGED, "lightning_pose")):
+    REF_ROOT = _STAGED
 
 
 def reference_available() -> bool:

@@ -124,3 +124,26 @@ def test_fused_head_node_refuses_cpu_tensors():
         head.forward_with_keypoints(torch.rand(1, 64, 2, 2))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         head.forward_with_keypoints(torch.rand(1, 64, 2, 2).bfloat16())
+
+
+def test_reference_arm_does_not_import_the_product():
+    """bench.py --impl reference / cpu_baseline run the reference's own files (oracle/ref_arm.py); the arm must not load
+    lightning_pose_b200 (or its .so) at all."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); import bench\n"
+        "from oracle.ref_arm import ReferenceStep\n"
+        "bench.FEAT_C, bench.FEAT_HW, bench.IMG, bench.HM = 64, 4, 128, 32\n"
+        "prob = bench.make_problem(1, 5, 'cpu', 'fresh')\n"
+        "step = ReferenceStep(prob, 128, 32, bench.B_LABELED, bench.T_UNLABELED)\n"
+        "v = step(True)\n"
+        "assert torch.isfinite(v), v\n"
+        "bad = [m for m in sys.modules if m.startswith('lightning_pose_b200')]\n"
+        "assert not bad, bad\n"
+        "print(step.kind)\n" % ROOT
+    )
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.strip().splitlines()[-1] in ("reference", "port")

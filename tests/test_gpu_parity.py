@@ -656,3 +656,176 @@ def test_remap_and_fused_mse_backward(lpb, dev, golden):
     p = pred.to(dev).requires_grad_(True)
     (lpb.heatmap_mse_from_keypoints(kp.to(dev), p, 128, 128, visibility=vis.to(dev)) * 1.3).backward()
     close(p.grad, pr.grad, atol=1e-8, rtol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: upsample (a3), TemporalHeatmapLoss backward (a14), every BASELINE config on native kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key,n,stages", [("U_n16_ds1", 16, 1), ("U_n16_ds2", 16, 2), ("U_n12_ds3", 12, 3), ("U_n96_ds2", 96, 2)])
+def test_upsample2x_matches_reference_operator(lpb, dev, golden, key, n, stages):
+    """a3: `upsample` (heads/heatmap.py:86-100) is the separable operator U h U^T; the golden U matrices are the
+    reference's own impulse responses (oracle/gen_golden.py)."""
+    U = torch.from_numpy(golden("decode")[key]).double()
+    torch.manual_seed(5)
+    h = torch.rand(2, 3, n, n)
+    x = h.to(dev)
+    for _ in range(stages):
+        x = lpb.upsample2x(x)
+    ref = torch.einsum("ia,bkac,jc->bkij", U, h.double(), U).float()
+    assert x.shape == ref.shape
+    close(x, ref, atol=2e-6)
+    # and against the oracle's restatement of the same function on a non-square plane
+    h2 = torch.rand(1, 2, 10, 14)
+    close(lpb.upsample2x(h2.to(dev)), O.upsample(h2), atol=2e-6)
+
+
+@pytest.mark.parametrize("kind,eps", [("mse", 1e-5), ("kl", [0.5, 1.0, 2.0])])
+def test_temporal_heatmap_loss_backward(lpb, dev, golden, kind, eps):
+    """a14: the reference trains through TemporalHeatmapLoss (losses.py:793-854); gradient vs oracle autograd."""
+    from lightning_pose_b200.losses.losses import TemporalHeatmapLoss
+
+    g = golden("losses")
+    hseq, cseq = T(g["thm_in_heatmaps"]), T(g["thm_in_conf"])
+    h_ref = hseq.clone().requires_grad_(True)
+    O.temporal_heatmap_loss(h_ref, cseq, kind, eps, 0.2).backward()
+    h = hseq.to(dev).requires_grad_(True)
+    v, _ = TemporalHeatmapLoss(f"temporal_heatmap_{kind}", epsilon=eps, prob_threshold=0.2)(h, cseq.to(dev))
+    close(v, g[f"thm_{kind}_out"])
+    (3.0 * v).backward()
+    assert h.grad is not None and float(h.grad.abs().max()) > 0
+    close(h.grad, 3.0 * h_ref.grad, atol=1e-7, rtol=1e-4)
+
+
+def _rand_head(arch, cin, k, gain=3.0, seed=13, final_softmax=True):
+    from lightning_pose_b200.models.heads.heatmap import HeatmapHead
+
+    torch.manual_seed(seed)
+    head = HeatmapHead(arch, cin, k, final_softmax=final_softmax)
+    for layer in list(head.upsampling_layers)[1:]:
+        torch.nn.init.xavier_uniform_(layer.weight, gain=gain)
+        torch.nn.init.uniform_(layer.bias, -0.3, 0.3)
+    return head
+
+
+def _bf16_head_oracle_n(feats_bf16, head, requires_grad=False):
+    """fp32 evaluation of the head on bf16-rounded operands (weights, inter-layer activations), any layer count."""
+    import torch.nn.functional as F
+
+    r = lambda t: (t.bfloat16().float() - t).detach() + t
+    deconvs = list(head.upsampling_layers)[1:]
+    f = feats_bf16.float().requires_grad_(requires_grad)
+    ps = [(d.weight.detach().clone().requires_grad_(requires_grad), d.bias.detach().clone().requires_grad_(requires_grad)) for d in deconvs]
+    x = F.pixel_shuffle(f, 2)
+    for i, (w, b) in enumerate(ps):
+        x = F.conv_transpose2d(r(x) if i else x, r(w), b, stride=2, padding=1, output_padding=1)
+    return x, f, ps
+
+
+# the head shapes of BASELINE configs 3 (ViT-S 256^2), 4 (ViT 384^2) and 5 (ResNet-50 512^2), plus config 2 on the banded kernels' sibling
+REAL_SHAPES = [("vits_dino", 384, 16, 16, 3), ("vits_dino", 384, 24, 24, 2), ("resnet50", 2048, 16, 16, 2), ("resnet50", 2048, 12, 12, 3)]
+
+
+@pytest.mark.parametrize("arch,c,fh,fw,b", REAL_SHAPES)
+def test_head_bf16_real_config_shapes_forward(lpb, dev, arch, c, fh, fw, b):
+    assert lpb.head_bf16_supported((b, c, fh, fw), [17] * (1 if arch.startswith("vit") else 2), train=True)
+    head = _rand_head(arch, c, 17)
+    feats = (torch.randn(b, c, fh, fw) * 0.5).bfloat16()
+    logits_ref, _, _ = _bf16_head_oracle_n(feats, head)
+    hm_ref = O.spatial_softmax2d(logits_ref.detach(), 1.0)
+    head = head.to(dev)
+    with torch.no_grad():
+        out = head(feats.to(dev))
+    assert out.dtype == torch.float32 and out.shape == hm_ref.shape
+    rel = ((out.cpu() - hm_ref).abs() / (hm_ref.abs() + 1e-7)).flatten()
+    assert float(rel.max()) < 3e-2 and float((rel > 1e-2).float().mean()) < 1e-4
+    close(out.sum((2, 3)), torch.ones(b, 17), atol=1e-5)
+    head.final_softmax = False
+    with torch.no_grad():
+        lg = head(feats.to(dev))
+    close(lg, logits_ref.detach(), atol=1e-2 * float(logits_ref.abs().max()), rtol=1e-2)
+    # same answer with the training-side buffers (saved operand copy) in play
+    head.final_softmax = True
+    out2 = head(feats.to(dev).requires_grad_(True))
+    close(out2, out, atol=0, rtol=0)
+
+
+@pytest.mark.parametrize("arch,c,fh,fw,b", REAL_SHAPES[:3])
+@pytest.mark.parametrize("softmax", [True, False])
+def test_head_bf16_real_config_shapes_backward(lpb, dev, arch, c, fh, fw, b, softmax):
+    head = _rand_head(arch, c, 17, final_softmax=softmax, seed=31)
+    feats = (torch.randn(b, c, fh, fw) * 0.5).bfloat16()
+    y, f_ref, ps = _bf16_head_oracle_n(feats, head, requires_grad=True)
+    up = y.shape[-1] // fw
+    gout = torch.randn(b, 17, up * fh, up * fw)
+    if softmax:
+        y = O.spatial_softmax2d(y, 1.0)
+    (y * gout).sum().backward()
+    head = head.to(dev)
+    f_dev = feats.to(dev).requires_grad_(True)
+    (head(f_dev) * gout.to(dev)).sum().backward()
+    deconvs = list(head.upsampling_layers)[1:]
+    checks = [("dfeat", f_dev.grad.float(), f_ref.grad)]
+    for i, (d, (w, bb)) in enumerate(zip(deconvs, ps)):
+        checks += [(f"dw{i}", d.weight.grad, w.grad), (f"db{i}", d.bias.grad, bb.grad)]
+    wscale = float(ps[-1][0].grad.abs().max())
+    for name, got, ref in checks:
+        err, scale = float((got.cpu() - ref).abs().max()), float(ref.abs().max())
+        if name.startswith("db"):  # cancelling sums (exactly 0 behind a softmax): rounding noise, bounded by the dw scale
+            scale = max(scale, wscale)
+        assert err <= 1e-2 * scale + 1e-9, (name, err, scale)
+
+
+def test_head_fused_keypoints_backward_one_deconv(lpb, dev):
+    """config-3 head (ViT, one deconv): forward_with_keypoints + sparse decode windows through the banded kernels."""
+    b, c, fh, fw = 4, 384, 16, 16
+    head = _rand_head("vits_dino", c, 17, gain=6.0, seed=37)
+    feats = (torch.randn(b, c, fh, fw) * 0.7).bfloat16()
+    head = head.to(dev)
+    f1 = feats.to(dev).requires_grad_(True)
+    hm, kp, cf = head.forward_with_keypoints(f1)
+    gk = torch.randn_like(kp)
+    (kp * gk).sum().backward()
+    g_fused = f1.grad.float().clone()
+    w_fused = list(head.upsampling_layers)[1].weight.grad.clone()
+    # the same through the dense decode backward on the head's own (already verified) dense path
+    head.zero_grad()
+    f2 = feats.to(dev).requires_grad_(True)
+    hm2 = head(f2)
+    kp2, _ = lpb.decode_softargmax(hm2, 2, 1000.0)
+    close(kp2, kp, atol=1e-4)
+    (kp2 * gk).sum().backward()
+    sc = float(f2.grad.float().abs().max())
+    assert float((g_fused - f2.grad.float()).abs().max()) <= 2e-2 * sc + 1e-9
+    wg = list(head.upsampling_layers)[1].weight.grad
+    assert float((w_fused - wg).abs().max()) <= 2e-2 * float(wg.abs().max()) + 1e-9
+
+
+@pytest.mark.parametrize("cfg", [("resnet50", 512, 17, 4, 6, 2, 2), ("vits_dino", 64, 5, 5, 7, 2, 2), ("resnet50", 256, 7, 3, 3, 1, 2)])
+def test_head_fp32_native_backward_any_depth(lpb, dev, cfg):
+    """fp32 precision path: 1-, 2- and 3-deconv heads (downsample_factor 1 on a stride-32 backbone -> 3 layers,
+    heads/heatmap.py:192-193) train through the native CUDA-core backward; no library convolution anywhere."""
+    from lightning_pose_b200.models.heads.heatmap import HeatmapHead
+
+    arch, cin, k, fh, fw, ds, b = cfg
+    torch.manual_seed(8)
+    head = HeatmapHead(arch, cin, k, downsample_factor=ds)
+    for layer in list(head.upsampling_layers)[1:]:
+        torch.nn.init.xavier_uniform_(layer.weight, gain=2.0)
+        torch.nn.init.uniform_(layer.bias, -0.2, 0.2)
+    deconvs = list(head.upsampling_layers)[1:]
+    feats = torch.randn(b, cin, fh, fw)
+    f_ref = feats.clone().requires_grad_(True)
+    ws = [d.weight.detach().clone().requires_grad_(True) for d in deconvs]
+    bs = [d.bias.detach().clone().requires_grad_(True) for d in deconvs]
+    ref = O.head_forward(f_ref, ws, bs)
+    gout = torch.randn_like(ref)
+    (ref * gout).sum().backward()
+    head = head.to(dev)
+    f = feats.to(dev).requires_grad_(True)
+    out = head(f)
+    close(out, ref, atol=1e-9)
+    (out * gout.to(dev)).sum().backward()
+    close(f.grad, f_ref.grad, atol=1e-7, rtol=1e-3)
+    for d, w_ref, b_ref in zip(deconvs, ws, bs):
+        close(d.weight.grad, w_ref.grad, atol=1e-7, rtol=1e-3)
+        close(d.bias.grad, b_ref.grad, atol=2e-6, rtol=1e-3)
