@@ -81,6 +81,13 @@ int lpb_generate_heatmaps(const float* keypoints, const int32_t* visibility, int
                           float img_height, float img_width, int oh, int ow, float sigma, float* out,
                           void* stream);
 
+/* the labeled-data rule that precedes target generation when targets are made on the GPU: keypoints an
+ * augmentation moved outside [0, width) x [0, height) become NaN in both coordinates
+ *   lightning_pose/data/datasets.py:496-508 (HeatmapDataset.compute_heatmap).  keypoints, out: [n_keypoints, 2]
+ * (may alias). */
+int lpb_keypoints_mask_oob(const float* keypoints, int64_t n_keypoints, float img_height, float img_width, float* out,
+                           void* stream);
+
 /* gradient of lpb_generate_heatmaps wrt keypoints (keep_gradients=True, data/heatmaps.py:37-40);
  * grad_out [n_planes,oh,ow] -> grad_keypoints [n_planes,2] */
 int lpb_generate_heatmaps_bwd(const float* keypoints, const int32_t* visibility, const float* grad_out,
@@ -170,6 +177,48 @@ int lpb_remap_keypoints(const float* keypoints_in, int64_t n, int K, const float
 int lpb_remap_keypoints_bwd(const float* grad_out, int64_t n, int K, const float* transforms, int per_frame,
                             int num_views, const float* bbox, int64_t n_bbox, float model_height, float model_width,
                             float* grad_in, void* stream);
+
+/* ---- MHCRNN context head ------------------------------------------------------------
+ * replaces UpsamplingCRNN.forward  lightning_pose/models/heads/heatmap_mhcrnn.py:268-316  and
+ * get_context_from_sequence  lightning_pose/models/base.py:159-196.
+ * H_f / H_b (grouped Conv2d k2 s2 -> grouped ConvTranspose2d k2 s2, no nonlinearity) are 4x4 affine maps per keypoint
+ * on 2x2 blocks:  lpb_crnn_prepare turns the four parameter tensors conv_w [K*F,1,2,2], conv_b [K*F], convt_w
+ * [K*F,1,2,2], convt_b [K] into L [K,4,4], h [K,4];  lpb_crnn_prepare_bwd maps (dL, dh) back to their gradients.
+ * lpb_crnn_combine_fwd: WF, WB [N, K, H, W] = W_f / W_b applied to each of N frames ONCE (head kernels), idx [M, 5] =
+ * frame index of each context slot of each of M outputs (overlapping windows share frames: no 5x feature tiling)
+ * -> out_logits [M, K, H, W] = (x_f + x_b) / 2 before the spatial softmax.  lpb_crnn_combine_bwd: its autograd
+ * (dWF, dWB [N,K,H,W], dLf/dLb [K,4,4], dhf/dhb [K,4]; all overwritten).  M * K < 65536 per call.
+ * lpb_context_gather: the materialised window tensor out[i][s] = seq[clamp(i + s - ctx/2)] for API parity
+ * (n items of item_bytes, a multiple of 16). */
+int lpb_crnn_prepare(const float* conv_w, const float* conv_b, const float* convt_w, const float* convt_b, int K, int F,
+                     float* L, float* h, void* stream);
+int lpb_crnn_prepare_bwd(const float* conv_w, const float* conv_b, const float* convt_w, const float* dL, const float* dh,
+                         int K, int F, float* d_conv_w, float* d_conv_b, float* d_convt_w, float* d_convt_b, void* stream);
+int lpb_crnn_combine_fwd(const float* WF, const float* WB, const int32_t* idx, int M, int N, int K, int H, int W,
+                         const float* Lf, const float* hf, const float* Lb, const float* hb, float* out_logits, void* stream);
+int lpb_crnn_combine_bwd(const float* WF, const float* WB, const int32_t* idx, const float* grad_logits, int M, int N, int K,
+                         int H, int W, const float* Lf, const float* hf, const float* Lb, const float* hb, float* dWF,
+                         float* dWB, float* dLf, float* dhf, float* dLb, float* dhb, void* stream);
+int lpb_context_gather(const void* seq, int64_t n, int64_t item_bytes, int ctx, void* out, void* stream);
+
+/* ---- video-ingest boundary ----------------------------------------------------------------
+ * replaces the tail of the DALI pipeline  lightning_pose/data/video/dali.py:157-197
+ *   fn.resize -> / 255 -> fn.crop_mirror_normalize(output_layout="FCHW", mean, std)
+ * frames_u8 [F, H, W, 3] decoded RGB (device) -> out [F, 3, out_h, out_w] (layout 0, the reference's FCHW) or
+ * [F, out_h, out_w, 3] (layout 1, channels-last), fp32 or bf16 (out_bf16).  mean3 / std3: HOST arrays of three floats
+ * in (0, 1) units (ImageNet statistics, dali.py:44-45).  Resize (when out size != input size): bilinear, half-pixel
+ * centres, no antialiasing. */
+int lpb_frames_normalize(const uint8_t* frames_u8, int F, int H, int W, int out_h, int out_w, const float* mean3,
+                         const float* std3, int layout, int out_bf16, void* out, void* stream);
+
+/* ---- batched inference ------------------------------------------------------------------
+ * replaces PredictionHandler.unpack_preds + make_pred_arr_undo_resize  lightning_pose/utils/predictions.py:97-144,180-206
+ * keypoints [n_frames, 2K], confidences [n_frames, K] of one chunk -> rows [r, r + n_frames) of the prediction table
+ * [n_rows, 3K] (columns bp0_x, bp0_y, bp0_likelihood, bp1_x, ...), r = *cursor (device int64, advanced by n_frames
+ * afterwards, so a captured chunk graph needs no host-side offset) or row0 when cursor is NULL.  Rows >= n_rows
+ * (padding frames of the last chunk) are dropped. */
+int lpb_pack_predictions(const float* keypoints, const float* confidences, int n_frames, int K, float* table,
+                         int64_t n_rows, int64_t* cursor, int64_t row0, void* stream);
 
 /* backward of the head's final spatial softmax: grad_logits = p * (g - sum(g * p)) per plane
  * (reference: autograd of spatial_softmax2d, lightning_pose/models/heads/heatmap.py:211) */

@@ -108,6 +108,32 @@ __global__ void evaluate_at_location_kernel(const float* __restrict__ heat, cons
 
 }  // namespace lpb
 
+namespace lpb {
+// labeled keypoints that an augmentation moved out of the frame become NaN (both coordinates), so that their target
+// plane is all-zero and the supervised losses skip them  (lightning_pose/data/datasets.py:496-508)
+__global__ void keypoints_mask_oob_kernel(const float* __restrict__ kp, int64_t n, float height, float width,
+                                          float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = kp[2 * i], y = kp[2 * i + 1];
+  const bool oob = x < 0.f || y < 0.f || x >= width || y >= height;
+  const float nanv = __int_as_float(0x7fc00000);
+  out[2 * i] = oob ? nanv : x;
+  out[2 * i + 1] = oob ? nanv : y;
+}
+}  // namespace lpb
+
+extern "C" int lpb_keypoints_mask_oob(const float* keypoints, int64_t n_keypoints, float img_height, float img_width,
+                                      float* out, void* stream) {
+  using namespace lpb;
+  LPB_REQUIRE(keypoints && out && n_keypoints >= 0 && img_height > 0.f && img_width > 0.f, "keypoints_mask_oob: bad arguments");
+  if (n_keypoints == 0) return LPB_OK;
+  keypoints_mask_oob_kernel<<<(unsigned)((n_keypoints + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      keypoints, n_keypoints, img_height, img_width, out);
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}
+
 extern "C" int lpb_generate_heatmaps(const float* keypoints, const int32_t* visibility, int64_t n_planes,
                                      float img_height, float img_width, int oh, int ow, float sigma, float* out,
                                      void* stream) {

@@ -26,6 +26,7 @@ import torch
 from torch.nn import functional as F
 
 from lightning_pose_b200 import ops
+from lightning_pose_b200.data.heatmaps import GaussianTargets
 from lightning_pose_b200.utils.pca import KeypointPCA
 
 __all__ = [
@@ -110,6 +111,12 @@ class HeatmapLoss(Loss):
         stage: Literal["train", "val", "test"] | None = None,
         **kwargs: Any,
     ) -> LossOutput:
+        if isinstance(heatmaps_targ, GaussianTargets):  # targets made on the GPU from (keypoints, visibility)
+            if self._kind == "mse":  # one kernel, target planes never written
+                scalar_loss = ops.heatmap_mse_from_keypoints(heatmaps_targ.keypoints, heatmaps_pred, heatmaps_targ.height, heatmaps_targ.width,
+                                                             sigma=heatmaps_targ.sigma, visibility=heatmaps_targ.visibility)
+                return scalar_loss, self.log_loss(loss=scalar_loss, stage=stage)
+            heatmaps_targ = heatmaps_targ.materialize()
         scalar_loss = ops.heatmap_loss(heatmaps_targ, heatmaps_pred, self._kind)
         return scalar_loss, self.log_loss(loss=scalar_loss, stage=stage)
 

@@ -21,6 +21,7 @@ from torch import nn
 
 from lightning_pose_b200 import ops
 from lightning_pose_b200.data.bboxes import model_to_frame_batch
+from lightning_pose_b200.data.heatmaps import GaussianTargets
 from lightning_pose_b200.losses.factory import LossFactory
 from lightning_pose_b200.losses.losses import RegressionRMSELoss
 from lightning_pose_b200.models.datatypes import HeatmapTrackerLabeledOutputsDict, HeatmapTrackerUnlabeledOutputsDict
@@ -102,9 +103,22 @@ class HeatmapTracker(nn.Module):
     def get_loss_inputs_labeled(self, batch_dict: dict) -> HeatmapTrackerLabeledOutputsDict:
         predicted_heatmaps, predicted_keypoints, confidence = self.forward_with_keypoints(batch_dict["images"])
         predicted_keypoints = model_to_frame_batch(batch_dict, predicted_keypoints)
-        target_keypoints = model_to_frame_batch(batch_dict, batch_dict["keypoints"])
+        keypoints = batch_dict["keypoints"]
+        if "heatmaps" in batch_dict:  # reference flow: DataLoader workers rendered the targets (data/datasets.py:516)
+            heatmaps_targ = batch_dict["heatmaps"]
+        else:
+            # on-GPU target pipeline: the batch ships (keypoints, visibility) only; the supervised loss
+            # renders the Gaussians itself (HeatmapMSELoss: fused with the loss, planes never written).  The
+            # out-of-frame -> NaN rule of HeatmapDataset.compute_heatmap is applied on the device and, as there
+            # (in-place on the example's keypoints), also reaches the RMSE targets.
+            images = batch_dict["images"]
+            h_img, w_img = images.shape[-2], images.shape[-1]
+            shape_hm = (h_img // 2**self.downsample_factor, w_img // 2**self.downsample_factor)
+            heatmaps_targ = GaussianTargets(keypoints, h_img, w_img, shape_hm, sigma=1.25, visibility=batch_dict.get("visibility"))
+            keypoints = heatmaps_targ.keypoints.reshape(keypoints.shape)
+        target_keypoints = model_to_frame_batch(batch_dict, keypoints, in_place="heatmaps" in batch_dict)
         return {
-            "heatmaps_targ": batch_dict["heatmaps"],
+            "heatmaps_targ": heatmaps_targ,
             "heatmaps_pred": predicted_heatmaps,
             "keypoints_targ": target_keypoints,
             "keypoints_pred": predicted_keypoints,

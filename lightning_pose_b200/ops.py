@@ -16,6 +16,7 @@ __all__ = [
     "decode_softargmax",
     "upsample2x",
     "generate_heatmaps",
+    "keypoints_mask_oob",
     "evaluate_heatmaps_at_location",
     "head_forward",
     "head_forward_f32",
@@ -158,6 +159,15 @@ def generate_heatmaps(keypoints, height, width, output_shape, sigma=1.25, keep_g
     if not keep_gradients:
         kp = kp.detach()
     return _GenerateHeatmaps.apply(kp, vis, height, width, int(output_shape[0]), int(output_shape[1]), sigma)
+
+
+def keypoints_mask_oob(keypoints, height, width):
+    """Keypoints outside [0, width) x [0, height) -> NaN in both coordinates (labeled-data rule, datasets.py:496-508)."""
+    kp = _cuda_f32(keypoints, "keypoints")
+    out = torch.empty_like(kp)
+    with torch.cuda.device(kp.device):
+        check(lib.lpb_keypoints_mask_oob(_ptr(kp), kp.numel() // 2, float(height), float(width), _ptr(out), _stream()))
+    return out
 
 
 def evaluate_heatmaps_at_location(heatmaps, locs, radius: int = 2):
@@ -384,6 +394,134 @@ def remap_keypoints(keypoints, transforms, bbox, model_height, model_width, is_m
     if out is not None and kp.requires_grad:
         out = None  # writing through a tensor that autograd tracks is not allowed; return a fresh one
     return _Remap.apply(kp, tf, per_frame, int(num_views), bb, float(model_height), float(model_width), out)
+
+
+# =====================================================================================
+# MHCRNN context branch
+# =====================================================================================
+class _CrnnCombine(torch.autograd.Function):
+    """(x_f + x_b) / 2 of the bidirectional conv-RNN, from per-frame deconv maps and a window index table."""
+
+    @staticmethod
+    def forward(ctx, wf, wb, idx, cwf, cbf, twf, tbf, cwb, cbb, twb, tbb):
+        n, k, h, w = wf.shape
+        m = idx.shape[0]
+        f = cwf.shape[0] // k
+        dev = wf.device
+        Lf, hf = torch.empty((k, 16), device=dev), torch.empty((k, 4), device=dev)
+        Lb, hb = torch.empty((k, 16), device=dev), torch.empty((k, 4), device=dev)
+        out = torch.empty((m, k, h, w), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(lib.lpb_crnn_prepare(_ptr(cwf), _ptr(cbf), _ptr(twf), _ptr(tbf), k, f, _ptr(Lf), _ptr(hf), _stream()))
+            check(lib.lpb_crnn_prepare(_ptr(cwb), _ptr(cbb), _ptr(twb), _ptr(tbb), k, f, _ptr(Lb), _ptr(hb), _stream()))
+            check(lib.lpb_crnn_combine_fwd(_ptr(wf), _ptr(wb), _ptr(idx), m, n, k, h, w, _ptr(Lf), _ptr(hf), _ptr(Lb), _ptr(hb), _ptr(out), _stream()))
+        ctx.save_for_backward(wf, wb, idx, cwf, cbf, twf, cwb, cbb, twb, Lf, hf, Lb, hb)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        wf, wb, idx, cwf, cbf, twf, cwb, cbb, twb, Lf, hf, Lb, hb = ctx.saved_tensors
+        n, k, h, w = wf.shape
+        m = idx.shape[0]
+        f = cwf.shape[0] // k
+        dev = wf.device
+        g = g.contiguous().float()
+        dwf, dwb = torch.empty_like(wf), torch.empty_like(wb)
+        dLf, dhf, dLb, dhb = torch.empty_like(Lf), torch.empty_like(hf), torch.empty_like(Lb), torch.empty_like(hb)
+        outs = [torch.empty_like(t) for t in (cwf, cbf, twf)] + [torch.empty((k,), device=dev)] + [torch.empty_like(t) for t in (cwb, cbb, twb)] + [torch.empty((k,), device=dev)]
+        with torch.cuda.device(dev):
+            check(lib.lpb_crnn_combine_bwd(_ptr(wf), _ptr(wb), _ptr(idx), _ptr(g), m, n, k, h, w, _ptr(Lf), _ptr(hf), _ptr(Lb), _ptr(hb),
+                                           _ptr(dwf), _ptr(dwb), _ptr(dLf), _ptr(dhf), _ptr(dLb), _ptr(dhb), _stream()))
+            check(lib.lpb_crnn_prepare_bwd(_ptr(cwf), _ptr(cbf), _ptr(twf), _ptr(dLf), _ptr(dhf), k, f, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), _stream()))
+            check(lib.lpb_crnn_prepare_bwd(_ptr(cwb), _ptr(cbb), _ptr(twb), _ptr(dLb), _ptr(dhb), k, f, _ptr(outs[4]), _ptr(outs[5]), _ptr(outs[6]), _ptr(outs[7]), _stream()))
+        return (dwf, dwb, None, *outs)
+
+
+def crnn_combine(wf, wb, idx, h_f_params, h_b_params):
+    """Pre-softmax MHCRNN logits (M, K, H, W).  ``wf`` / ``wb``: (N, K, H, W) maps W_f(x_t) / W_b(x_t) of N frames;
+    ``idx``: (M, 5) int32 frame indices of the context slots; ``h_*_params`` = (conv.weight, conv.bias, convT.weight,
+    convT.bias) of ``H_f`` / ``H_b``.  Differentiable in the maps and in the eight parameter tensors."""
+    wf, wb = _cuda_f32(wf, "wf"), _cuda_f32(wb, "wb")
+    if wf.shape != wb.shape or wf.dim() != 4 or wf.shape[2] % 2 or wf.shape[3] % 2:
+        raise ValueError(f"deconv maps must be (N, K, H, W) with even H, W; got {tuple(wf.shape)} / {tuple(wb.shape)}")
+    idx = idx.to(device=wf.device, dtype=torch.int32).contiguous()
+    if idx.dim() != 2 or idx.shape[1] != 5:
+        raise ValueError(f"idx must be (M, 5); got {tuple(idx.shape)}")
+    ps = [_cuda_f32(t, "crnn parameter") for t in (*h_f_params, *h_b_params)]
+    k = wf.shape[1]
+    if idx.shape[0] * k >= 65536:  # grid.y limit of one launch: split the windows
+        parts = [_CrnnCombine.apply(wf, wb, idx[i : i + 65535 // k], *ps) for i in range(0, idx.shape[0], 65535 // k)]
+        return torch.cat(parts, dim=0)
+    return _CrnnCombine.apply(wf, wb, idx, *ps)
+
+
+class _PlaneSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits):
+        p = logits.contiguous().float().clone()
+        plane_softmax_(p)
+        ctx.save_for_backward(p)
+        return p
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        return plane_softmax_backward(p, g)
+
+
+def plane_softmax(logits: torch.Tensor) -> torch.Tensor:
+    """spatial_softmax2d(x, temperature=1) with its native backward."""
+    return _PlaneSoftmax.apply(_cuda_f32(logits, "logits"))
+
+
+def context_gather(seq: torch.Tensor, context_length: int = 5) -> torch.Tensor:
+    """get_context_from_sequence (base.py:159-196): (n, ...) -> (n, ctx, ...) windows with replicated edges."""
+    if not isinstance(seq, torch.Tensor) or not seq.is_cuda:
+        raise RuntimeError("lpb200: `img_seq` must be a CUDA tensor (this package has no CPU fallback)")
+    x = seq.contiguous()
+    n = x.shape[0]
+    item = x[0].numel() * x.element_size()
+    if item % 16:
+        raise ValueError(f"items of {item} bytes: the gather moves 16-byte vectors")
+    out = torch.empty((n, context_length, *x.shape[1:]), device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        check(lib.lpb_context_gather(_ptr(x), n, item, int(context_length), _ptr(out), _stream()))
+    return out
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # lightning_pose/data/__init__.py (_IMAGENET_MEAN / _IMAGENET_STD)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def frames_normalize(frames_u8, size=None, mean=IMAGENET_MEAN, std=IMAGENET_STD, channels_last=False, dtype=torch.float32):
+    """uint8 (F, H, W, 3) decoded RGB frames -> normalised (F, 3, h, w) [or (F, h, w, 3)] fp32 / bf16 in one pass."""
+    if not isinstance(frames_u8, torch.Tensor) or not frames_u8.is_cuda:
+        raise RuntimeError("lpb200: `frames` must be a CUDA tensor (this package has no CPU fallback)")
+    if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3:
+        raise ValueError(f"frames must be uint8 (F, H, W, 3); got {tuple(frames_u8.shape)} {frames_u8.dtype}")
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("dtype must be float32 or bfloat16")
+    x = frames_u8.contiguous()
+    f, h, w, _ = x.shape
+    oh, ow = (int(size[0]), int(size[1])) if size is not None else (h, w)
+    out = torch.empty((f, oh, ow, 3) if channels_last else (f, 3, oh, ow), device=x.device, dtype=dtype)
+    m3, s3 = (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std])
+    with torch.cuda.device(x.device):
+        check(lib.lpb_frames_normalize(_ptr(x), f, h, w, oh, ow, m3, s3, int(bool(channels_last)), int(dtype == torch.bfloat16), _ptr(out), _stream()))
+    return out
+
+
+def pack_predictions(keypoints, confidences, table, cursor=None, row0: int = 0):
+    """Write one chunk's (keypoints (T, 2K), confidences (T, K)) into rows of ``table`` (N, 3K) at the device cursor
+    (int64 tensor, advanced by T) or at ``row0``.  Mutates ``table`` (and ``cursor``)."""
+    kp = _cuda_f32(keypoints, "keypoints")
+    cf = _cuda_f32(confidences, "confidences")
+    t, k = cf.shape
+    if table.dtype != torch.float32 or not table.is_contiguous() or table.shape[1] != 3 * k:
+        raise ValueError(f"table must be contiguous fp32 (N, {3 * k}); got {tuple(table.shape)} {table.dtype}")
+    with torch.cuda.device(kp.device):
+        check(lib.lpb_pack_predictions(_ptr(kp), _ptr(cf), t, k, _ptr(table), table.shape[0], _ptr(cursor), int(row0), _stream()))
+    return table
 
 
 def plane_softmax_backward(probs: torch.Tensor, grad_probs: torch.Tensor) -> torch.Tensor:

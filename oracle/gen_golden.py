@@ -328,6 +328,55 @@ def gen_losses(ll, lf, dh, pca_mod):
     return g
 
 
+def _mhcrnn_params(head):
+    m = head.head_mf
+    p = {"W_f": (m.W_f.weight, m.W_f.bias), "W_b": (m.W_b.weight, m.W_b.bias),
+         "H_f": (m.H_f[0].weight, m.H_f[0].bias, m.H_f[1].weight, m.H_f[1].bias),
+         "H_b": (m.H_b[0].weight, m.H_b[0].bias, m.H_b[1].weight, m.H_b[1].bias)}
+    if m.upsampling_factor == 2:
+        p["W_pre"] = (m.W_pre.weight, m.W_pre.bias)
+    return p
+
+
+def gen_mhcrnn(mh, base_src_path):
+    """HeatmapMHCRNNHead / UpsamplingCRNN (heads/heatmap_mhcrnn.py) and get_context_from_sequence (models/base.py:159-196;
+    base.py itself needs Lightning to import, so that one function is executed from its source text)."""
+    import ast
+    import textwrap
+
+    g = {}
+    src = open(base_src_path).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "get_context_from_sequence")
+    code = "\n".join(src.splitlines()[fn.lineno - 1 : fn.end_lineno])
+    code = textwrap.dedent(code)
+    # strip the jaxtyping annotations of the signature (not importable pieces of base.py's header)
+    body_start = code.index('"""')
+    code = "def get_context_from_sequence(img_seq, context_length):\n    " + code[body_start:]
+    ns = {"torch": torch}
+    exec(code, ns)
+    gen = torch.Generator().manual_seed(51)
+    seq = torch.randn(7, 3, 4, 4, generator=gen)
+    out = ns["get_context_from_sequence"](seq, 5)
+    g["ctx_in_seq"], g["ctx_out_windows"] = _np(seq), _np(out)
+    _check("get_context_from_sequence", out, O.context_windows(seq, 5))
+    for tag, arch, cin, uf in (("vit", "vits_dino", 64, 1), ("resnet", "resnet50", 64, 2)):
+        torch.manual_seed(52)
+        head = mh.HeatmapMHCRNNHead(arch, cin, 5, upsampling_factor=uf)
+        for prm in head.head_sf.parameters():  # peaked, non-degenerate maps
+            torch.nn.init.normal_(prm, std=0.3)
+        feats = torch.randn(3, cin, 4, 6, 5, generator=gen)
+        sf, mf = head(feats, torch.Size([3, 5, 3, 64, 96]), False)
+        g[f"{tag}_in_features"] = _np(feats)
+        for name, t in head.state_dict().items():
+            if ".layers." not in name:  # ModuleList aliases of the same tensors
+                g[f"{tag}_param_{name}"] = _np(t)
+        g[f"{tag}_out_sf"], g[f"{tag}_out_mf"] = _np(sf), _np(mf)
+        _check(f"mhcrnn multi-frame {tag}", mf, O.mhcrnn_multiframe(feats.permute(4, 0, 1, 2, 3), _mhcrnn_params(head), uf))
+        d = list(head.head_sf.upsampling_layers)[1:]
+        _check(f"mhcrnn single-frame {tag}", sf, O.head_forward(feats[..., 2], [x.weight for x in d], [x.bias for x in d]))
+    return g
+
+
 def main():
     assert R.reference_available(), "needs /root/reference (authoring container only)"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -338,6 +387,7 @@ def main():
     du = R.load("lightning_pose.data.utils")
     db = R.load("lightning_pose.data.bboxes")
     pm = R.load("lightning_pose.utils.pca")
+    mh = R.load("lightning_pose.models.heads.heatmap_mhcrnn")
     with torch.no_grad():
         groups = {
             "decode": gen_decode(hm, dh),
@@ -345,6 +395,7 @@ def main():
             "head": gen_head(hm),
             "remap": gen_remap(du, db),
             "losses": gen_losses(ll, lf, dh, pm),
+            "mhcrnn": gen_mhcrnn(mh, os.path.join(R.REF_ROOT, "lightning_pose", "models", "base.py")),
         }
     for name, arrays in groups.items():
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")

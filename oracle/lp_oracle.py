@@ -124,6 +124,44 @@ def head_forward(
     return x
 
 
+def context_windows(seq: torch.Tensor, context_length: int = 5) -> torch.Tensor:
+    """(n, ...) -> (n, ctx, ...): window i = padded[i : i + ctx], padded = [s0, s0, s..., s_last, s_last].
+
+    lightning_pose/models/base.py:159-196 (get_context_from_sequence; the result there is always float32).
+    """
+    n = seq.shape[0]
+    half = context_length // 2
+    idx = (torch.arange(n)[:, None] + torch.arange(context_length)[None, :] - half).clamp(0, n - 1)
+    return seq[idx].float()
+
+
+def mhcrnn_multiframe(features: torch.Tensor, p: dict, upsampling_factor: int) -> torch.Tensor:
+    """UpsamplingCRNN.forward: features (frames, batch, C, h, w) -> softmaxed heatmaps (batch, K, H, W).
+
+    lightning_pose/models/heads/heatmap_mhcrnn.py:268-316.  ``p``: W_pre (w, b) [upsampling_factor 2 only], W_f, W_b
+    (ConvTranspose2d k3 s2 p1 op1), H_f / H_b = (conv_w, conv_b, convt_w, convt_b) with groups = K, kernel = stride = 2.
+    """
+    frames, batch = features.shape[:2]
+    k = p["W_f"][0].shape[1]
+    ct = lambda x, wb: F.conv_transpose2d(x, wb[0], wb[1], stride=2, padding=1, output_padding=1)
+    x = F.pixel_shuffle(features.reshape(frames * batch, *features.shape[2:]), 2)
+    if upsampling_factor == 2:
+        x = ct(x, p["W_pre"])
+    x = x.reshape(frames, batch, *x.shape[1:])
+
+    def hidden(z, hp):
+        z = F.conv2d(z, hp[0], hp[1], stride=2, groups=k)
+        return F.conv_transpose2d(z, hp[2], hp[3], stride=2, groups=k)
+
+    xf = ct(x[0], p["W_f"])
+    for t in range(1, frames):
+        xf = ct(x[t], p["W_f"]) + hidden(xf, p["H_f"])
+    xb = ct(x[frames - 1], p["W_b"])
+    for t in range(frames - 2, -1, -1):
+        xb = ct(x[t], p["W_b"]) + hidden(xb, p["H_b"])
+    return spatial_softmax2d((xf + xb) / 2, 1.0)
+
+
 # --------------------------------------------------------------------------------------
 # a3/a4/a5: soft-argmax decode (heads/heatmap.py:86-144, data/heatmaps.py:90-142)
 # --------------------------------------------------------------------------------------

@@ -119,6 +119,9 @@ def install() -> None:
 
     fac = importlib.import_module("lightning_pose.models.backbones.factory")
     sys.modules["lightning_pose.models.backbones"].BACKBONE_STRIDES = fac.BACKBONE_STRIDES  # type: ignore
+    # heads/__init__ re-exports HeatmapHead (heatmap_mhcrnn.py imports it from the package)
+    hm = importlib.import_module("lightning_pose.models.heads.heatmap")
+    sys.modules["lightning_pose.models.heads"].HeatmapHead = hm.HeatmapHead  # type: ignore
 
 
 def load(name: str) -> types.ModuleType:

@@ -829,3 +829,203 @@ def test_head_fp32_native_backward_any_depth(lpb, dev, cfg):
     for d, w_ref, b_ref in zip(deconvs, ws, bs):
         close(d.weight.grad, w_ref.grad, atol=1e-7, rtol=1e-3)
         close(d.bias.grad, b_ref.grad, atol=2e-6, rtol=1e-3)
+
+
+@pytest.mark.parametrize("size", [None, (64, 96), (50, 70)])
+@pytest.mark.parametrize("dtype,channels_last", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)])
+def test_video_ingest_boundary(lpb, dev, size, dtype, channels_last):
+    """f4: uint8 frames -> normalised FCHW (reference dali.py:157-197: resize, /255, crop_mirror_normalize)."""
+    import torch.nn.functional as F
+    from lightning_pose_b200.data.video import frames_to_unlabeled_batch
+
+    torch.manual_seed(2)
+    u8 = torch.randint(0, 256, (5, 100, 140, 3), dtype=torch.uint8)
+    x = u8.permute(0, 3, 1, 2).float()
+    if size is not None:
+        x = F.interpolate(x, size=size, mode="bilinear", align_corners=False, antialias=False)
+    mean, std = torch.tensor(lpb.IMAGENET_MEAN).view(1, 3, 1, 1), torch.tensor(lpb.IMAGENET_STD).view(1, 3, 1, 1)
+    ref = (x / 255.0 - mean) / std
+    bd = frames_to_unlabeled_batch(u8.to(dev), resize_dims=size, dtype=dtype, channels_last=channels_last)
+    got = bd["frames"].float().cpu()
+    if channels_last:
+        got = got.permute(0, 3, 1, 2)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    close(got, ref, atol=tol, rtol=1e-4 if dtype == torch.float32 else 1e-2)
+    assert bd["is_multiview"] is False and bd["transforms"].tolist() == [-1.0]
+    close(bd["bbox"], torch.tensor([[0.0, 0.0, 100.0, 140.0]]).repeat(5, 1))
+    mv = frames_to_unlabeled_batch([u8.to(dev), u8.flip(0).to(dev)], resize_dims=size, dtype=dtype)
+    assert mv["is_multiview"] and mv["frames"].shape[:3] == (5, 2, 3) and mv["bbox"].shape == (5, 8) and mv["transforms"].shape == (2, 1)
+
+
+def test_tracker_on_gpu_target_pipeline(lpb, dev):
+    """f2: a labeled batch that ships (keypoints, visibility) only - targets rendered inside the supervised loss - gives
+    the loss / gradients of the reference flow (worker-rendered ``heatmaps``), out-of-frame rule included."""
+    from lightning_pose_b200.losses.factory import LossFactory
+    from lightning_pose_b200.models.heatmap_tracker import HeatmapTracker
+
+    torch.manual_seed(12)
+    k, b, img = 6, 3, 64
+
+    class Backbone(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 64, 3, stride=32, padding=1)
+
+        def forward(self, x):
+            return self.conv(x)
+
+    def make():
+        torch.manual_seed(77)
+        t = HeatmapTracker(k, loss_factory=LossFactory({"heatmap_mse": {"log_weight": 0.0}}, None), backbone=Backbone(), num_fc_input_features=64).to(dev)
+        for layer in list(t.head.upsampling_layers)[1:]:
+            torch.nn.init.xavier_uniform_(layer.weight, gain=2.0)
+        return t
+
+    images = torch.randn(b, 3, img, img)
+    kp = torch.rand(b, k, 2) * img
+    kp[0, 1] = torch.tensor([-3.0, 10.0])   # moved out of the frame by an augmentation -> NaN -> zero plane
+    kp[1, 2] = torch.tensor([20.0, 64.0])   # y == height is out
+    kp[2, 0] = float("nan")
+    vis = torch.randint(0, 3, (b, k))
+    bbox = torch.tensor([[0.0, 0.0, float(img), float(img)]]).repeat(b, 1)
+    kp_masked = kp.clone()
+    oob = (kp[..., 0] < 0) | (kp[..., 1] < 0) | (kp[..., 0] >= img) | (kp[..., 1] >= img)
+    kp_masked[oob] = float("nan")
+    targets = O.gaussian_targets(kp_masked, img, img, (16, 16), visibility=vis)
+    t_ref = make()
+    l_ref = t_ref.evaluate_labeled({"images": images.to(dev), "keypoints": kp_masked.reshape(b, -1).to(dev).clone(), "heatmaps": targets.to(dev), "bbox": bbox.to(dev)}, "train", 1.0)
+    l_ref.backward()
+    t_new = make()
+    l_new = t_new.evaluate_labeled({"images": images.to(dev), "keypoints": kp.reshape(b, -1).to(dev).clone(), "visibility": vis.to(dev), "bbox": bbox.to(dev)}, "train", 1.0)
+    l_new.backward()
+    close(l_new, l_ref, atol=1e-7)
+    for p_new, p_ref in zip(t_new.parameters(), t_ref.parameters()):
+        close(p_new.grad, p_ref.grad, atol=1e-7, rtol=1e-3)
+    close(t_new.last_rmse, t_ref.last_rmse, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# MHCRNN context head (a17 / a18 / f3)
+# ------------------------------------------------------------------------------------------------
+def _load_mhcrnn(g, tag, arch, cin, uf, dev):
+    from lightning_pose_b200.models.heads.heatmap_mhcrnn import HeatmapMHCRNNHead
+
+    head = HeatmapMHCRNNHead(arch, cin, 5, upsampling_factor=uf)
+    sd = {k[len(f"{tag}_param_"):]: T(g[k]) for k in g.files if k.startswith(f"{tag}_param_")}
+    for k in list(sd):  # the ModuleList aliases share storage with the named modules
+        pass
+    missing, unexpected = head.load_state_dict(sd, strict=False)
+    assert not unexpected and all(".layers." in m for m in missing), (missing, unexpected)
+    return head.to(dev)
+
+
+def _mhcrnn_oracle_params(head):
+    m = head.head_mf
+    c = lambda t: t.detach().cpu().clone()
+    p = {"W_f": (c(m.W_f.weight), c(m.W_f.bias)), "W_b": (c(m.W_b.weight), c(m.W_b.bias)),
+         "H_f": tuple(c(t) for t in (m.H_f[0].weight, m.H_f[0].bias, m.H_f[1].weight, m.H_f[1].bias)),
+         "H_b": tuple(c(t) for t in (m.H_b[0].weight, m.H_b[0].bias, m.H_b[1].weight, m.H_b[1].bias))}
+    if m.upsampling_factor == 2:
+        p["W_pre"] = (c(m.W_pre.weight), c(m.W_pre.bias))
+    return p
+
+
+def test_context_gather_golden(lpb, dev, golden):
+    g = golden("mhcrnn")
+    from lightning_pose_b200.models.heads.heatmap_mhcrnn import get_context_from_sequence
+
+    out = get_context_from_sequence(T(g["ctx_in_seq"]).to(dev), 5)
+    close(out, g["ctx_out_windows"], atol=0, rtol=0)
+
+
+@pytest.mark.parametrize("tag,arch,uf", [("vit", "vits_dino", 1), ("resnet", "resnet50", 2)])
+def test_mhcrnn_head_golden(lpb, dev, golden, tag, arch, uf):
+    """HeatmapMHCRNNHead.forward against the outputs of the reference's own module (heads/heatmap_mhcrnn.py), and the
+    fused video form against the reference call form on materialised windows."""
+    g = golden("mhcrnn")
+    head = _load_mhcrnn(g, tag, arch, 64, uf, dev)
+    feats = T(g[f"{tag}_in_features"]).to(dev)
+    sf, mf = head(feats, torch.Size([3, 5, 3, 64, 96]), False)
+    close(sf, g[f"{tag}_out_sf"], atol=1e-8)
+    close(mf, g[f"{tag}_out_mf"], atol=1e-8)
+    close(mf.sum((2, 3)), torch.ones(3, 5), atol=1e-5)
+    # video form: T = 9 frames -> 5 valid outputs; equals the call form on get_context_from_sequence(...)[2:-2]
+    torch.manual_seed(6)
+    seq = torch.randn(9, 64, 4, 6, device=dev)
+    sf_s, mf_s = head.forward_sequence(seq)
+    win = lpb.context_gather(seq, 5)[2:-2]  # (5, 5, C, h, w)
+    sf_w, mf_w = head(win.permute(0, 2, 3, 4, 1).contiguous(), torch.Size([9, 3, 64, 96]), False)
+    close(sf_s, sf_w, atol=0, rtol=0)
+    close(mf_s, mf_w, atol=1e-9, rtol=1e-6)
+
+
+@pytest.mark.parametrize("tag,arch,uf", [("vit", "vits_dino", 1), ("resnet", "resnet50", 2)])
+def test_mhcrnn_backward_vs_oracle_autograd(lpb, dev, golden, tag, arch, uf):
+    g = golden("mhcrnn")
+    head = _load_mhcrnn(g, tag, arch, 64, uf, dev)
+    p = _mhcrnn_oracle_params(head)
+    leaves = []
+    for key, tup in p.items():
+        p[key] = tuple(t.requires_grad_(True) for t in tup)
+        leaves += list(p[key])
+    torch.manual_seed(9)
+    seq = torch.randn(8, 64, 4, 6)
+    gout = torch.randn(4, 5, 16 if uf == 1 else 32, 24 if uf == 1 else 48)
+    f_ref = seq.clone().requires_grad_(True)
+    win = O.context_windows(f_ref, 5)[2:-2]  # (4, 5, C, h, w) -> frames first
+    mf_ref = O.mhcrnn_multiframe(win.permute(1, 0, 2, 3, 4), p, uf)
+    (mf_ref * gout).sum().backward()
+    f = seq.to(dev).requires_grad_(True)
+    _, mf = head.forward_sequence(f)
+    close(mf, mf_ref, atol=1e-8)
+    (mf * gout.to(dev)).sum().backward()
+    close(f.grad, f_ref.grad, atol=1e-7, rtol=2e-3)
+    m = head.head_mf
+    mods = {"W_f": [m.W_f], "W_b": [m.W_b], "H_f": [m.H_f[0], m.H_f[1]], "H_b": [m.H_b[0], m.H_b[1]]}
+    if uf == 2:
+        mods["W_pre"] = [m.W_pre]
+    for key, ms in mods.items():
+        got = [t for mod in ms for t in (mod.weight.grad, mod.bias.grad)]
+        for a, b in zip(got, p[key]):
+            close(a, b.grad, atol=2e-6, rtol=2e-3)
+
+
+def test_mhcrnn_bf16_real_shape_and_tracker(lpb, dev):
+    """config 3: ViT-S features (384, 16, 16) of a 256x256 clip, bf16, through the tcgen05 deconv maps + recurrence kernel."""
+    from lightning_pose_b200.models.heatmap_tracker_mhcrnn import SemiSupervisedHeatmapTrackerMHCRNN
+    from lightning_pose_b200.losses.factory import LossFactory
+
+    torch.manual_seed(21)
+    k, t = 17, 12
+
+    class Feats(torch.nn.Module):  # stands in for ViT-S: (n, 3, 256, 256) -> (n, 384, 16, 16) bf16
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 384, 16, stride=16)
+
+        def forward(self, x):
+            return self.conv(x).bfloat16()
+
+    tr = SemiSupervisedHeatmapTrackerMHCRNN(
+        k, loss_factory=LossFactory({"heatmap_mse": {"log_weight": 0.0}}, None),
+        loss_factory_unsupervised=LossFactory({"temporal": {"log_weight": 5.0, "epsilon": 5.0, "prob_threshold": 0.05}}, None),
+        backbone=Feats(), backbone_arch="vits_dino", num_fc_input_features=384).to(dev)
+    frames = torch.randn(t, 3, 256, 256, device=dev)
+    with torch.no_grad():
+        feats = tr.backbone(frames)
+        sf, mf = tr.head.forward_sequence(feats)
+    assert sf.shape == mf.shape == (t - 4, k, 64, 64)
+    p = _mhcrnn_oracle_params(tr.head)
+    r = lambda x: x.bfloat16().float()
+    p_r = {key: tuple(r(x) if x.dim() == 4 and key.startswith("W") else x for x in tup) for key, tup in p.items()}
+    win = O.context_windows(feats.float().cpu(), 5)[2:-2]
+    mf_ref = O.mhcrnn_multiframe(win.permute(1, 0, 2, 3, 4), p_r, 1)
+    rel = ((mf.cpu() - mf_ref).abs() / (mf_ref.abs() + 1e-7)).flatten()
+    assert float(rel.max()) < 3e-2 and float((rel > 1e-2).float().mean()) < 1e-4
+    # one semi-supervised step runs end to end and reaches the backbone
+    bbox = torch.tensor([[0.0, 0.0, 256.0, 256.0]], device=dev).repeat(t, 1)
+    loss = tr.evaluate_unlabeled({"frames": frames, "transforms": torch.tensor([-1.0], device=dev), "bbox": bbox, "is_multiview": False}, "train", 1.0)
+    loss.backward()
+    assert torch.isfinite(loss) and tr.backbone.conv.weight.grad is not None and torch.isfinite(tr.backbone.conv.weight.grad).all()
+    kp, cf = tr.predict_step({"frames": frames, "bbox": bbox}, 0)
+    assert kp.shape == (t - 4, 2 * k) and cf.shape == (t - 4, k)

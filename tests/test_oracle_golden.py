@@ -217,3 +217,22 @@ def test_kat_factory_anneal_exemption():
     close(O.combine_losses(losses, 1.0), w + w + 2 * O.loss_weight(np.log(2.0)))
     close(O.combine_losses(losses, 0.0), w)           # only the heatmap loss survives anneal_weight = 0
     close(O.combine_losses(losses, 0.25), w + 0.25 * (w + 2 * O.loss_weight(np.log(2.0))))
+
+
+def test_mhcrnn_oracle_matches_reference_goldens(golden):
+    """heads/heatmap_mhcrnn.py (UpsamplingCRNN / HeatmapMHCRNNHead) and models/base.py:159-196 (context windows)."""
+    g = golden("mhcrnn")
+    close(O.context_windows(T(g["ctx_in_seq"]), 5), g["ctx_out_windows"])
+    for tag, uf in (("vit", 1), ("resnet", 2)):
+        pr = lambda n: T(g[f"{tag}_param_head_mf.{n}"])
+        p = {"W_f": (pr("W_f.weight"), pr("W_f.bias")), "W_b": (pr("W_b.weight"), pr("W_b.bias")),
+             "H_f": (pr("H_f.0.weight"), pr("H_f.0.bias"), pr("H_f.1.weight"), pr("H_f.1.bias")),
+             "H_b": (pr("H_b.0.weight"), pr("H_b.0.bias"), pr("H_b.1.weight"), pr("H_b.1.bias"))}
+        if uf == 2:
+            p["W_pre"] = (pr("W_pre.weight"), pr("W_pre.bias"))
+        feats = T(g[f"{tag}_in_features"])
+        close(O.mhcrnn_multiframe(feats.permute(4, 0, 1, 2, 3), p, uf), g[f"{tag}_out_mf"], atol=1e-8)
+        n = 1 if uf == 1 else 2
+        ws = [T(g[f"{tag}_param_head_sf.upsampling_layers.{i + 1}.weight"]) for i in range(n)]
+        bs = [T(g[f"{tag}_param_head_sf.upsampling_layers.{i + 1}.bias"]) for i in range(n)]
+        close(O.head_forward(feats[..., 2], ws, bs), g[f"{tag}_out_sf"], atol=1e-8)
