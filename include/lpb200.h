@@ -38,6 +38,15 @@ int lpb_version(void);                /* e.g. 100 = 0.1.0 */
 const char* lpb_last_error(void);     /* message of the last failing call on this thread */
 const char* lpb_build_arch(void);     /* "sm_100a" */
 
+/* kernel-variant switches: a bring-up / profiling aid (A/B two implementations of the same stage on the same inputs);
+ * every variant computes the same results.  lpb_get_tuning returns -1 for an unknown key. */
+#define LPB_TUNE_K1A_ROW_TRANSPOSER 0   /* 1 (default): row-per-lane operand transposer, coalesced saved-copy stores */
+#define LPB_TUNE_SOFTMAX_EPILOGUE_V2 1  /* 1 (default): softmax epilogue with one vote per tile and hoisted addressing */
+#define LPB_TUNE_WAIT_BACKOFF 2         /* 1 (default): idle warps back off between mbarrier polls */
+#define LPB_TUNE_COUNT 3
+int lpb_set_tuning(int key, int value);
+int lpb_get_tuning(int key);
+
 /* ---- soft-argmax decode ---------------------------------------------------------------------
  * replaces run_subpixelmaxima / HeatmapHead.run_subpixelmaxima
  *   lightning_pose/models/heads/heatmap.py:103-144, :214-227

@@ -36,6 +36,8 @@ SIGNATURES = {
     "lpb_version": (C.c_int, []),
     "lpb_last_error": (C.c_char_p, []),
     "lpb_build_arch": (C.c_char_p, []),
+    "lpb_set_tuning": (C.c_int, [_I, _I]),
+    "lpb_get_tuning": (C.c_int, [_I]),
     "lpb_decode_prepare": (C.c_int, [_I, _I, _I]),
     "lpb_decode_fwd": (C.c_int, [_P, _L, _I, _I, _I, _F, _P, _P, _P, _P]),
     "lpb_decode_bwd": (C.c_int, [_P, _P, _P, _L, _I, _I, _I, _F, _P, _P]),
@@ -93,6 +95,12 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
+
+# LPB_TUNE="key=value,..." selects kernel variants (include/lpb200.h LPB_TUNE_*): a profiling / bring-up aid
+for _kv in filter(None, os.environ.get("LPB_TUNE", "").split(",")):
+    _k, _v = _kv.split("=")
+    if lib.lpb_set_tuning(int(_k), int(_v)) != 0:
+        raise ValueError(f"LPB_TUNE: unknown key {_k}")
 
 
 class LpbError(RuntimeError):

@@ -8,3 +8,19 @@ const char* last_error_cstr();
 extern "C" int lpb_version(void) { return 100; }
 extern "C" const char* lpb_last_error(void) { return lpb::last_error_cstr(); }
 extern "C" const char* lpb_build_arch(void) { return "sm_100a"; }
+
+// Kernel-variant switches (profiling / bring-up aid; defaults are the measured-best variants).  Process-global, read at
+// launch time only.
+namespace lpb {
+int g_tuning[LPB_TUNE_COUNT] = {
+    1,  // LPB_TUNE_K1A_ROW_TRANSPOSER
+    1,  // LPB_TUNE_SOFTMAX_EPILOGUE_V2
+    1,  // LPB_TUNE_WAIT_BACKOFF
+};
+}
+extern "C" int lpb_set_tuning(int key, int value) {
+  if (key < 0 || key >= LPB_TUNE_COUNT) return LPB_ERR_INVALID;
+  lpb::g_tuning[key] = value;
+  return LPB_OK;
+}
+extern "C" int lpb_get_tuning(int key) { return (key < 0 || key >= LPB_TUNE_COUNT) ? -1 : lpb::g_tuning[key]; }

@@ -128,6 +128,8 @@ struct K1aParams {
   RowLayout Lmid, Lxs;
   int B, C, HW, W;            // feature geometry (C = 4 * Cin)
   int c1, nstages;
+  int row_transposer;         // 1: row-per-lane transposer (coalesced operand-copy stores); 0: 8x8 register-block transposer
+  int backoff;                // idle warps sleep between barrier polls
   HeadGeom g;
 };
 
@@ -195,6 +197,44 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
         bulk_g2s(stage_base + s * stage_bytes + a_stage_bytes,
                  reinterpret_cast<const unsigned char*>(P.wpk) + (size_t)st * HB_BSTAGE_BYTES, HB_BSTAGE_BYTES, &full[s]);
       }
+    }
+  } else if (warp < K1A_TW && P.row_transposer) {
+    // ================= transposers, row form: lane = shuffled pixel n of one image row ==================
+    // A warp takes (K-chunk kc, image row m) pairs; lane n gathers its 8 channels (source channels 4(8kc+e)+q, q =
+    // 2(m&1) + (n&1), position (m>>1, n>>1)) with 2-byte shared loads -- conflict-free: even / odd lanes read two
+    // channel rows 288 B apart -- and stores ONE 16-byte operand row.  Consecutive lanes write consecutive rows, so
+    // both the shared-memory store and the global store of the saved copy are fully coalesced (the 8x8 register-block
+    // form writes 16 bytes per lane at a 256-byte stride: 32 half-used sectors per store instruction, which made the
+    // transposers' LSU time -- not the tensor core -- the critical path of a training forward).
+    const int Hi = g.Hi, Wi = g.Wi, npair = 4 * Hi;
+    for (int it = 0; it < total_it; ++it) {
+      const int s = it % K1A_ASTAGES, r = it % K1A_RSTAGES;
+      mbar_wait(&raw_full[r], (it / K1A_RSTAGES) & 1);
+      mbar_wait(&empty[s], ((it / K1A_ASTAGES) & 1) ^ 1);
+      unsigned char* As = stage_base + s * stage_bytes;
+      unsigned char* xs_st = nullptr;
+      if (P.xs) {
+        const int b = blockIdx.x + (it / P.nstages) * gridDim.x, st = it % P.nstages;
+        xs_st = reinterpret_cast<unsigned char*>(P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)P.Lxs.rows * 8);
+      }
+      const unsigned short* raw = reinterpret_cast<const unsigned short*>(raw_base + r * raw_bytes);
+      for (int pr = warp; pr < npair; pr += K1A_TW) {
+        const int kc = pr / Hi, m = pr - kc * Hi;
+        const int chan0 = 32 * kc + 2 * (m & 1);  // source channel of e = 0, dj = 0
+        for (int n = lane; n < Wi; n += 32) {
+          const unsigned short* src = raw + (size_t)(chan0 + (n & 1)) * P.HW + (m >> 1) * P.W + (n >> 1);
+          uint32_t pk[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) pk[e2] = (uint32_t)src[(size_t)(8 * e2) * P.HW] | ((uint32_t)src[(size_t)(8 * e2 + 4) * P.HW] << 16);
+          const uint4 o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          const int row = m * g.P + n;
+          *reinterpret_cast<uint4*>(As + ((size_t)kc * g.rows_alloc + row) * 16) = o;
+          if (xs_st) *reinterpret_cast<uint4*>(xs_st + ((size_t)kc * P.Lxs.rows + P.Lxs.lead + row) * 16) = o;
+        }
+      }
+      fence_proxy_async();
+      tc::mbar_arrive(&full[s]);
+      tc::mbar_arrive(&raw_empty[r]);
     }
   } else if (warp < K1A_TW) {
     // ================= transposers: raw NCHW slab (smem) -> K-major rows, PixelShuffle folded in ======
@@ -309,7 +349,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
     const int q = warp & 3;
     uint32_t fph = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
-      mbar_wait(tmem_full, fph);
+      mbar_wait_idle(tmem_full, fph, P.backoff);
       tc::fence_after_sync();
       for (int t = 0; t < g.tiles; ++t) {
         float d[HB_NCOLS];
@@ -741,9 +781,28 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   pa.W = W;
   pa.c1 = c1;
   pa.nstages = nst;
+  pa.row_transposer = g_tuning[LPB_TUNE_K1A_ROW_TRANSPOSER];
+  pa.backoff = g_tuning[LPB_TUNE_WAIT_BACKOFF];
   pa.g = g1;
   LPB_CUDA(cudaFuncSetAttribute(k1a_shuffle_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
   k1a_shuffle_convt_kernel<<<B < sms ? B : sms, K1A_THREADS, s1, s>>>(pa);
+  if (g_tuning[LPB_TUNE_SOFTMAX_EPILOGUE_V2]) {
+    // layer 2 on the banded kernel (head_rows_bf16.cu): same GEMM, leaner softmax epilogue
+    ConvtRowsParams p2{};
+    p2.X = mid;
+    p2.L = Lmid;
+    p2.wpk = wp2;
+    p2.bias = nullptr;  // folded into the GEMM through the ones channel
+    p2.nst = 1;
+    p2.B = B;
+    p2.cout = c2;
+    p2.out = out;
+    p2.mode = final_softmax ? CONVT_ROWS_SOFTMAX : CONVT_ROWS_PLANES;
+    const int rc = launch_convt_rows(p2, sms, s);
+    if (rc != LPB_OK) return rc;
+    LPB_CUDA(cudaGetLastError());
+    return LPB_OK;
+  }
   K1bParams pb;
   pb.mid = mid;
   pb.L = Lmid;

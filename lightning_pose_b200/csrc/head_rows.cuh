@@ -19,7 +19,7 @@ struct ConvtRowsParams {
   __nv_bfloat16* mid;        // CONVT_ROWS_MID: [B][4][Lout.rows][8], channel `cout` = 1
   RowLayout Lout;
   float* out;                // planes [B][cout][2Hi][2Wi] (raw or softmaxed)
-  int R, rows_alloc;         // filled by launch_convt_rows
+  int R, rows_alloc, backoff;  // filled by launch_convt_rows
 };
 
 int launch_rows_shuffle(const __nv_bfloat16* feat, int B, int C, int H, int W, __nv_bfloat16* xs, cudaStream_t s);

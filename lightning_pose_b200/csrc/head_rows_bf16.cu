@@ -77,13 +77,16 @@ constexpr int CR_EPI = 256;
 constexpr int CR_TILES = 3;      // M-tiles per band (3 * 80 = 240 of the CTA's 256 TMEM columns)
 constexpr int CR_STAGES = 2;
 
-template <int MODE>
+// NPL: compile-time plane count (17 = the usual keypoint count) or 0 for a run-time count <= 20.
+// V2: softmax epilogue with one warp vote per tile (instead of one per plane), the running-max rescale out of the
+// common path, (shift, 1/sum) fetched as one 8-byte shared load and the output pointer advanced by addition.
+template <int MODE, int NPL, bool V2>
 __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_constant__ ConvtRowsParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Pp = P.L.Pp, Wi = P.L.Wi, Hi = P.L.Hi;
   const int a_bytes = 4 * P.rows_alloc * 16, stage_bytes = a_bytes + CR_BSTAGE;
   float* stat = reinterpret_cast<float*>(smem + CR_STAGES * stage_bytes);  // [2][CR_CLS][8 warps]
-  float* fin = stat + 2 * CR_CLS * 8;                                       // [2][CR_CLS]
+  float* fin = stat + 2 * CR_CLS * 8;                                       // [CR_CLS][2] = (max * log2 e, 1 / sum)
   uint64_t* bars = reinterpret_cast<uint64_t*>(fin + 2 * CR_CLS + 8);
   uint64_t* full = bars;       // [2]
   uint64_t* empty = bars + 2;  // [2]
@@ -112,9 +115,11 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
   const int R = P.R, nbands = (Hi + R - 1) / R, nst = P.nst;
   const int npass = MODE == CONVT_ROWS_SOFTMAX ? 2 : 1;
   const int Ho = 2 * Hi, Wo = 2 * Wi;
+  const int ncls = NPL ? NPL : P.cout;  // planes handled by the unrolled loops
 
   if (warp == 0) {
     // ================= loader: one bulk copy per K-chunk (band rows + the halo row below) + the stage's weights ====
+    // single-stage GEMMs (K = 32) keep their weights resident: each ring slot receives them once
     int it = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x)
       for (int pass = 0; pass < npass; ++pass)
@@ -123,11 +128,12 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
           const uint32_t nbytes = (uint32_t)((rb + 1) * Pp * 16);
           for (int st = 0; st < nst; ++st, ++it) {
             const int s = it % CR_STAGES;
-            mbar_wait(&empty[s], ((it / CR_STAGES) & 1) ^ 1);
+            mbar_wait_idle(&empty[s], ((it / CR_STAGES) & 1) ^ 1, P.backoff);
             unsigned char* As = smem + s * stage_bytes;
+            const bool load_b = nst > 1 || it < CR_STAGES;
             if (lane == 0) {
-              mbar_expect_tx(&full[s], 4 * nbytes + CR_BSTAGE);
-              bulk_g2s(As + a_bytes, reinterpret_cast<const unsigned char*>(P.wpk) + (size_t)st * CR_BSTAGE, CR_BSTAGE, &full[s]);
+              mbar_expect_tx(&full[s], 4 * nbytes + (load_b ? CR_BSTAGE : 0));
+              if (load_b) bulk_g2s(As + a_bytes, reinterpret_cast<const unsigned char*>(P.wpk) + (size_t)st * CR_BSTAGE, CR_BSTAGE, &full[s]);
             }
             __syncwarp();
             if (lane < 4)
@@ -183,14 +189,14 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
       float mx[CR_CLS], sm[CR_CLS];
 #pragma unroll
       for (int o = 0; o < CR_CLS; ++o) {
-        mx[o] = -3.0e38f;
+        mx[o] = -1.0e30f;
         sm[o] = 0.f;
       }
       for (int pass = 0; pass < npass; ++pass) {
         const bool write = (pass == npass - 1);
         for (int band = 0; band < nbands; ++band, ++nb) {
           const int y0 = band * R, rb = min(R, Hi - y0), tiles = (rb * Pp + 127) / 128;
-          mbar_wait(t_full, nb & 1);
+          mbar_wait_idle(t_full, nb & 1, P.backoff);
           tc::fence_after_sync();
           for (int t = 0; t < tiles; ++t) {
             float d[48];
@@ -238,13 +244,57 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
                 return;
               }
               float* dst = P.out + ((size_t)b * P.cout * Ho + y) * Wo + x;  // plane o adds o * Ho * Wo
+              if constexpr (V2 && MODE == CONVT_ROWS_SOFTMAX) {
+                if (!write) {
+                  // ---- pass 0: per-thread online (max, sum) per plane; the rescale is rare after the first tiles ----
+                  bool need = false;
+#pragma unroll
+                  for (int o = 0; o < CR_CLS; ++o) {
+                    if (o >= ncls) break;
+                    need |= fmaxf(d[8 * E + o], d[8 * E + CR_CLS + o]) > mx[o];
+                  }
+                  if (__any_sync(0xffffffffu, need && valid)) {
+                    if (valid) {
+#pragma unroll
+                      for (int o = 0; o < CR_CLS; ++o) {
+                        if (o >= ncls) break;
+                        const float tm = fmaxf(d[8 * E + o], d[8 * E + CR_CLS + o]);
+                        if (tm > mx[o]) {
+                          sm[o] *= fast_exp2((mx[o] - tm) * L2E);
+                          mx[o] = tm;
+                        }
+                      }
+                    }
+                  }
+                  if (valid) {
+#pragma unroll
+                    for (int o = 0; o < CR_CLS; ++o) {
+                      if (o >= ncls) break;
+                      const float mL = mx[o] * L2E;
+                      sm[o] += fast_exp2(fmaf(d[8 * E + o], L2E, -mL)) + fast_exp2(fmaf(d[8 * E + CR_CLS + o], L2E, -mL));
+                    }
+                  }
+                } else if (valid) {
+                  // ---- pass 1: normalise and store; (shift, 1 / sum) is one 8-byte shared load per plane ----
+#pragma unroll
+                  for (int o = 0; o < CR_CLS; ++o) {
+                    if (o >= ncls) break;
+                    const float2 f = reinterpret_cast<const float2*>(fin)[o];
+                    const float p0 = fast_exp2(fmaf(d[8 * E + o], L2E, -f.x)) * f.y;
+                    const float p1 = fast_exp2(fmaf(d[8 * E + CR_CLS + o], L2E, -f.x)) * f.y;
+                    *reinterpret_cast<float2*>(dst) = make_float2(p0, p1);
+                    dst += plane_stride;
+                  }
+                }
+                return;
+              }
 #pragma unroll
               for (int o = 0; o < CR_CLS; ++o) {
-                if (o >= P.cout) break;
+                if (o >= ncls) break;
                 const float bo = use_bias ? __ldg(P.bias + o) : 0.f;
                 const float l0 = d[8 * E + o] + bo, l1 = d[8 * E + CR_CLS + o] + bo;
                 if (!write) {
-                  const float mm = valid ? fmaxf(l0, l1) : -3.0e38f;
+                  const float mm = valid ? fmaxf(l0, l1) : -1.0e30f;
                   if (__any_sync(0xffffffffu, mm > mx[o])) {
                     const float mn = fmaxf(mx[o], mm);
                     sm[o] *= fast_exp2((mx[o] - mn) * L2E);
@@ -257,7 +307,7 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
                 } else if (valid) {
                   float p0 = l0, p1 = l1;
                   if (MODE == CONVT_ROWS_SOFTMAX) {
-                    const float mL = fin[o], inv = fin[CR_CLS + o];
+                    const float mL = fin[2 * o], inv = fin[2 * o + 1];
                     p0 = fast_exp2(fmaf(l0, L2E, -mL)) * inv;
                     p1 = fast_exp2(fmaf(l1, L2E, -mL)) * inv;
                   }
@@ -275,7 +325,7 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
           // merge the online-softmax states: lanes -> warp (shuffles) -> 8 epilogue warps (smem)
 #pragma unroll
           for (int o = 0; o < CR_CLS; ++o) {
-            if (o >= P.cout) break;
+            if (o >= ncls) break;
             const float M = warp_max(mx[o]);
             const float S = warp_sum(sm[o] * fast_exp2((mx[o] - M) * L2E));
             if (lane == 0) {
@@ -284,7 +334,7 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
             }
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (tid - 64 < P.cout) {
+          if (tid - 64 < ncls) {
             const int o = tid - 64;
             float M = stat[o * 8];
 #pragma unroll
@@ -292,8 +342,8 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
             float S = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) S += stat[(CR_CLS + o) * 8 + i] * fast_exp2((stat[o * 8 + i] - M) * L2E);
-            fin[o] = M * L2E;
-            fin[CR_CLS + o] = 1.0f / S;
+            fin[2 * o] = M * L2E;
+            fin[2 * o + 1] = 1.0f / S;
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
@@ -318,14 +368,17 @@ int launch_convt_rows(ConvtRowsParams p, int sms, cudaStream_t s) {
   const size_t smem = (size_t)CR_STAGES * (4 * p.rows_alloc * 16 + CR_BSTAGE) + (2 * CR_CLS * 8 + 2 * CR_CLS + 8) * sizeof(float) + 64;
   LPB_REQUIRE(smem <= 113 * 1024, "head_fwd_bf16: band stages need %zu B shared memory", smem);
   const int grid = p.B < 2 * sms ? p.B : 2 * sms;
+  p.backoff = g_tuning[LPB_TUNE_WAIT_BACKOFF];
   auto run = [&](auto kern) -> int {
     LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, CR_THREADS, smem, s>>>(p);
     return LPB_OK;
   };
-  if (p.mode == CONVT_ROWS_MID) return run(convt_rows_kernel<CONVT_ROWS_MID>);
-  if (p.mode == CONVT_ROWS_PLANES) return run(convt_rows_kernel<CONVT_ROWS_PLANES>);
-  return run(convt_rows_kernel<CONVT_ROWS_SOFTMAX>);
+  const bool v2 = g_tuning[LPB_TUNE_SOFTMAX_EPILOGUE_V2] != 0, k17 = p.cout == 17;
+  if (p.mode == CONVT_ROWS_MID) return run(convt_rows_kernel<CONVT_ROWS_MID, 0, false>);
+  if (p.mode == CONVT_ROWS_PLANES) return k17 ? run(convt_rows_kernel<CONVT_ROWS_PLANES, 17, false>) : run(convt_rows_kernel<CONVT_ROWS_PLANES, 0, false>);
+  if (v2) return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 17, true>) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 0, true>);
+  return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 17, false>) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 0, false>);
 }
 
 }  // namespace lpb

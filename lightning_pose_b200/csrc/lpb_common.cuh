@@ -27,6 +27,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (e__ != cudaSuccess) return ::lpb::cuda_fail(e__, #call, __FILE__, __LINE__); \
   } while (0)
 
+extern int g_tuning[];  // abi.cu: kernel-variant switches (LPB_TUNE_*)
+
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -83,6 +85,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+// the same wait for warps that expect to idle for a long time (epilogue warps during a frame's MMAs, loaders ahead of
+// their consumers): poll, then sleep between polls so the spinning does not take issue slots from the working warps
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity, int backoff) {
+  if (!backoff) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(96);
+  }
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-B aligned.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
