@@ -23,6 +23,7 @@
 #include <type_traits>
 
 #include "../../include/lpb200.h"
+#include "head_prep.cuh"
 #include "head_rows.cuh"
 #include "lpb_common.cuh"
 #include "row_layout.cuh"
@@ -108,6 +109,98 @@ __global__ void pack_convt_weights_kernel(const float* __restrict__ w, const flo
     out[i] = __float2bfloat16_rn(v);
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x) zero[i] = __float2bfloat16_rn(0.f);
+}
+
+// ---- everything a head call prepares, in one launch (head_prep.cuh) -------------------------------------------
+constexpr int PREP_GB_K = 80, PREP_GB_KC = 10, PREP_GB_CLS = 20;  // class-major K of the gradient operands (head_bwd_bf16.cu)
+
+__global__ void __launch_bounds__(256) head_prep_kernel(const __grid_constant__ PrepJobs J) {
+  const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (!J.fpack[j].out) continue;
+    const float* w = J.fpack[j].w;
+    const float* bias = J.fpack[j].bias;
+    const int Cin = J.fpack[j].Cin, Cout = J.fpack[j].Cout;
+    const long long total = (long long)J.fpack[j].nstages * 4 * 4 * HB_NCOLS * 8;
+    for (long long i = tid0; i < total; i += nthr) {
+      const int e = (int)(i & 7);
+      long long r = i >> 3;
+      const int nrow = (int)(r % HB_NCOLS);
+      r /= HB_NCOLS;
+      const int kc = (int)(r & 3);
+      r >>= 2;
+      const int sh = (int)(r & 3);
+      const int st = (int)(r >> 2);
+      const int c = st * HB_KSTAGE + kc * 8 + e;
+      const int cls = nrow / HB_CLS, o = nrow % HB_CLS;
+      const int py = cls >> 1, px = cls & 1, dm = sh >> 1, dn = sh & 1;
+      float v = 0.f;
+      if (c < Cin && o < Cout && !(py == 0 && dm == 1) && !(px == 0 && dn == 1)) {
+        const int ky = py == 0 ? 1 : (dm ? 0 : 2);
+        const int kx = px == 0 ? 1 : (dn ? 0 : 2);
+        v = w[((size_t)c * Cout + o) * 9 + ky * 3 + kx];
+      } else if (bias && c == Cin && o < Cout && sh == 0) {
+        v = bias[o];
+      }
+      J.fpack[j].out[i] = __float2bfloat16_rn(v);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (!J.dpack[j].out) continue;
+    const float* w = J.dpack[j].w;
+    const int Cin = J.dpack[j].Cin, Cout = J.dpack[j].Cout, rpt = J.dpack[j].rows_per_tile;
+    const long long total = (long long)J.dpack[j].ntiles * 4 * PREP_GB_KC * rpt * 8;
+    for (long long i = tid0; i < total; i += nthr) {
+      const int e = (int)(i & 7);
+      long long r = i >> 3;
+      const int row = (int)(r % rpt);
+      r /= rpt;
+      const int kc = (int)(r % PREP_GB_KC);
+      r /= PREP_GB_KC;
+      const int sh = (int)(r & 3);
+      const int tile = (int)(r >> 2);
+      const int c = tile * rpt + row;
+      const int k = kc * 8 + e;
+      const int cls = k / PREP_GB_CLS, o = k % PREP_GB_CLS;
+      const int py = cls >> 1, px = cls & 1, dm = sh >> 1, dn = sh & 1;
+      float v = 0.f;
+      if (c < Cin && o < Cout && !(py == 0 && dm == 1) && !(px == 0 && dn == 1)) {
+        const int ky = py == 0 ? 1 : (dm ? 0 : 2);
+        const int kx = px == 0 ? 1 : (dn ? 0 : 2);
+        v = w[((size_t)c * Cout + o) * 9 + ky * 3 + kx];
+      }
+      J.dpack[j].out[i] = __float2bfloat16_rn(v);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (!J.pads[j].buf) continue;
+    const RowLayout L = J.pads[j].L;
+    const int body0 = L.lead, body1 = L.lead + L.Hi * L.Pp;
+    const int npad = L.lead + (L.rows - body1) + L.Hi;
+    const long long total = J.pads[j].nslabs * npad;
+    for (long long i = tid0; i < total; i += nthr) {
+      const long long slab = i / npad;
+      const int e = (int)(i - slab * npad);
+      int row;
+      if (e < L.lead) row = e;
+      else if (e < L.lead + (L.rows - body1)) row = body1 + (e - L.lead);
+      else row = body0 + (e - L.lead - (L.rows - body1)) * L.Pp + L.Wi;
+      *reinterpret_cast<uint4*>(J.pads[j].buf + ((size_t)slab * L.rows + row) * 8) = make_uint4(0, 0, 0, 0);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (!J.zero[j].p) continue;
+    for (long long i = tid0; i < J.zero[j].n; i += nthr) J.zero[j].p[i] = 0.f;
+  }
+}
+
+int launch_head_prep(const PrepJobs& jobs, cudaStream_t s) {
+  head_prep_kernel<<<148 * 2, 256, 0, s>>>(jobs);
+  return LPB_OK;
 }
 
 // =====================================================================================================
@@ -715,14 +808,21 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   __nv_bfloat16* wp1 = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* wp2 = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)nst * HB_BSTAGE_BYTES);
   __nv_bfloat16* mid = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES);
-  pack_convt_weights_kernel<<<64, 256, 0, s>>>(w1, nullptr, C / 4, c1, nst, wp1, nullptr, 0);
-  // layer 2: bias rides on the constant-one channel c1 of the mid activations (only needed without softmax:
-  // a per-plane constant does not change a softmax)
-  if (c2 > 0) {
-    pack_convt_weights_kernel<<<8, 256, 0, s>>>(w2, final_softmax ? nullptr : b2, c1, c2, 1, wp2, nullptr, 0);
-    launch_zero_row_pads(mid, Lmid, (long long)B * 4, stream);
+  const bool fast = head_fast_path(C, H, W, c2, max_smem);
+  {
+    // one launch: both operand packs + the pad rows of the fresh row-layout buffers
+    PrepJobs jobs{};
+    jobs.fpack[0] = {w1, nullptr, C / 4, c1, nst, wp1};
+    // layer 2: bias rides on the constant-one channel c1 of the mid activations (only needed without softmax:
+    // a per-plane constant does not change a softmax)
+    if (c2 > 0) {
+      jobs.fpack[1] = {w2, final_softmax ? nullptr : b2, c1, c2, 1, wp2};
+      jobs.pads[0] = {mid, Lmid, (long long)B * 4};
+    }
+    if (fast && saved_xs) jobs.pads[1] = {static_cast<__nv_bfloat16*>(saved_xs), Lxs, (long long)B * (C / 32)};  // (the banded path's shuffle kernel writes its own pads)
+    launch_head_prep(jobs, s);
   }
-  if (!head_fast_path(C, H, W, c2, max_smem)) {
+  if (!fast) {
     // ---- generic path: shuffle rows -> banded GEMM(s) ----
     LPB_REQUIRE(saved_xs, "head_fwd_bf16: this shape takes the banded kernels (lpb_head_bf16_plan = 0): pass the "
                           "lpb_head_bf16_saved_bytes() buffer as saved_xs");
@@ -766,7 +866,6 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   }
   const HeadGeom g1 = make_geom(2 * H, 2 * W), g2 = make_half_geom(2 * H, 4 * W);  // layer 2: 4H rows in two halves
   const size_t s1 = k1a_smem_bytes(g1, H * W), s2 = k1b_smem_bytes(g2);
-  if (saved_xs) launch_zero_row_pads(static_cast<__nv_bfloat16*>(saved_xs), Lxs, (long long)B * (C / 32), stream);
   K1aParams pa;
   pa.feat = static_cast<const __nv_bfloat16*>(features);
   pa.wpk = wp1;

@@ -13,6 +13,7 @@
 #include <cstdint>
 
 #include "../../include/lpb200.h"
+#include "head_prep.cuh"
 #include "lpb_common.cuh"
 #include "row_layout.cuh"
 #include "tcgen05.cuh"
@@ -842,13 +843,15 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int C4 = C / 4, Hi1 = 2 * H, Wi1 = 2 * W, Hi2 = 4 * H, Wi2 = 4 * W;
   const int kout = two ? c2 : c1;
-  LPB_CUDA(cudaMemsetAsync(dw1, 0, sizeof(float) * (size_t)C4 * c1 * 9, s));
-  LPB_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * c1, s));
-  if (two) {
-    LPB_CUDA(cudaMemsetAsync(dw2, 0, sizeof(float) * (size_t)c1 * c2 * 9, s));
-    LPB_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * c2, s));
+  if (B == 0) {
+    LPB_CUDA(cudaMemsetAsync(dw1, 0, sizeof(float) * (size_t)C4 * c1 * 9, s));
+    LPB_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * c1, s));
+    if (two) {
+      LPB_CUDA(cudaMemsetAsync(dw2, 0, sizeof(float) * (size_t)c1 * c2 * 9, s));
+      LPB_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * c2, s));
+    }
+    return LPB_OK;
   }
-  if (B == 0) return LPB_OK;
   const int Hh = b3a_band_rows(Hi1, Wi1);
   if (Hh < 4) {
     set_error("head_bwd_bf16: feature map %dx%d outside this build's TMEM tiling", H, W);
@@ -871,12 +874,21 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
   const size_t fwd_mid_off = (size_t)(C4 / 32 + 1) * (4 * 4 * 80 * 16);
   const __nv_bfloat16* mid = reinterpret_cast<const __nv_bfloat16*>(static_cast<const unsigned char*>(fwd_workspace) + fwd_mid_off);
 
-  pack_dgrad_weights_kernel<<<128, 256, 0, s>>>(w1, C4, c1, ntile1, 128, wp1, nullptr, 0);
-  if (two) {
-    pack_dgrad_weights_kernel<<<8, 256, 0, s>>>(w2, c1, c2, 1, 32, wp2, nullptr, 0);
-    launch_zero_row_pads(G2, L2, (long long)B * GB_KC, stream);
+  {
+    // one launch: gradient accumulators zeroed, both data-gradient operand packs, pad rows of G2 / G1
+    PrepJobs jobs{};
+    jobs.dpack[0] = {w1, C4, c1, ntile1, 128, wp1};
+    jobs.pads[0] = {G1, L1, (long long)B * GB_KC};
+    jobs.zero[0] = {dw1, (long long)C4 * c1 * 9};
+    jobs.zero[1] = {db1, (long long)c1};
+    if (two) {
+      jobs.dpack[1] = {w2, c1, c2, 1, 32, wp2};
+      jobs.pads[1] = {G2, L2, (long long)B * GB_KC};
+      jobs.zero[2] = {dw2, (long long)c1 * c2 * 9};
+      jobs.zero[3] = {db2, (long long)c2};
+    }
+    launch_head_prep(jobs, s);
   }
-  launch_zero_row_pads(G1, L1, (long long)B * GB_KC, stream);
   {
     // gradient front end on the head's OUTPUT grid: G2 for a two-deconv head, G1 for a one-deconv head
     const int Hio = two ? Hi2 : Hi1, Wio = two ? Wi2 : Wi1;

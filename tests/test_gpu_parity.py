@@ -1029,3 +1029,56 @@ def test_mhcrnn_bf16_real_shape_and_tracker(lpb, dev):
     assert torch.isfinite(loss) and tr.backbone.conv.weight.grad is not None and torch.isfinite(tr.backbone.conv.weight.grad).all()
     kp, cf = tr.predict_step({"frames": frames, "bbox": bbox}, 0)
     assert kp.shape == (t - 4, 2 * k) and cf.shape == (t - 4, k)
+
+
+def test_multiview_transformer_tracker_config4(lpb, dev):
+    """config 4: 4 views x 384x384 -> per-view ViT token grids (384, 24, 24) -> the SAME head on views * batch maps ->
+    heatmaps folded to (batch, 4 * 17, 96, 96) (reference heatmap_tracker_multiview.py:143-258); bf16 banded kernels
+    against the fp32 oracle on identical features, then one supervised + multi-view step end to end."""
+    from lightning_pose_b200.losses.factory import LossFactory
+    from lightning_pose_b200.models.heatmap_tracker_multiview import HeatmapTrackerMultiviewTransformer
+
+    torch.manual_seed(17)
+    k, v, b, d, img = 17, 4, 2, 384, 384
+
+    class Patch(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.proj = torch.nn.Conv2d(3, d, 16, stride=16)
+
+        def forward(self, x):
+            return self.proj(x).flatten(2).transpose(1, 2)
+
+    class Mix(torch.nn.Module):  # stands in for the attention blocks: mixes tokens ACROSS views
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(d, d)
+
+        def forward(self, t):
+            return (self.lin(t) + t.mean(1, keepdim=True)).bfloat16()
+
+    tr = HeatmapTrackerMultiviewTransformer(k, v, Patch(), Mix(), d, loss_factory=LossFactory({"heatmap_mse": {"log_weight": 0.0}}, None)).to(dev)
+    for layer in list(tr.head.upsampling_layers)[1:]:
+        torch.nn.init.xavier_uniform_(layer.weight, gain=3.0)
+    images = torch.randn(b, v, 3, img, img, device=dev)
+    with torch.no_grad():
+        feats = tr.forward_vit(images.reshape(-1, 3, img, img))
+        hm = tr(images)
+    assert feats.shape == (b * v, d, 24, 24) and feats.dtype == torch.bfloat16 and hm.shape == (b, v * k, 96, 96)
+    dc = list(tr.head.upsampling_layers)[1]
+    ref = O.head_forward(feats.float().cpu(), [dc.weight.detach().cpu().bfloat16().float()], [dc.bias.detach().cpu()]).reshape(b, v * k, 96, 96)
+    rel = ((hm.cpu() - ref).abs() / (ref.abs() + 1e-7)).flatten()
+    assert float(rel.max()) < 3e-2 and float((rel > 1e-2).float().mean()) < 1e-4
+    # view mixing really happened: changing view 3 of example 0 changes view 0's heatmaps of example 0 only
+    images2 = images.clone()
+    images2[0, 3] += 1.0
+    with torch.no_grad():
+        hm2 = tr(images2)
+    assert float((hm2[0, :k] - hm[0, :k]).abs().max()) > 0 and float((hm2[1] - hm[1]).abs().max()) == 0
+    kp = torch.rand(b, v * k * 2, device=dev) * img
+    targets = lpb.generate_heatmaps(kp.reshape(b, v * k, 2), img, img, (96, 96))
+    bbox = torch.tensor([[0.0, 0.0, 400.0, 420.0] * v], device=dev).repeat(b, 1)
+    loss = tr.evaluate_labeled({"images": images, "keypoints": kp.clone(), "heatmaps": targets, "bbox": bbox, "num_views": torch.full((b,), v, device=dev)}, "train", 1.0)
+    loss.backward()
+    assert torch.isfinite(loss) and tr.view_embeddings.grad is not None and float(tr.view_embeddings.grad.abs().max()) > 0
+    assert tr.patch_embed.proj.weight.grad is not None and torch.isfinite(tr.patch_embed.proj.weight.grad).all()
