@@ -43,7 +43,8 @@ const char* lpb_build_arch(void);     /* "sm_100a" */
 #define LPB_TUNE_K1A_ROW_TRANSPOSER 0   /* 1 (default): row-per-lane operand transposer, coalesced saved-copy stores */
 #define LPB_TUNE_SOFTMAX_EPILOGUE_V2 1  /* 1 (default): softmax epilogue with one vote per tile and hoisted addressing */
 #define LPB_TUNE_WAIT_BACKOFF 2         /* 1 (default): idle warps back off between mbarrier polls */
-#define LPB_TUNE_COUNT 3
+#define LPB_TUNE_DECODE_RING 3          /* 1 (default): soft-argmax planes staged once in shared memory by a bulk-copy ring */
+#define LPB_TUNE_COUNT 4
 int lpb_set_tuning(int key, int value);
 int lpb_get_tuning(int key);
 

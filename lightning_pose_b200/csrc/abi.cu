@@ -16,6 +16,7 @@ int g_tuning[LPB_TUNE_COUNT] = {
     1,  // LPB_TUNE_K1A_ROW_TRANSPOSER
     1,  // LPB_TUNE_SOFTMAX_EPILOGUE_V2
     1,  // LPB_TUNE_WAIT_BACKOFF
+    1,  // LPB_TUNE_DECODE_RING
 };
 }
 extern "C" int lpb_set_tuning(int key, int value) {

@@ -527,6 +527,10 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
 // and run by the CTA kernel in queue mode, so every plane produces the same outputs either way.
 constexpr int DECW_WIN = 32, DECW_WP = 33;
 
+__device__ __forceinline__ void tc_free_slot(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int DS>
 __device__ float eval_point_win(const float* tile, int r0w, int c0w, const float* __restrict__ tabH,
                                 const float* __restrict__ tabW, int i, int j) {
@@ -544,28 +548,26 @@ __device__ float eval_point_win(const float* tile, int r0w, int c0w, const float
   return acc;
 }
 
-template <int DS>
+template <int DS, bool STAGED>
 __device__ __forceinline__ void load_window(float* tile, const float* __restrict__ src, int h, int w, int r0w, int c0w, int lane) {
   const int x = c0w + lane;
   const bool xin = x >= 0 && x < w;
 #pragma unroll 8
   for (int r = 0; r < DECW_WIN; ++r) {
     const int y = r0w + r;
-    tile[r * DECW_WP + lane] = (xin && y >= 0 && y < h) ? __ldg(src + (size_t)y * w + x) : 0.f;
+    tile[r * DECW_WP + lane] = (xin && y >= 0 && y < h) ? (STAGED ? src[(size_t)y * w + x] : __ldg(src + (size_t)y * w + x)) : 0.f;
   }
 }
 
-template <int DS>
-__global__ void __launch_bounds__(128) decode_fwd_warp_kernel(const __grid_constant__ DecodeParams<DS> P, int* __restrict__ queue) {
+// One plane, one warp.  STAGED = false: `src` is the plane in global memory (read-only path, three sweeps of it);
+// STAGED = true: `src` is the plane already staged in shared memory by the ring kernel below (one HBM read per plane).
+template <int DS, bool STAGED>
+__device__ void decode_plane_warp(const DecodeParams<DS>& P, long long plane, const float* __restrict__ src, float* tile,
+                                  int* __restrict__ queue, int lane) {
   constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
-  __shared__ float tile_s[4][DECW_WIN * DECW_WP];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long plane = (long long)blockIdx.x * 4 + warp;
-  if (plane >= P.n_planes) return;
   const int h = P.h, w = P.w, w4 = w >> 2, n4 = h * w4;
-  const float* __restrict__ src = P.heat + (size_t)plane * h * w;
   const float4* __restrict__ src4 = reinterpret_cast<const float4*>(src);
-  float* tile = tile_s[warp];
+  auto ld4 = [&](int idx) -> float4 { return STAGED ? src4[idx] : __ldg(src4 + idx); };
   auto to_queue = [&]() {
     if (lane == 0) queue[1 + atomicAdd(queue, 1)] = (int)plane;
   };
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(128) decode_fwd_warp_kernel(const __grid_const
   int bidx = 0;
 #pragma unroll 8
   for (int idx = lane; idx < n4; idx += 32) {
-    const float4 x = __ldg(src4 + idx);
+    const float4 x = ld4(idx);
     const float m4 = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
     if (m4 > best) {
       best = m4;
@@ -598,12 +600,12 @@ __global__ void __launch_bounds__(128) decode_fwd_warp_kernel(const __grid_const
   const int besta = bidx / w4;
   int bestb = (bidx - besta * w4) * 4;
   {
-    const float4 x = __ldg(src4 + bidx);
+    const float4 x = ld4(bidx);
     bestb += (fabsf(x.x) == best) ? 0 : ((fabsf(x.y) == best) ? 1 : ((fabsf(x.z) == best) ? 2 : 3));
   }
   // ---- lower bound of the field maximum: exact values on the arg max's F x F block ---------------------
   int r0w = besta - DECW_WIN / 2, c0w = bestb - DECW_WIN / 2;
-  load_window<DS>(tile, src, h, w, r0w, c0w, lane);
+  load_window<DS, STAGED>(tile, src, h, w, r0w, c0w, lane);
   __syncwarp();
   float lb = -3.0e38f;
   if (lane < F * F) lb = eval_point_win<DS>(tile, r0w, c0w, P.tabH, P.tabW, besta * F + lane / F, bestb * F + lane % F);
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(128) decode_fwd_warp_kernel(const __grid_const
     }
 #pragma unroll 4
     for (int idx = lane; idx < n4; idx += 32) {
-      const float4 x = __ldg(src4 + idx);
+      const float4 x = ld4(idx);
       const bool c = (fabsf(x.x) >= theta) || (fabsf(x.y) >= theta) || (fabsf(x.z) >= theta) || (fabsf(x.w) >= theta);
       if (c) {
         amin = min(amin, a);
@@ -651,7 +653,7 @@ __global__ void __launch_bounds__(128) decode_fwd_warp_kernel(const __grid_const
   r0w = A0 - R - 1;
   c0w = B0 - R - 1;
   __syncwarp();
-  load_window<DS>(tile, src, h, w, r0w, c0w, lane);
+  load_window<DS, STAGED>(tile, src, h, w, r0w, c0w, lane);
   __syncwarp();
 
   // ---- rows that can carry weight (tap-decay bound, see decode_bwd_window_kernel); lane r owns window row r ----
@@ -774,6 +776,67 @@ __global__ void __launch_bounds__(128) decode_fwd_warp_kernel(const __grid_const
       st[6] = (float)B0;
       st[7] = (float)B1;
     }
+  }
+}
+
+template <int DS>
+__global__ void __launch_bounds__(128) decode_fwd_warp_kernel(const __grid_constant__ DecodeParams<DS> P, int* __restrict__ queue) {
+  __shared__ float tile_s[4][DECW_WIN * DECW_WP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long plane = (long long)blockIdx.x * 4 + warp;
+  if (plane >= P.n_planes) return;
+  decode_plane_warp<DS, false>(P, plane, P.heat + (size_t)plane * P.h * P.w, tile_s[warp], queue, lane);
+}
+
+// ---- ring form: every plane crosses HBM once -----------------------------------------------------------------
+// Persistent CTAs.  One producer thread streams whole planes (contiguous h*w*4 bytes = ONE bulk copy each) into a ring
+// of shared-memory slots; DECR_WARPS consumer warps each take the next filled slot and run the same per-plane code as
+// above on the staged copy -- the arg-max sweep, the candidate-hull sweep and both window loads read shared memory, so
+// DRAM traffic is the algorithmic 4*h*w bytes per plane (the warp kernel above reads each plane twice from
+// global memory: 2.05x measured).  Consumer warps never synchronise with each other, only with the producer through
+// the slot's full / empty mbarriers.
+constexpr int DECR_WARPS = 4;
+
+template <int DS>
+__global__ void __launch_bounds__(32 * (DECR_WARPS + 1), 1) decode_fwd_ring_kernel(const __grid_constant__ DecodeParams<DS> P, int* __restrict__ queue,
+                                                                                    int nslots) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  const int plane_bytes = P.h * P.w * 4;
+  float* tiles = reinterpret_cast<float*>(dsm);                                   // [DECR_WARPS][WIN * WP]
+  unsigned char* slots = dsm + ((DECR_WARPS * DECW_WIN * DECW_WP * 4 + 127) & ~127);  // [nslots][plane_bytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slots + (size_t)nslots * plane_bytes);  // full[nslots], empty[nslots]
+  uint64_t* full = bars;
+  uint64_t* empty = bars + nslots;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nslots; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // planes of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const long long first = blockIdx.x, stride = gridDim.x;
+  const long long mine = first < P.n_planes ? (P.n_planes - first + stride - 1) / stride : 0;
+  if (warp == DECR_WARPS) {
+    if (lane == 0) {
+      for (long long i = 0; i < mine; ++i) {
+        const int sl = (int)(i % nslots);
+        mbar_wait(&empty[sl], (uint32_t)(((i / nslots) & 1) ^ 1));
+        mbar_expect_tx(&full[sl], (uint32_t)plane_bytes);
+        bulk_g2s(slots + (size_t)sl * plane_bytes, P.heat + (size_t)(first + i * stride) * P.h * P.w, (uint32_t)plane_bytes, &full[sl]);
+      }
+    }
+    return;
+  }
+  for (long long i = warp; i < mine; i += DECR_WARPS) {
+    const int sl = (int)(i % nslots);
+    mbar_wait(&full[sl], (uint32_t)((i / nslots) & 1));
+    decode_plane_warp<DS, true>(P, first + i * stride, reinterpret_cast<const float*>(slots + (size_t)sl * plane_bytes),
+                                tiles + warp * DECW_WIN * DECW_WP, queue, lane);
+    __syncwarp();
+    if (lane == 0) tc_free_slot(&empty[sl]);
   }
 }
 
@@ -1168,7 +1231,17 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
     const size_t qints = (size_t)(2 * n_planes + 1) + (size_t)n_planes * DEC_MAX_PARTS * 4;
     LPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&queue), sizeof(int) * qints, stream));
     LPB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int) * (size_t)(2 * n_planes + 1), stream));
-    decode_fwd_warp_kernel<DS><<<(unsigned)((n_planes + 3) / 4), 128, 0, stream>>>(P, queue);
+    // ring form when at least two planes (+ the per-warp windows) fit in shared memory: one HBM read per plane
+    const size_t plane_bytes = (size_t)h * w * 4, tiles_b = (size_t)((DECR_WARPS * DECW_WIN * DECW_WP * 4 + 127) & ~127);
+    int nslots = (int)(((size_t)max_smem - tiles_b - 256) / plane_bytes);
+    if (nslots > 8) nslots = 8;
+    if (g_tuning[LPB_TUNE_DECODE_RING] && nslots >= 2 && plane_bytes % 16 == 0) {
+      const size_t rsm = tiles_b + (size_t)nslots * plane_bytes + (size_t)2 * nslots * 8 + 64;
+      LPB_CUDA(cudaFuncSetAttribute(decode_fwd_ring_kernel<DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+      decode_fwd_ring_kernel<DS><<<(unsigned)(n_planes < sms ? n_planes : sms), 32 * (DECR_WARPS + 1), rsm, stream>>>(P, queue, nslots);
+    } else {
+      decode_fwd_warp_kernel<DS><<<(unsigned)((n_planes + 3) / 4), 128, 0, stream>>>(P, queue);
+    }
     P.queue = queue;
     P.qcounter = queue + 1 + n_planes;
     P.qscratch = reinterpret_cast<float*>(queue + 1 + 2 * n_planes);

@@ -9,7 +9,7 @@ echo "tests exit $rc" >> gpurun_out/r2a_tests.log
 tail -30 gpurun_out/r2a_tests.log
 if [ $rc -ne 0 ]; then
   # which failures belong to the new kernel variants?  same suite with the round-1 variants
-  LPB_TUNE="0=0,1=0,2=0" timeout 2400 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/r2a_tests_oldvariants.log 2>&1
+  LPB_TUNE="0=0,1=0,2=0,3=0" timeout 2400 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/r2a_tests_oldvariants.log 2>&1
   echo "old-variant tests exit $?" >> gpurun_out/r2a_tests_oldvariants.log
   tail -30 gpurun_out/r2a_tests_oldvariants.log
   timeout 2400 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/r2a_tests_all.log 2>&1
@@ -24,6 +24,6 @@ echo "bench exit $?"
 tail -c 3500 gpurun_out/r2a_bench.json
 tail -5 gpurun_out/r2a_bench.err
 timeout 600 python scripts/kp_error_hist.py > gpurun_out/r2a_kp_hist.log 2>&1; tail -c 1500 gpurun_out/r2a_kp_hist.log
-LPB_TUNE="0=0,1=0,2=0" timeout 600 python bench.py --steps 10 --warmup 3 --no-flat --no-cpu-baseline > gpurun_out/r2a_bench_oldvariants.json 2> gpurun_out/r2a_bench_oldvariants.err
+LPB_TUNE="0=0,1=0,2=0,3=0" timeout 600 python bench.py --steps 10 --warmup 3 --no-flat --no-cpu-baseline > gpurun_out/r2a_bench_oldvariants.json 2> gpurun_out/r2a_bench_oldvariants.err
 echo "bench (round-1 variants) exit $?"
 tail -c 1500 gpurun_out/r2a_bench_oldvariants.json
