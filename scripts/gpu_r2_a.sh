@@ -23,6 +23,7 @@ timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2a_bench.json 2>
 echo "bench exit $?"
 tail -c 3500 gpurun_out/r2a_bench.json
 tail -5 gpurun_out/r2a_bench.err
+timeout 600 python scripts/bench_configs.py > gpurun_out/r2a_configs.log 2>&1; tail -c 2500 gpurun_out/r2a_configs.log
 timeout 600 python scripts/kp_error_hist.py > gpurun_out/r2a_kp_hist.log 2>&1; tail -c 1500 gpurun_out/r2a_kp_hist.log
 LPB_TUNE="0=0,1=0,2=0,3=0" timeout 600 python bench.py --steps 10 --warmup 3 --no-flat --no-cpu-baseline > gpurun_out/r2a_bench_oldvariants.json 2> gpurun_out/r2a_bench_oldvariants.err
 echo "bench (round-1 variants) exit $?"
