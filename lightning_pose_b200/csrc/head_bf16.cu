@@ -36,30 +36,6 @@ constexpr int HB_CLS = 20;
 constexpr int HB_KSTAGE = 32;        // channels per pipeline stage (4 K-chunks of 8)
 constexpr int HB_BSTAGE_BYTES = 4 * 4 * HB_NCOLS * 16;  // [shift][kchunk][80 rows][16 B]
 
-__global__ void zero_row_pads_kernel(__nv_bfloat16* __restrict__ buf, RowLayout L, long long nslabs) {
-  const int body0 = L.lead, body1 = L.lead + L.Hi * L.Pp;
-  const int npad = L.lead + (L.rows - body1) + L.Hi;  // lead rows, trail rows, one pad column entry per image row
-  const long long total = nslabs * npad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long slab = i / npad;
-    const int e = (int)(i - slab * npad);
-    int row;
-    if (e < L.lead) row = e;
-    else if (e < L.lead + (L.rows - body1)) row = body1 + (e - L.lead);
-    else row = body0 + (e - L.lead - (L.rows - body1)) * L.Pp + L.Wi;
-    *reinterpret_cast<uint4*>(buf + ((size_t)slab * L.rows + row) * 8) = make_uint4(0, 0, 0, 0);
-  }
-}
-
-int launch_zero_row_pads(__nv_bfloat16* buf, RowLayout L, long long nslabs, void* stream) {
-  const int npad = L.lead + (L.rows - L.lead - L.Hi * L.Pp) + L.Hi;
-  long long blocks = (nslabs * npad + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (blocks < 1) return LPB_OK;
-  zero_row_pads_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(buf, L, nslabs);
-  return LPB_OK;
-}
-
 struct HeadGeom {
   int Hi, Wi;       // conv input spatial size (after PixelShuffle for layer 1)
   int P;            // row pitch = Wi + 1 (zero column)
@@ -79,39 +55,9 @@ __host__ inline HeadGeom make_geom(int Hi, int Wi) {
   return g;
 }
 
-// ---- weight packing: W[Cin][Cout][3][3] (fp32) -> B[stage][shift][kchunk][80][8] bf16 -----------------
-// bias != nullptr: input channel `Cin` is the constant-one channel and carries the bias (shift (0,0) only,
-// which every output class uses exactly once).  zero/nzero: optional buffer to clear in the same launch.
-__global__ void pack_convt_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias, int Cin, int Cout,
-                                          int nstages, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ zero,
-                                          int nzero) {
-  const int total = nstages * 4 * 4 * HB_NCOLS * 8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i & 7;
-    int r = i >> 3;
-    const int nrow = r % HB_NCOLS;
-    r /= HB_NCOLS;
-    const int kc = r & 3;
-    r >>= 2;
-    const int sh = r & 3;
-    const int st = r >> 2;
-    const int c = st * HB_KSTAGE + kc * 8 + e;
-    const int cls = nrow / HB_CLS, o = nrow % HB_CLS;
-    const int py = cls >> 1, px = cls & 1, dm = sh >> 1, dn = sh & 1;
-    float v = 0.f;
-    if (c < Cin && o < Cout && !(py == 0 && dm == 1) && !(px == 0 && dn == 1)) {
-      const int ky = py == 0 ? 1 : (dm ? 0 : 2);
-      const int kx = px == 0 ? 1 : (dn ? 0 : 2);
-      v = w[((size_t)c * Cout + o) * 9 + ky * 3 + kx];
-    } else if (bias && c == Cin && o < Cout && sh == 0) {
-      v = bias[o];
-    }
-    out[i] = __float2bfloat16_rn(v);
-  }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x) zero[i] = __float2bfloat16_rn(0.f);
-}
-
 // ---- everything a head call prepares, in one launch (head_prep.cuh) -------------------------------------------
+// forward packs: W[Cin][Cout][3][3] (fp32) -> B[stage][shift][kchunk][80][8] bf16; a non-null bias rides on input
+// channel `Cin` (the constant-one channel of the mid activations; shift (0,0) only, which every output class uses once)
 constexpr int PREP_GB_K = 80, PREP_GB_KC = 10, PREP_GB_CLS = 20;  // class-major K of the gradient operands (head_bwd_bf16.cu)
 
 __global__ void __launch_bounds__(256) head_prep_kernel(const __grid_constant__ PrepJobs J) {

@@ -230,35 +230,8 @@ static void launch_g2_build(const G2Src& S, int B, int C, int Hi, int Wi, __nv_b
   }
 }
 
-// ---- weight packing for the data-gradient GEMMs ----------------------------------------------------------
-// out[tile][shift][kchunk][r][8]: element (r, k) = W[tile*rows_per_tile + r][o][ky][kx] for k = cls*20 + o when
-// (cls, shift) is a valid tap, else 0.  rows_per_tile = 32 (layer 2, N operand) or 128 (layer 1, M operand).
-__global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, int Cin, int Cout, int ntiles, int rows_per_tile,
-                                          __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ zero, int nzero) {
-  const int total = ntiles * 4 * GB_KC * rows_per_tile * 8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i & 7;
-    int r = i >> 3;
-    const int row = r % rows_per_tile;
-    r /= rows_per_tile;
-    const int kc = r % GB_KC;
-    r /= GB_KC;
-    const int sh = r & 3;
-    const int tile = r >> 2;
-    const int c = tile * rows_per_tile + row;
-    const int k = kc * 8 + e;
-    const int cls = k / GB_CLS, o = k % GB_CLS;
-    const int py = cls >> 1, px = cls & 1, dm = sh >> 1, dn = sh & 1;
-    float v = 0.f;
-    if (c < Cin && o < Cout && !(py == 0 && dm == 1) && !(px == 0 && dn == 1)) {
-      const int ky = py == 0 ? 1 : (dm ? 0 : 2);
-      const int kx = px == 0 ? 1 : (dn ? 0 : 2);
-      v = w[((size_t)c * Cout + o) * 9 + ky * 3 + kx];
-    }
-    out[i] = __float2bfloat16_rn(v);
-  }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x) zero[i] = __float2bfloat16_rn(0.f);
-}
+// (the data-gradient operand packs  out[tile][shift][kchunk][r][8]: element (r, k) = W[tile*rows_per_tile + r][o][ky][kx]
+// for k = cls*20 + o when (cls, shift) is a valid tap, else 0  are produced by head_prep_kernel, head_bf16.cu)
 
 // =====================================================================================================
 // b2d: data gradient of the second deconv:  G2 -> d mid, emitted as G1 (+ bias gradient of layer 1)

@@ -12,7 +12,7 @@ enum { CONVT_ROWS_MID = 0, CONVT_ROWS_PLANES = 1, CONVT_ROWS_SOFTMAX = 2 };
 struct ConvtRowsParams {
   const __nv_bfloat16* X;    // [B][4*nst][L.rows][8] padded row layout of the conv input
   RowLayout L;
-  const __nv_bfloat16* wpk;  // [nst][4 shifts][4 kchunks][80][8] (pack_convt_weights_kernel)
+  const __nv_bfloat16* wpk;  // [nst][4 shifts][4 kchunks][80][8] (head_prep_kernel)
   const float* bias;         // [cout] added in the epilogue, or null (bias folded into the GEMM / irrelevant)
   int nst;                   // 32-channel K stages
   int B, cout, mode;

@@ -4,7 +4,7 @@
 // byte-for-byte the operand image the kernels keep in shared memory (zero column = horizontal halo, lead /
 // trail rows = vertical halo), so any run of image rows -- halo included -- is ONE contiguous bulk copy per
 // K-chunk instead of one copy per image row (the TMA unit spends ~50 cycles per copy, whatever its size).
-// Producers write only real pixels; zero_row_pads_kernel clears the pads once per buffer.
+// Producers write only real pixels; the head's preparation launch (head_prep.cuh) clears the pads of fresh buffers.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -28,10 +28,5 @@ __host__ __device__ inline RowLayout make_row_layout(int Hi, int Wi) {
   L.rows = (Hi * L.Pp + 2 * L.lead + 7) & ~7;
   return L;
 }
-
-// one thread per pad row entry: nslabs = B * kchunks slabs of L.rows rows
-__global__ void zero_row_pads_kernel(__nv_bfloat16* __restrict__ buf, RowLayout L, long long nslabs);
-
-int launch_zero_row_pads(__nv_bfloat16* buf, RowLayout L, long long nslabs, void* stream);
 
 }  // namespace lpb
