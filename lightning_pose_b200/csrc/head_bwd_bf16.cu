@@ -405,7 +405,8 @@ struct B3aParams {
   __nv_bfloat16* dfeat;      // [B][4*C4][(Hi/2)*(Wi/2)]
   int B, C4, Hi, Wi;         // shuffled-image geometry (Hi = 2H, Wi = 2W)
   int Hh;                    // image rows per band (multiple of 4)
-  int ncols;                 // TMEM columns per band = Hh * (Wi + 1) rounded up to 16 (<= 304)
+  int ncols;                 // TMEM columns per band = Hh * (Wi + 1) rounded up to 16 (<= 304; <= 256: double-buffered)
+  int backoff;
 };
 
 // A frame is processed in bands of Hh image rows (the accumulator of a band, N = Hh * (Wi + 1) pixels, must fit TMEM next
@@ -424,11 +425,14 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
   uint64_t* g_full = bars;       // [2]
   uint64_t* g_empty = bars + 2;  // [2]
   uint64_t* w_full = bars + 4;
-  uint64_t* t_full = bars + 5;
-  uint64_t* t_empty = bars + 6;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* t_full = bars + 5;   // [2]
+  uint64_t* t_empty = bars + 7;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntile = (P.C4 + 127) / 128;
+  // accumulator buffers: two when a band's columns fit twice into the 512 TMEM columns (the MMAs of band i + 1 then
+  // overlap the epilogue of band i), else one
+  const int nbuf = P.ncols <= 256 ? 2 : 1;
   const int mt = blockIdx.x % ntile, slot = blockIdx.x / ntile, nslot = gridDim.x / ntile;
 
   for (int i = tid; i < 2 * g_bytes / 16; i += B3A_THREADS) reinterpret_cast<uint4*>(Gs)[i] = make_uint4(0, 0, 0, 0);
@@ -438,8 +442,10 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
       mbar_init(&g_empty[st], 1);
     }
     mbar_init(w_full, 1);
-    mbar_init(t_full, 1);
-    mbar_init(t_empty, 256);
+    for (int st = 0; st < 2; ++st) {
+      mbar_init(&t_full[st], 1);
+      mbar_init(&t_empty[st], 256);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
@@ -481,8 +487,10 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
     for (int b = slot; b < P.B; b += nslot)
       for (int band = 0; band < nbands; ++band, ++it) {
         const int st = it & 1;
+        const int tb = it % nbuf, tph = (it / nbuf) & 1;
+        const uint32_t dcol = tmem_base + tb * 256;
         mbar_wait(&g_full[st], (it >> 1) & 1);
-        mbar_wait(t_empty, (it & 1) ^ 1);
+        mbar_wait(&t_empty[tb], tph ^ 1);
         tc::fence_after_sync();
         if (lane == 0) {
           const uint32_t g0 = smem_u32(Gs + (size_t)st * g_bytes);
@@ -494,12 +502,12 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
               const uint32_t ww = w0 + ((sh * GB_KC + 2 * k16) * 128) * 16;
               const uint32_t gg = g0 + (2 * k16) * lbo_g + (LEAD - shift_rows) * 16;
               const uint64_t wd = tc::make_smem_desc(ww, lbo_w, 128);
-              tc::umma_bf16(tmem_base, wd, tc::make_smem_desc(gg, lbo_g, 128), idesc0, (sh | k16) != 0 ? 1u : 0u);
+              tc::umma_bf16(dcol, wd, tc::make_smem_desc(gg, lbo_g, 128), idesc0, (sh | k16) != 0 ? 1u : 0u);
               if (n1 > 0)
-                tc::umma_bf16(tmem_base + n0, wd, tc::make_smem_desc(gg + n0 * 16, lbo_g, 128), idesc1, (sh | k16) != 0 ? 1u : 0u);
+                tc::umma_bf16(dcol + n0, wd, tc::make_smem_desc(gg + n0 * 16, lbo_g, 128), idesc1, (sh | k16) != 0 ? 1u : 0u);
             }
           }
-          tc::umma_commit(t_full);
+          tc::umma_commit(&t_full[tb]);
           tc::umma_commit(&g_empty[st]);
         }
         __syncwarp();
@@ -518,7 +526,9 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
       for (int band = 0; band < nbands; ++band, ++it) {
         const int y0 = band * Hh, hb = min(Hh, Hi - y0);
         const int npairs = hb / 4;  // feature-row pairs in this band
-        mbar_wait(t_full, it & 1);
+        const int tb = it % nbuf, tph = (it / nbuf) & 1;
+        const uint32_t dcol = tmem_base + tb * 256;
+        mbar_wait_idle(&t_full[tb], tph, P.backoff);
         tc::fence_after_sync();
         for (int item = e; item < 2 * npairs; item += 2) {
           const int di = item & 1, ip = item >> 1;
@@ -528,7 +538,7 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
           for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int k = 0; k < NCH; ++k)
-              tc::tmem_ld16_async(tmem_base + ((uint32_t)(32 * q) << 16) + (ml + 2 * r) * Pp + 16 * k, &v[r][16 * k]);
+              tc::tmem_ld16_async(dcol + ((uint32_t)(32 * q) << 16) + (ml + 2 * r) * Pp + 16 * k, &v[r][16 * k]);
           tc::tmem_ld_wait();
           if (c < P.C4) {
             const int i0 = y0 / 2 + 2 * ip;  // first feature row of the pair
@@ -552,7 +562,7 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
           }
         }
         tc::fence_before_sync();
-        tc::mbar_arrive(t_empty);
+        tc::mbar_arrive(&t_empty[tb]);
       }
   }
   tc::fence_before_sync();
@@ -776,7 +786,8 @@ __global__ void __launch_bounds__(256) rows_colsum_kernel(const __nv_bfloat16* _
 
 // largest rows-per-band Hh (multiple of 4) whose accumulator fits the b3a TMEM tiling
 static int b3a_band_rows(int Hi1, int Wi1) {
-  int hh = (304 / (Wi1 + 1)) & ~3;
+  int hh = (256 / (Wi1 + 1)) & ~3;  // two accumulator buffers fit
+  if (hh < 4) hh = (304 / (Wi1 + 1)) & ~3;  // wide maps: one buffer
   if (hh > Hi1) hh = Hi1;
   return hh;
 }
@@ -929,8 +940,9 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
     p.Wi = Wi1;
     p.Hh = Hh;
     p.ncols = (Hh * (Wi1 + 1) + 15) & ~15;
+    p.backoff = g_tuning[LPB_TUNE_WAIT_BACKOFF];
     const int rows_alloc = (Wi1 + 2 + p.ncols + 7) & ~7;
-    const size_t smem = (size_t)2 * GB_KC * rows_alloc * 16 + (size_t)4 * GB_KC * 128 * 16 + 128;
+    const size_t smem = (size_t)2 * GB_KC * rows_alloc * 16 + (size_t)4 * GB_KC * 128 * 16 + 160;
     LPB_REQUIRE(smem <= 225 * 1024, "head_bwd_bf16: layer-1 operands need %zu B shared memory", smem);
     int slots = sms / ntile1;
     if (slots < 1) slots = 1;
