@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B
   __shared__ float sdot[GB_CLS];
   __shared__ int4 smeta[GB_CLS];
   __shared__ float wtile[HAS_WIN ? GB_CLS * 2 * G2B_MROWS * 32 : 1];
+  __shared__ unsigned shit;
   const int m0 = t0 / Wi;
   if (threadIdx.x < GB_CLS) {
     float d = 0.f;
@@ -102,6 +103,13 @@ __global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B
     }
     sdot[threadIdx.x] = d;
     smeta[threadIdx.x] = mt;
+    if (HAS_WIN) {
+      // does this plane's window (or its dense fallback) touch the CTA's output rows [2 m0, 2 m0 + 2 MROWS)?  A 32x32
+      // window covers a ninth of a 96x96 plane: most (CTA, plane) pairs skip the look-ups altogether (uniform branch)
+      const bool hit = mt.z == 2 || (mt.z == 1 && mt.x < 2 * m0 + 2 * G2B_MROWS && mt.x + 32 > 2 * m0);
+      const unsigned bal = __ballot_sync((1u << GB_CLS) - 1, hit);
+      if (threadIdx.x == 0) shit = bal;
+    }
   }
   if (HAS_WIN) {
     __syncthreads();
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B
     for (int k = 0; k < NSTEP; ++k) {
       const int r = wq + k * (G2B_THREADS / 32), o = r / (2 * G2B_MROWS), yl = r - o * (2 * G2B_MROWS);
       float v = 0.f;
-      if (o < C) {
+      if (o < C && ((shit >> o) & 1u)) {
         const int4 mt = smeta[o];
         const int ly = 2 * m0 + yl - mt.x;
         if (mt.z == 1 && (unsigned)ly < 32u) v = __ldg(S.win + ((size_t)b * C + o) * 1024 + ly * 32 + lane);
@@ -144,9 +152,10 @@ __global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B
     }
     if (HAS_WIN) {
       const float* wrow = wtile + (2 * (m - m0) + py) * 32;
+      const unsigned hits = shit;
 #pragma unroll
       for (int o = 0; o < GB_CLS; ++o) {
-        if (o < C) {
+        if (o < C && ((hits >> o) & 1u)) {
           const int4 mt = smeta[o];
           const int lx = x - mt.y;  // window column of output pixel x; x + 1 -> lx + 1
           const float w0 = wrow[o * (64 * G2B_MROWS) + min(max(lx, 0), 31)];
