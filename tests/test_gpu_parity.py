@@ -1082,3 +1082,38 @@ def test_multiview_transformer_tracker_config4(lpb, dev):
     loss.backward()
     assert torch.isfinite(loss) and tr.view_embeddings.grad is not None and float(tr.view_embeddings.grad.abs().max()) > 0
     assert tr.patch_embed.proj.weight.grad is not None and torch.isfinite(tr.patch_embed.proj.weight.grad).all()
+
+
+def test_kernel_variants_agree(lpb, dev):
+    """Every LPB_TUNE_* switch selects a different implementation of the SAME stage: results must agree to rounding
+    (row-form vs block-form operand producer: bit-identical operands; softmax epilogues and decode drivers: same math
+    in a different order)."""
+    from lightning_pose_b200._lib import lib
+
+    head = _rand_head("resnet50", 2048, 17, gain=4.0, seed=41).to(dev)
+    feats = (torch.randn(6, 2048, 12, 12) * 0.5).bfloat16().to(dev)
+    gk = torch.randn(6, 34, device=dev)
+
+    def run():
+        head.zero_grad()
+        f = feats.clone().requires_grad_(True)
+        hm, kp, cf = head.forward_with_keypoints(f)
+        ((kp * gk).sum() * 1e-3 + (hm * hm).sum()).backward()
+        return hm.detach().clone(), kp.detach().clone(), cf.detach().clone(), f.grad.float().clone(), list(head.upsampling_layers)[1].weight.grad.clone()
+
+    saved = [lib.lpb_get_tuning(k) for k in range(4)]
+    try:
+        for k in range(4):
+            lib.lpb_set_tuning(k, 1)
+        new = run()
+        for k in range(4):
+            lib.lpb_set_tuning(k, 0)
+        old = run()
+    finally:
+        for k, v in enumerate(saved):
+            lib.lpb_set_tuning(k, v)
+    close(new[0], old[0], atol=1e-9, rtol=2e-5)   # heatmaps
+    close(new[1], old[1], atol=2e-3, rtol=1e-5)   # keypoints (T = 1000 amplifies the last ulp of a heatmap)
+    close(new[2], old[2], atol=1e-5, rtol=1e-4)   # confidences
+    for a, b in zip(new[3:], old[3:]):
+        assert float((a - b).abs().max()) <= 2e-3 * float(b.abs().max()) + 1e-12
