@@ -147,3 +147,56 @@ def test_reference_arm_does_not_import_the_product():
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     assert res.stdout.strip().splitlines()[-1] in ("reference", "port")
+
+
+def test_round2_entry_points_validate_arguments_without_gpu():
+    """Every entry added in round 2 rejects null / malformed arguments with an error code (never a crash), and the
+    shape planner works without a device (callers size buffers with it)."""
+    import ctypes as C
+
+    from lightning_pose_b200 import _lib
+
+    L = _lib.lib
+    plan = C.c_int(-1)
+    assert L.lpb_head_bf16_plan(2048, 12, 12, 17, 17, C.byref(plan)) == 0 and plan.value == 1   # cfg 2: whole frame in TMEM
+    assert L.lpb_head_bf16_plan(2048, 16, 16, 17, 17, C.byref(plan)) == 0 and plan.value == 0   # cfg 5: banded
+    assert L.lpb_head_bf16_plan(384, 16, 16, 17, 0, C.byref(plan)) == 0 and plan.value == 0     # cfg 3: one deconv
+    assert L.lpb_head_bf16_plan(384, 24, 24, 17, 0, C.byref(plan)) == 0 and plan.value == 0     # cfg 4
+    assert L.lpb_head_bf16_plan(100, 12, 12, 17, 17, C.byref(plan)) == -1                          # C % 128
+    assert L.lpb_head_bf16_plan(2048, 12, 12, 20, 17, C.byref(plan)) == -1                         # c1 must leave the ones channel
+    n = C.c_size_t(0)
+    assert L.lpb_head_bf16_workspace_bytes(2, 384, 16, 16, 17, 0, C.byref(n)) == 0 and n.value == 3 * 20480 + 20480  # no mid for one deconv
+    assert L.lpb_head_bwd_bf16_workspace_bytes(2, 384, 16, 16, 17, 0, C.byref(n)) == 0 and n.value > 0
+    for rc in (
+        L.lpb_convt_fwd_f32(None, 1, 4, 4, 4, 1, None, None, 2, None, None),
+        L.lpb_convt_bwd_f32(None, None, 1, 4, 4, 4, 1, None, 2, None, None, None, None),
+        L.lpb_plane_softmax_f32(None, 1, 16, None),
+        L.lpb_temporal_heatmap_loss_bwd(None, None, None, 4, 2, 8, 8, 0, None, 0.1, None, None, None),
+        L.lpb_keypoints_mask_oob(None, 4, 64.0, 64.0, None, None),
+        L.lpb_crnn_prepare(None, None, None, None, 5, 16, None, None, None),
+        L.lpb_crnn_combine_fwd(None, None, None, 1, 5, 5, 8, 8, None, None, None, None, None, None),
+        L.lpb_crnn_combine_bwd(None, None, None, None, 1, 5, 5, 8, 8, None, None, None, None, None, None, None, None, None, None, None),
+        L.lpb_context_gather(None, 4, 64, 5, None, None),
+        L.lpb_frames_normalize(None, 1, 8, 8, 8, 8, None, None, 0, 0, None, None),
+        L.lpb_pack_predictions(None, None, 1, 2, None, 4, None, 0, None),
+        L.lpb_head_fwd_bf16(None, 1, 384, 16, 16, None, None, 17, None, None, 0, 1, None, None, None, None),
+        L.lpb_head_bwd_bf16(None, None, None, None, None, None, None, 1, 384, 16, 16, None, 17, None, 0, None, None, None, None, None, None, None),
+    ):
+        assert rc == -1, (rc, L.lpb_last_error())
+    assert L.lpb_context_gather(C.c_void_p(16), 4, 24, 5, C.c_void_p(16), None) == -1  # items must be 16-byte multiples
+    assert L.lpb_set_tuning(99, 1) == -1 and L.lpb_get_tuning(99) == -1
+    for k in range(4):
+        assert L.lpb_get_tuning(k) in (0, 1)
+
+
+def test_head_shape_planner_python_side():
+    from lightning_pose_b200 import ops
+
+    ok = ops.head_bf16_supported
+    assert ok((8, 2048, 12, 12), [17, 17], train=True) and ok((8, 2048, 16, 16), [17, 17], train=True)   # cfg 2, cfg 5
+    assert ok((8, 384, 16, 16), [17], train=True) and ok((8, 384, 24, 24), [17], train=True)              # cfg 3, cfg 4
+    assert not ok((8, 2048, 13, 13), [17, 17], train=False)      # H*W % 8
+    assert not ok((8, 2048, 12, 12), [17, 17, 17], train=False)  # three deconvs: fp32 kernels
+    assert not ok((8, 2048, 12, 12), [20, 17], train=False)      # no room for the ones channel
+    assert ok((8, 512, 6, 4), [17, 17], train=False) and not ok((8, 512, 6, 20), [17, 17], train=True)  # width outside the dgrad epilogue set
+    assert not ok((8, 384, 15, 16), [17], train=True) and ok((8, 384, 15, 16), [17], train=False)      # odd height: forward only
