@@ -121,8 +121,12 @@ class BatchedPredictor:
     """
 
     def __init__(self, head, num_keypoints: int, n_frames: int, chunk: int, image_hw: tuple[int, int],
-                 features_of: Callable[[torch.Tensor], torch.Tensor] | None = None, device=None, use_graph: bool = True) -> None:
+                 features_of: Callable[[torch.Tensor], torch.Tensor] | None = None, device=None, use_graph: bool = True,
+                 sub_chunk: int | None = None) -> None:
         self.head, self.k, self.n_frames, self.chunk = head, int(num_keypoints), int(n_frames), int(chunk)
+        # frames per head / decode call inside a chunk: small enough that the heatmaps written by the head are still in
+        # the 126 MB L2 when the decode reads them (None: the whole chunk at once)
+        self.sub_chunk = int(sub_chunk) if sub_chunk else self.chunk
         self.image_hw = (int(image_hw[0]), int(image_hw[1]))
         self.features_of = features_of
         self.device = torch.device(device) if device is not None else next(head.parameters()).device
@@ -138,10 +142,11 @@ class BatchedPredictor:
     def _chunk(self, x: torch.Tensor, bbox: torch.Tensor) -> None:
         feats = self.features_of(x) if self.features_of is not None else x
         with torch.no_grad():
-            heatmaps = self.head(feats)
-            kp, cf = self.head.run_subpixelmaxima(heatmaps)
-            kp = ops.remap_keypoints(kp, None, bbox, self.image_hw[0], self.image_hw[1])  # model -> frame (bboxes.py:222-288)
-            ops.pack_predictions(kp, cf, self.table, cursor=self.cursor)
+            for i in range(0, self.chunk, self.sub_chunk):
+                heatmaps = self.head(feats[i : i + self.sub_chunk])
+                kp, cf = self.head.run_subpixelmaxima(heatmaps)
+                kp = ops.remap_keypoints(kp, None, bbox[i : i + self.sub_chunk], self.image_hw[0], self.image_hw[1])  # model -> frame (bboxes.py:222-288)
+                ops.pack_predictions(kp, cf, self.table, cursor=self.cursor)
 
     def _capture(self, x: torch.Tensor, bbox: torch.Tensor) -> None:
         self._static_in = torch.empty_like(x)

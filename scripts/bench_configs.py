@@ -74,8 +74,8 @@ res["cfg3_mhcrnn_backward"] = {"frames": 64, "ms": ms, "us_per_frame": 1e3 * ms 
 head = head_for("resnet50", 2048).eval()
 chunk, nchunks = 96, 100
 pool = [(torch.randn(chunk, 2048, 16, 16, device=dev) * 0.5).bfloat16() for _ in range(4)]
-for use_graph in (True, False):
-    bp = BatchedPredictor(head, K, chunk * nchunks, chunk, (512, 512), use_graph=use_graph)
+for use_graph, sub in ((True, None), (False, None), (True, 24), (True, 48)):
+    bp = BatchedPredictor(head, K, chunk * nchunks, chunk, (512, 512), use_graph=use_graph, sub_chunk=sub)
     bp.feed(pool[0])  # capture / warm
     bp.cursor.zero_()
     torch.cuda.synchronize()
@@ -87,7 +87,7 @@ for use_graph in (True, False):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     nb = chunk * nchunks * (2048 * 256 * 2 + 204)
-    res[f"cfg5_batched_inference_{'graph' if use_graph else 'eager'}"] = {
+    res[f"cfg5_batched_inference_{'graph' if use_graph else 'eager'}_sub{sub or chunk}"] = {
         "frames": chunk * nchunks, "ms": ms, "frames_per_s": chunk * nchunks / ms * 1e3, "algorithmic_bytes": nb, "frac_hbm": nb / ms / 1e6 / pk["hbm_gbs"],
         "note": "features resident on the device (includes the D2D copy of each chunk into the graph's static input); K1+K2 algorithmic bytes = features + 204 B/frame"}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
