@@ -416,7 +416,8 @@ def test_head_bf16_tcgen05_vs_oracle(lpb, dev, shape):
     feats = (torch.randn(b, c, fh, fw) * 0.5).bfloat16()
     logits_ref, hm_ref = _bf16_head_oracle(feats, head)
     head = head.to(dev)
-    out = head(feats.to(dev))
+    with torch.no_grad():  # forward-only: every listed shape is inside the tcgen05 forward tiling (training on the 4x6
+        out = head(feats.to(dev))  # map, whose width has no dgrad epilogue, is routed to the fp32 kernels instead)
     assert out.dtype == torch.float32 and out.shape == hm_ref.shape
     # 1e-2 relative (north star, bf16).  A mid activation that sits on a bf16 rounding boundary may round the
     # other way than in the oracle (fp32 summation order), moving a few logits by ~1 bf16 ulp: allow <= 0.01 %
@@ -425,7 +426,8 @@ def test_head_bf16_tcgen05_vs_oracle(lpb, dev, shape):
     assert float(rel.max()) < 3e-2 and float((rel > 1e-2).float().mean()) < 1e-4
     close(out.sum((2, 3)), torch.ones(b, 17), atol=1e-5)
     head.final_softmax = False
-    close(head(feats.to(dev)), logits_ref, atol=1e-2 * float(logits_ref.abs().max()), rtol=1e-2)
+    with torch.no_grad():
+        close(head(feats.to(dev)), logits_ref, atol=1e-2 * float(logits_ref.abs().max()), rtol=1e-2)
     # decode of the bf16-path heatmaps agrees with the decode of the oracle heatmaps to sub-pixel level
     kp, cf = lpb.decode_softargmax(out, 2, 1000.0)
     kp_ref, cf_ref = O.decode_softargmax(hm_ref, 2, 1000.0)
@@ -826,8 +828,8 @@ def test_head_fp32_native_backward_any_depth(lpb, dev, cfg):
     close(out, ref, atol=1e-9)
     (out * gout.to(dev)).sum().backward()
     close(f.grad, f_ref.grad, atol=1e-7, rtol=1e-3)
-    for d, w_ref, b_ref in zip(deconvs, ws, bs):
-        close(d.weight.grad, w_ref.grad, atol=1e-7, rtol=1e-3)
+    for d, w_ref, b_ref in zip(deconvs, ws, bs):  # atomically accumulated fp32 sums: absolute floor ~ a few ulps of the largest entries
+        close(d.weight.grad, w_ref.grad, atol=1e-6 * max(1.0, float(w_ref.grad.abs().max())), rtol=1e-3)
         close(d.bias.grad, b_ref.grad, atol=2e-6, rtol=1e-3)
 
 
