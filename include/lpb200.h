@@ -40,10 +40,10 @@ const char* lpb_build_arch(void);     /* "sm_100a" */
 
 /* kernel-variant switches: a bring-up / profiling aid (A/B two implementations of the same stage on the same inputs);
  * every variant computes the same results.  lpb_get_tuning returns -1 for an unknown key. */
-#define LPB_TUNE_K1A_ROW_TRANSPOSER 0   /* 1 (default): row-per-lane operand transposer, coalesced saved-copy stores */
+#define LPB_TUNE_K1A_ROW_TRANSPOSER 0   /* 1: row-per-lane operand transposer (coalesced saved-copy stores); 0 (default): 8x8 register blocks */
 #define LPB_TUNE_SOFTMAX_EPILOGUE_V2 1  /* 1 (default): softmax epilogue with one vote per tile and hoisted addressing */
 #define LPB_TUNE_WAIT_BACKOFF 2         /* 1 (default): idle warps back off between mbarrier polls */
-#define LPB_TUNE_DECODE_RING 3          /* 1 (default): soft-argmax planes staged once in shared memory by a bulk-copy ring */
+#define LPB_TUNE_DECODE_RING 3          /* 1: soft-argmax planes staged once in shared memory by a bulk-copy ring; 0 (default): warp per plane from global */
 #define LPB_TUNE_COUNT 4
 int lpb_set_tuning(int key, int value);
 int lpb_get_tuning(int key);

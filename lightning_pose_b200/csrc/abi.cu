@@ -13,10 +13,10 @@ extern "C" const char* lpb_build_arch(void) { return "sm_100a"; }
 // launch time only.
 namespace lpb {
 int g_tuning[LPB_TUNE_COUNT] = {
-    1,  // LPB_TUNE_K1A_ROW_TRANSPOSER
+    0,  // LPB_TUNE_K1A_ROW_TRANSPOSER (measured: 2x the instructions of the block form, slower)
     1,  // LPB_TUNE_SOFTMAX_EPILOGUE_V2
     1,  // LPB_TUNE_WAIT_BACKOFF
-    1,  // LPB_TUNE_DECODE_RING
+    0,  // LPB_TUNE_DECODE_RING (measured: 1.0x DRAM traffic but too few resident warps: 2x slower at 96x96)
 };
 }
 extern "C" int lpb_set_tuning(int key, int value) {

@@ -830,7 +830,11 @@ __global__ void __launch_bounds__(32 * (DECR_WARPS + 1), 1) decode_fwd_ring_kern
     }
     return;
   }
-  for (long long i = warp; i < mine; i += DECR_WARPS) {
+  // a consumer may wait for phase p of a slot only once phase p - 1 has completed (a parity wait cannot tell phases two
+  // apart): with static assignment that holds iff the number of consumers does not exceed the number of slots
+  const int ncons = nslots < DECR_WARPS ? nslots : DECR_WARPS;
+  if (warp >= ncons) return;
+  for (long long i = warp; i < mine; i += ncons) {
     const int sl = (int)(i % nslots);
     mbar_wait(&full[sl], (uint32_t)((i / nslots) & 1));
     decode_plane_warp<DS, true>(P, first + i * stride, reinterpret_cast<const float*>(slots + (size_t)sl * plane_bytes),

@@ -25,6 +25,7 @@ FILES = [
     "lightning_pose/data/heatmaps.py",
     "lightning_pose/data/utils.py",
     "lightning_pose/data/bboxes.py",
+    "lightning_pose/data/datatypes.py",  # TypedDicts imported by bboxes.py
     "lightning_pose/losses/losses.py",
     "lightning_pose/losses/factory.py",
     "lightning_pose/utils/pca.py",

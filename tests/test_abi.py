@@ -147,6 +147,12 @@ def test_reference_arm_does_not_import_the_product():
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     assert res.stdout.strip().splitlines()[-1] in ("reference", "port")
+    # the staged copy (what the GPU box executes: it has no /root/reference) must be self-sufficient
+    staged = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.isdir(os.path.join(staged, "lightning_pose")):
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env={**os.environ, "LP_REFERENCE_ROOT": staged})
+        assert res.returncode == 0, res.stderr[-2000:]
+        assert res.stdout.strip().splitlines()[-1] == "reference"
 
 
 def test_round2_entry_points_validate_arguments_without_gpu():
