@@ -169,6 +169,7 @@ struct K1aParams {
   int c1, nstages;
   int row_transposer;         // 1: row-per-lane transposer (coalesced operand-copy stores); 0: 8x8 register-block transposer
   int backoff;                // idle warps sleep between barrier polls
+  int xs_bulk;                // 1: the saved operand copy is written by TMA bulk stores straight from the operand stage
   HeadGeom g;
 };
 
@@ -188,15 +189,18 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
   uint64_t* tmem_full = bars + 8;
   uint64_t* tmem_empty = bars + 9;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  unsigned char* zreg = reinterpret_cast<unsigned char*>(bars) + 128;  // 1 KB of zeros: source of the saved copy's lead rows
+  const bool xs_bulk = P.xs && P.xs_bulk;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // zero the operand stages once: halo rows/columns are never written again
   for (int i = tid; i < K1A_ASTAGES * stage_bytes / 16; i += K1A_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < 64) reinterpret_cast<uint4*>(zreg)[tid] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&full[s], 32 * K1A_TW + 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], xs_bulk ? 2 : 1);  // the MMAs have read the stage (+ the bulk stores of the saved copy have)
       mbar_init(&raw_full[s], 1);
       mbar_init(&raw_empty[s], 32 * K1A_TW);
     }
@@ -235,7 +239,29 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
         mbar_expect_tx(&full[s], HB_BSTAGE_BYTES);
         bulk_g2s(stage_base + s * stage_bytes + a_stage_bytes,
                  reinterpret_cast<const unsigned char*>(P.wpk) + (size_t)st * HB_BSTAGE_BYTES, HB_BSTAGE_BYTES, &full[s]);
+        if (xs_bulk) {
+          // The operand stage IS the saved copy's layout (row_layout.cuh): once the producers have filled it, each
+          // K-chunk goes to global memory as two bulk stores (the zero lead rows, then raster + halo rows) -- fully
+          // coalesced, asynchronous, and no store instruction on the producers' LSU path (their 16-byte stores at a
+          // 256-byte stride were k1a's critical path in training).  The stage is released once the MMAs AND these
+          // stores have read it.
+          mbar_wait(&full[s], (it / K1A_ASTAGES) & 1);
+          const int b = blockIdx.x + (it / P.nstages) * gridDim.x;
+          unsigned char* slab = reinterpret_cast<unsigned char*>(P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)P.Lxs.rows * 8);
+          const unsigned char* As = stage_base + s * stage_bytes;
+          const uint32_t lead_b = (uint32_t)P.Lxs.lead * 16, body_b = (uint32_t)(g.rows + g.P + 1) * 16;
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc) {
+            unsigned char* dst = slab + (size_t)kc * P.Lxs.rows * 16;
+            bulk_s2g(dst, zreg, lead_b);
+            bulk_s2g(dst + lead_b, As + (size_t)kc * g.rows_alloc * 16, body_b);
+          }
+          bulk_commit_group();
+          bulk_wait_group_read0();
+          tc::mbar_arrive(&empty[s]);
+        }
       }
+      if (xs_bulk) bulk_wait_group0();  // the copies are in global memory before the kernel ends
     }
   } else if (warp < K1A_TW && P.row_transposer) {
     // ================= transposers, row form: lane = shuffled pixel n of one image row ==================
@@ -252,7 +278,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
       mbar_wait(&empty[s], ((it / K1A_ASTAGES) & 1) ^ 1);
       unsigned char* As = stage_base + s * stage_bytes;
       unsigned char* xs_st = nullptr;
-      if (P.xs) {
+      if (P.xs && !xs_bulk) {
         const int b = blockIdx.x + (it / P.nstages) * gridDim.x, st = it % P.nstages;
         xs_st = reinterpret_cast<unsigned char*>(P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)P.Lxs.rows * 8);
       }
@@ -310,7 +336,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
       mbar_wait(&empty[s], ((it / K1A_ASTAGES) & 1) ^ 1);
       unsigned char* As = stage_base + s * stage_bytes;
       unsigned char* xs_st = nullptr;  // this (frame, stage)'s 4 K-chunks of the saved copy
-      if (P.xs) {
+      if (P.xs && !xs_bulk) {
         const int b = blockIdx.x + (it / P.nstages) * gridDim.x, st = it % P.nstages;
         xs_st = reinterpret_cast<unsigned char*>(P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)P.Lxs.rows * 8);
       }
@@ -661,7 +687,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 2) k1b_convt_softmax_kernel(const
 }
 
 static size_t k1a_smem_bytes(const HeadGeom& g, int HW) {
-  return (size_t)K1A_ASTAGES * (4 * g.rows_alloc * 16 + HB_BSTAGE_BYTES) + (size_t)K1A_RSTAGES * 4 * HB_KSTAGE * HW * 2 + 128;
+  return (size_t)K1A_ASTAGES * (4 * g.rows_alloc * 16 + HB_BSTAGE_BYTES) + (size_t)K1A_RSTAGES * 4 * HB_KSTAGE * HW * 2 + 128 + 1024;
 }
 static size_t k1b_smem_bytes(const HeadGeom& g) {
   return (size_t)4 * g.rows_alloc * 16 + HB_BSTAGE_BYTES + (2 * HB_CLS * 8 + 2 * HB_CLS + 8) * sizeof(float) + 64;
@@ -683,7 +709,7 @@ __host__ inline HeadGeom make_half_geom(int Hh, int Wi) {
 static bool head_fast_path(int C, int H, int W, int c2, int max_smem) {
   using namespace lpb;
   if (c2 <= 0) return false;
-  if (!((W >= 7 || W == 4 || W == 6) && H * W <= 192)) return false;
+  if (!((W >= 7 || W == 4 || W == 6) && H * W <= 192 && W <= 31)) return false;  // W <= 31: the saved copy's lead rows fit the 1 KB zero source
   const HeadGeom g1 = make_geom(2 * H, 2 * W), g2 = make_half_geom(2 * H, 4 * W);
   if (g1.tiles * HB_NCOLS > 512) return false;
   return (int64_t)k1a_smem_bytes(g1, H * W) <= max_smem && (int64_t)k1b_smem_bytes(g2) <= max_smem;
@@ -765,7 +791,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
       jobs.fpack[1] = {w2, final_softmax ? nullptr : b2, c1, c2, 1, wp2};
       jobs.pads[0] = {mid, Lmid, (long long)B * 4};
     }
-    if (fast && saved_xs) jobs.pads[1] = {static_cast<__nv_bfloat16*>(saved_xs), Lxs, (long long)B * (C / 32)};  // (the banded path's shuffle kernel writes its own pads)
+    if (fast && saved_xs && !g_tuning[LPB_TUNE_K1A_BULK_XS]) jobs.pads[1] = {static_cast<__nv_bfloat16*>(saved_xs), Lxs, (long long)B * (C / 32)};  // (the banded path's shuffle kernel writes its own pads)
     launch_head_prep(jobs, s);
   }
   if (!fast) {
@@ -828,6 +854,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   pa.nstages = nst;
   pa.row_transposer = g_tuning[LPB_TUNE_K1A_ROW_TRANSPOSER];
   pa.backoff = g_tuning[LPB_TUNE_WAIT_BACKOFF];
+  pa.xs_bulk = g_tuning[LPB_TUNE_K1A_BULK_XS];
   pa.g = g1;
   LPB_CUDA(cudaFuncSetAttribute(k1a_shuffle_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
   k1a_shuffle_convt_kernel<<<B < sms ? B : sms, K1A_THREADS, s1, s>>>(pa);
