@@ -44,7 +44,7 @@ const char* lpb_build_arch(void);     /* "sm_100a" */
 #define LPB_TUNE_SOFTMAX_EPILOGUE_V2 1  /* 1 (default): softmax epilogue with one vote per tile and hoisted addressing */
 #define LPB_TUNE_WAIT_BACKOFF 2         /* 1 (default): idle warps back off between mbarrier polls */
 #define LPB_TUNE_DECODE_RING 3          /* 1: soft-argmax planes staged once in shared memory by a bulk-copy ring; 0 (default): warp per plane from global */
-#define LPB_TUNE_K1A_BULK_XS 4          /* 1 (default): the saved operand copy leaves k1a by TMA bulk stores from the operand stage */
+#define LPB_TUNE_K1A_BULK_XS 4          /* 1: the saved operand copy leaves k1a by TMA bulk stores from the operand stage; 0 (default): producer stores */
 #define LPB_TUNE_COUNT 5
 int lpb_set_tuning(int key, int value);
 int lpb_get_tuning(int key);

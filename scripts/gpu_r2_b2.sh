@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
 echo "bench exit $?"; tail -c 3500 gpurun_out/r2_bench.json; tail -3 gpurun_out/r2_bench.err
-for v in "0=0" "1=0" "2=0" "3=0" "0=0,1=0,2=0,3=0"; do
+for v in "0=1" "1=0" "2=0" "3=1" "4=1"; do
   LPB_TUNE="$v" timeout 400 python bench.py --steps 10 --warmup 3 --no-flat --no-cpu-baseline > "gpurun_out/r2_bench_tune_${v//[=,]/_}.json" 2>/dev/null
   echo "tune $v:"; python - "$v" <<'PY'
 import json,sys
