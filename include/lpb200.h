@@ -45,7 +45,9 @@ const char* lpb_build_arch(void);     /* "sm_100a" */
 #define LPB_TUNE_WAIT_BACKOFF 2         /* 1 (default): idle warps back off between mbarrier polls */
 #define LPB_TUNE_DECODE_RING 3          /* 1: soft-argmax planes staged once in shared memory by a bulk-copy ring; 0 (default): warp per plane from global */
 #define LPB_TUNE_K1A_BULK_XS 4          /* 1: the saved operand copy leaves k1a by TMA bulk stores from the operand stage; 0 (default): producer stores */
-#define LPB_TUNE_COUNT 5
+#define LPB_TUNE_DECODE_L2_HINTS 5      /* 1 (default): L2 evict_last / evict_first hints on the decode's two sweeps of a plane */
+#define LPB_TUNE_B3A_PREFETCH 6         /* 1 (default): b3a epilogue issues the next item's TMEM loads before storing the current one */
+#define LPB_TUNE_COUNT 7
 int lpb_set_tuning(int key, int value);
 int lpb_get_tuning(int key);
 

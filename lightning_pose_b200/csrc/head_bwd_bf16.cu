@@ -415,7 +415,7 @@ struct B3aParams {
   int B, C4, Hi, Wi;         // shuffled-image geometry (Hi = 2H, Wi = 2W)
   int Hh;                    // image rows per band (multiple of 4)
   int ncols;                 // TMEM columns per band = Hh * (Wi + 1) rounded up to 16 (<= 304; <= 256: double-buffered)
-  int backoff;
+  int backoff, prefetch;
 };
 
 // A frame is processed in bands of Hh image rows (the accumulator of a band, N = Hh * (Wi + 1) pixels, must fit TMEM next
@@ -539,35 +539,58 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
         const uint32_t dcol = tmem_base + tb * 256;
         mbar_wait_idle(&t_full[tb], tph, P.backoff);
         tc::fence_after_sync();
-        for (int item = e; item < 2 * npairs; item += 2) {
-          const int di = item & 1, ip = item >> 1;
-          const int ml = 4 * ip + di;  // first accumulator row of the item within this band
-          float v[2][NCH * 16];
+        auto issue = [&](int item, float (&buf)[2][NCH * 16]) {
+          const int ml = 4 * (item >> 1) + (item & 1);  // first accumulator row of the item within this band
 #pragma unroll
           for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int k = 0; k < NCH; ++k)
-              tc::tmem_ld16_async(dcol + ((uint32_t)(32 * q) << 16) + (ml + 2 * r) * Pp + 16 * k, &v[r][16 * k]);
-          tc::tmem_ld_wait();
-          if (c < P.C4) {
-            const int i0 = y0 / 2 + 2 * ip;  // first feature row of the pair
+              tc::tmem_ld16_async(dcol + ((uint32_t)(32 * q) << 16) + (ml + 2 * r) * Pp + 16 * k, &buf[r][16 * k]);
+        };
+        auto emit = [&](int item, const float (&v)[2][NCH * 16]) {
+          if (c >= P.C4) return;
+          const int di = item & 1, ip = item >> 1;
+          const int i0 = y0 / 2 + 2 * ip;  // first feature row of the pair
 #pragma unroll
-            for (int dj = 0; dj < 2; ++dj) {
-              __nv_bfloat16* dst = P.dfeat + ((size_t)b * 4 * P.C4 + 4 * c + 2 * di + dj) * HW + (size_t)i0 * WS2;
+          for (int dj = 0; dj < 2; ++dj) {
+            __nv_bfloat16* dst = P.dfeat + ((size_t)b * 4 * P.C4 + 4 * c + 2 * di + dj) * HW + (size_t)i0 * WS2;
 #pragma unroll
-              for (int s4 = 0; s4 < (2 * WS2) / 8; ++s4) {  // 8 consecutive elements of [row r][j]
-                uint32_t pk[4];
+            for (int s4 = 0; s4 < (2 * WS2) / 8; ++s4) {  // 8 consecutive elements of [row r][j]
+              uint32_t pk[4];
 #pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) {
-                  const int x0 = 8 * s4 + 2 * e2, x1 = x0 + 1;  // index into the 2*WS2 run
-                  const float f0 = v[x0 / WS2][2 * (x0 % WS2) + dj];
-                  const float f1 = v[x1 / WS2][2 * (x1 % WS2) + dj];
-                  __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-                  pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
-                }
-                *reinterpret_cast<uint4*>(dst + 8 * s4) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              for (int e2 = 0; e2 < 4; ++e2) {
+                const int x0 = 8 * s4 + 2 * e2, x1 = x0 + 1;  // index into the 2*WS2 run
+                const float f0 = v[x0 / WS2][2 * (x0 % WS2) + dj];
+                const float f1 = v[x1 / WS2][2 * (x1 % WS2) + dj];
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
               }
+              *reinterpret_cast<uint4*>(dst + 8 * s4) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
+          }
+        };
+        const int nitems = 2 * npairs;
+        if (NCH <= 2 && P.prefetch) {
+          // the TMEM loads of the next item are in flight while the current item is converted and stored (the
+          // epilogue was TMEM-load-latency bound: ~55 % of its stall samples sat behind tcgen05.wait::ld)
+          float va[2][NCH * 16], vb[2][NCH * 16];
+          if (e < nitems) issue(e, va);
+          for (int item = e; item < nitems; item += 4) {
+            tc::tmem_ld_wait();
+            if (item + 2 < nitems) issue(item + 2, vb);
+            emit(item, va);
+            if (item + 2 < nitems) {
+              tc::tmem_ld_wait();
+              if (item + 4 < nitems) issue(item + 4, va);
+              emit(item + 2, vb);
+            }
+          }
+        } else {
+          for (int item = e; item < nitems; item += 2) {
+            float v[2][NCH * 16];
+            issue(item, v);
+            tc::tmem_ld_wait();
+            emit(item, v);
           }
         }
         tc::fence_before_sync();
@@ -950,6 +973,7 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
     p.Hh = Hh;
     p.ncols = (Hh * (Wi1 + 1) + 15) & ~15;
     p.backoff = g_tuning[LPB_TUNE_WAIT_BACKOFF];
+    p.prefetch = g_tuning[LPB_TUNE_B3A_PREFETCH];
     const int rows_alloc = (Wi1 + 2 + p.ncols + 7) & ~7;
     const size_t smem = (size_t)2 * GB_KC * rows_alloc * 16 + (size_t)4 * GB_KC * 128 * 16 + 160;
     LPB_REQUIRE(smem <= 225 * 1024, "head_bwd_bf16: layer-1 operands need %zu B shared memory", smem);
