@@ -155,14 +155,14 @@ BACKBONE_PARAMS = 23_508_032  # ResNet-50 trunk (94.4 MB of fp32 gr
 
 
 class HotPath:
-    # our own kernel launches per step (library kernels of torch are not counted)
-    # per head call: 2 weight packs + 1 pad clear (mid) + k1a + k1b + decode (warp kernel + queued CTA kernel) = 7
-    # (+1 pad clear for the saved operand copy when training); two calls: labeled, unlabeled;
-    # + target+mse (2) + remap + unsup losses
-    LAUNCHES_FWD = 2 * 7 + 2 + 1 + 1
-    # unsup bwd, remap bwd, target+mse bwd; per head backward: 2 packs + 2 pad clears + plane dots + G2 front end
-    # + wgrad2 + dgrad2 + wgrad1 + dgrad1 = 10 (x2), + decode windows and its dense-fallback launch (unlabeled)
-    LAUNCHES_BWD = 2 + 3 + 2 * 10 + 2
+    # our own kernel launches per step, counted from the committed ncu launch list (profiles/r02_launches_train_step.csv);
+    # library kernels of torch (Adam, a dozen scalar element-wise ops, NCCL) are not counted
+    # per head call: preparation (packs + pads) + k1a + banded layer 2 + decode (warp kernel + queued CTA kernel) = 5;
+    # labeled: + fused targets/MSE (2);  unlabeled: + remap + unsupervised losses (2)
+    LAUNCHES_FWD = 2 * 5 + 2 + 2
+    # unlabeled: unsup bwd, remap bwd, decode windows + dense fallback, then per head backward: preparation, plane dots,
+    # G2 front end, wgrad2, dgrad2, wgrad1, dgrad1 = 7;  labeled: targets/MSE bwd + the same 7
+    LAUNCHES_BWD = (4 + 7) + (1 + 7)
 
     def __init__(self, prob, device, fwd_only: bool, world: int = 1, ddp_payload_floats: int = 0):
         from lightning_pose_b200 import ops
@@ -345,8 +345,8 @@ def kernel_breakdown(hp: "HotPath", feats, reps=20):
     out = {}
 
     def add(name, fn, nbytes, what):
-        ms, med = time_stage(fn, flush, reps)
-        out[name] = {"ms": ms, "ms_median": med, "algorithmic_bytes": nbytes, "gbs": nbytes / ms / 1e6, "what": what}
+        ms, med = time_stage(fn, flush, reps)  # rates use the MEDIAN of the repetitions (robust to a stray slow repetition)
+        out[name] = {"ms": med, "ms_mean": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / med / 1e6, "what": what}
 
     with torch.no_grad():
         hm = hp.head(feats)
@@ -534,8 +534,8 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": f"{dom}: {br[dom]['what']}", "achieved": br[dom]["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": br[dom]["gbs"] / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
                      "algorithmic_bytes_per_launch": br[dom]["algorithmic_bytes"], "launch_ms": br[dom]["ms"],
-                     "selection": "arg-max of the per-stage device times below (each stage timed alone, 20 reps, L2 flushed)"},
-        "stages": {k: {"ms": round(v["ms"], 4), "ms_median": round(v["ms_median"], 4), "GBps": round(v["gbs"], 1), "frac_hbm": round(v["gbs"] / pk["hbm_gbs"], 4)} for k, v in br.items()},
+                     "selection": "arg-max of the per-stage device times below (each stage timed alone, median of 20 repetitions, L2 flushed before each)"},
+        "stages": {k: {"ms": round(v["ms"], 4), "ms_mean": round(v["ms_mean"], 4), "GBps": round(v["gbs"], 1), "frac_hbm": round(v["gbs"] / pk["hbm_gbs"], 4)} for k, v in br.items()},
     }
     if fwd_only_value is not None:
         line["forward_only"] = fwd_only_value

@@ -70,11 +70,38 @@ g1, g2 = torch.randn_like(sf), torch.randn_like(mf)
 ms, _ = bench.time_stage(lambda: torch.autograd.grad([sf, mf], [s2] + list(mh.parameters()), [g1, g2], retain_graph=True, allow_unused=True), flush)
 res["cfg3_mhcrnn_backward"] = {"frames": 64, "ms": ms, "us_per_frame": 1e3 * ms / 64}
 
-# config 5: batched inference driver, 100 chunks of 96 frames of (2048, 16, 16) bf16 features (4 resident chunks cycled: 403 MB > L2)
-head = head_for("resnet50", 2048).eval()
+# decode alone on trained-like (peaked) planes of each config's heatmap size: the head timings above use random weights, whose
+# multi-modal heatmaps take the dense decode path (worst case); a trained network's planes are unimodal
+def peaked(n, s_):
+    yy, xx = torch.meshgrid(torch.arange(s_, device=dev), torch.arange(s_, device=dev), indexing="ij")
+    c = torch.rand(n, K, 2, device=dev) * (s_ - 20) + 10
+    hm = torch.exp(-((yy[None, None] - c[..., 1, None, None]) ** 2 + (xx[None, None] - c[..., 0, None, None]) ** 2) / (2 * 1.3**2)) + 1e-6
+    return hm / hm.sum((2, 3), keepdim=True)
+
+
+from lightning_pose_b200 import ops  # noqa: E402
+
+for name, n, s_ in (("cfg3_64", 96, 64), ("cfg4_96", 32, 96), ("cfg5_128", 96, 128)):
+    hm = peaked(n, s_)
+    ms, _ = bench.time_stage(lambda: ops.decode_softargmax(hm, 2, 1000.0), flush)
+    nb = n * (K * s_ * s_ * 4 + 204)
+    res[f"{name}_decode_fwd_peaked"] = {"frames": n, "ms": ms, "us_per_frame": 1e3 * ms / n, "algorithmic_bytes": nb, "frac_hbm": nb / ms / 1e6 / pk["hbm_gbs"]}
+
+# config 5: batched inference driver on a trained-like response: bench.make_problem at the 512x512 geometry
+# (features (., 2048, 16, 16), heatmaps 128x128), 100 chunks of 96 frames (4 resident chunks cycled: 403 MB > L2)
+bench.FEAT_HW, bench.HM, bench.IMG = 16, 128, 512
+prob = bench.make_problem(8, seed=7, device=dev, regime="trained")  # 8 clips x 48 = 384 frames = 4 chunks
+bench.FEAT_HW, bench.HM, bench.IMG = 12, 96, 384
+head = HeatmapHead("resnet50", 2048, K)
+d1, d2 = list(head.upsampling_layers)[1:]
+with torch.no_grad():
+    w1, b1, w2, b2 = prob["head_params"]
+    d1.weight.copy_(w1), d1.bias.copy_(b1), d2.weight.copy_(w2), d2.bias.copy_(b2)
+head = head.to(dev).eval()
 chunk, nchunks = 96, 100
-pool = [(torch.randn(chunk, 2048, 16, 16, device=dev) * 0.5).bfloat16() for _ in range(4)]
-for use_graph, sub in ((True, None), (False, None), (True, 24), (True, 48)):
+feats_all = prob["feats"].bfloat16().to(dev)
+pool = [feats_all[i * chunk : (i + 1) * chunk].contiguous() for i in range(4)]
+for use_graph, sub in ((True, None), (False, None), (True, 48)):
     bp = BatchedPredictor(head, K, chunk * nchunks, chunk, (512, 512), use_graph=use_graph, sub_chunk=sub)
     bp.feed(pool[0])  # capture / warm
     bp.cursor.zero_()
@@ -87,9 +114,11 @@ for use_graph, sub in ((True, None), (False, None), (True, 24), (True, 48)):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     nb = chunk * nchunks * (2048 * 256 * 2 + 204)
+    kp, cf = bp.results()
     res[f"cfg5_batched_inference_{'graph' if use_graph else 'eager'}_sub{sub or chunk}"] = {
         "frames": chunk * nchunks, "ms": ms, "frames_per_s": chunk * nchunks / ms * 1e3, "algorithmic_bytes": nb, "frac_hbm": nb / ms / 1e6 / pk["hbm_gbs"],
-        "note": "features resident on the device (includes the D2D copy of each chunk into the graph's static input); K1+K2 algorithmic bytes = features + 204 B/frame"}
+        "mean_confidence": float(cf.mean()),
+        "note": "trained-like planted response (unimodal heatmaps); features resident on the device (includes the D2D copy of each chunk into the graph's static input); K1+K2 algorithmic bytes = features + 204 B/frame"}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "r02_configs.json"), "w"), indent=1)
 print(json.dumps(res, indent=1))
