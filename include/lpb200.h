@@ -47,7 +47,8 @@ const char* lpb_build_arch(void);     /* "sm_100a" */
 #define LPB_TUNE_K1A_BULK_XS 4          /* 1: the saved operand copy leaves k1a by TMA bulk stores from the operand stage; 0 (default): producer stores */
 #define LPB_TUNE_DECODE_L2_HINTS 5      /* 1 (default): L2 evict_last / evict_first hints on the decode's two sweeps of a plane */
 #define LPB_TUNE_B3A_PREFETCH 6         /* 1 (default): b3a epilogue issues the next item's TMEM loads before storing the current one */
-#define LPB_TUNE_COUNT 7
+#define LPB_TUNE_SOFTMAX_SPLIT 7         /* 1 (default): plane softmax as two launches parallel over (frame, band) instead of one per-frame two-pass kernel */
+#define LPB_TUNE_COUNT 8
 int lpb_set_tuning(int key, int value);
 int lpb_get_tuning(int key);
 

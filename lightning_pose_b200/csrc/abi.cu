@@ -20,6 +20,7 @@ int g_tuning[LPB_TUNE_COUNT] = {
     0,  // LPB_TUNE_K1A_BULK_XS (measured: 268 vs 223 us per 512 frames: the loader's wait on the filled stage costs more than the producers' stores)
     1,  // LPB_TUNE_DECODE_L2_HINTS
     1,  // LPB_TUNE_B3A_PREFETCH
+    1,  // LPB_TUNE_SOFTMAX_SPLIT
 };
 }
 extern "C" int lpb_set_tuning(int key, int value) {

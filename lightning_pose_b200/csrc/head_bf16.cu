@@ -756,7 +756,9 @@ extern "C" int lpb_head_bf16_workspace_bytes(int B, int C, int H, int W, int c1,
   LPB_REQUIRE(B >= 0 && C >= 128 && C % 128 == 0 && H >= 1 && W >= 1 && c1 >= 1 && c2 >= 0, "head_bf16_workspace_bytes: bad shape");
   const size_t w1 = (size_t)(C / 4 / HB_KSTAGE) * HB_BSTAGE_BYTES, w2 = HB_BSTAGE_BYTES;
   const size_t mid = c2 > 0 ? (size_t)B * 4 * make_row_layout(4 * H, 4 * W).rows * 16 : 0;
-  *bytes = w1 + w2 + mid;
+  // + the split softmax's per-band statistics of the LAST layer
+  const size_t part = c2 > 0 ? convt_rows_partials_bytes(B, 4 * H, 4 * W) : convt_rows_partials_bytes(B, 2 * H, 2 * W);
+  *bytes = w1 + w2 + mid + ((part + 255) & ~(size_t)255);
   return LPB_OK;
 }
 
@@ -780,6 +782,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   __nv_bfloat16* wp1 = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* wp2 = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)nst * HB_BSTAGE_BYTES);
   __nv_bfloat16* mid = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES);
+  float* partials = reinterpret_cast<float*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES + (c2 > 0 ? (size_t)B * 4 * Lmid.rows * 16 : 0));
   const bool fast = head_fast_path(C, H, W, c2, max_smem);
   {
     // one launch: both operand packs + the pad rows of the fresh row-layout buffers
@@ -810,6 +813,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
     p.B = B;
     p.cout = c1;
     p.out = out;
+    p.partials = partials;
     if (c2 == 0) {
       p.mode = final_softmax ? CONVT_ROWS_SOFTMAX : CONVT_ROWS_PLANES;
       rc = launch_convt_rows(p, sms, s);
@@ -829,6 +833,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
       p2.B = B;
       p2.cout = c2;
       p2.out = out;
+      p2.partials = partials;
       p2.mode = final_softmax ? CONVT_ROWS_SOFTMAX : CONVT_ROWS_PLANES;
       rc = launch_convt_rows(p2, sms, s);
       if (rc != LPB_OK) return rc;
@@ -869,6 +874,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
     p2.B = B;
     p2.cout = c2;
     p2.out = out;
+    p2.partials = partials;
     p2.mode = final_softmax ? CONVT_ROWS_SOFTMAX : CONVT_ROWS_PLANES;
     const int rc = launch_convt_rows(p2, sms, s);
     if (rc != LPB_OK) return rc;

@@ -115,15 +115,23 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
   const int R = P.R, nbands = (Hi + R - 1) / R, nst = P.nst;
   const int npass = MODE == CONVT_ROWS_SOFTMAX ? 2 : 1;
   const int Ho = 2 * Hi, Wo = 2 * Wi;
+  // Work items.  The fused two-pass softmax needs a whole frame per CTA (its per-plane max / sum run over all bands);
+  // every other mode -- including the two halves of the SPLIT softmax (P0: per-band partial (max, sum) to global
+  // scratch; P1: normalise with the frame's merged statistics) -- is independent per (frame, band), so small batches
+  // (inference chunks, ViT training batches) still fill the GPU and large ones balance to within one band.
+  constexpr bool PER_BAND = MODE != CONVT_ROWS_SOFTMAX;
+  const int nitems = PER_BAND ? P.B * nbands : P.B;
+  const int bands_per_item = PER_BAND ? 1 : nbands;
   const int ncls = NPL ? NPL : P.cout;  // planes handled by the unrolled loops
 
   if (warp == 0) {
     // ================= loader: one bulk copy per K-chunk (band rows + the halo row below) + the stage's weights ====
     // single-stage GEMMs (K = 32) keep their weights resident: each ring slot receives them once
     int it = 0;
-    for (int b = blockIdx.x; b < P.B; b += gridDim.x)
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x)
       for (int pass = 0; pass < npass; ++pass)
-        for (int band = 0; band < nbands; ++band) {
+        for (int bi = 0; bi < bands_per_item; ++bi) {
+          const int b = PER_BAND ? item / nbands : item, band = PER_BAND ? item - b * nbands : bi;
           const int y0 = band * R, rb = min(R, Hi - y0);
           const uint32_t nbytes = (uint32_t)((rb + 1) * Pp * 16);
           for (int st = 0; st < nst; ++st, ++it) {
@@ -146,9 +154,10 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
     const uint32_t idesc = tc::make_idesc_bf16_f32(128, CR_NCOLS);
     const uint32_t lbo_a = P.rows_alloc * 16, lbo_b = CR_NCOLS * 16;
     int it = 0, nb = 0;
-    for (int b = blockIdx.x; b < P.B; b += gridDim.x)
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x)
       for (int pass = 0; pass < npass; ++pass)
-        for (int band = 0; band < nbands; ++band, ++nb) {
+        for (int bi = 0; bi < bands_per_item; ++bi, ++nb) {
+          const int band = PER_BAND ? item % nbands : bi;
           const int rb = min(R, Hi - band * R), tiles = (rb * Pp + 127) / 128;
           mbar_wait(t_empty, (nb & 1) ^ 1);
           tc::fence_after_sync();
@@ -183,18 +192,35 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
     const int q = warp & 3, e = (warp - 2) >> 2, ew = warp - 2;
     const float L2E = 1.4426950408889634f;
     const size_t plane_stride = (size_t)Ho * Wo;
-    const bool use_bias = P.bias && MODE != CONVT_ROWS_SOFTMAX;  // a per-plane constant does not change a softmax
+    const bool use_bias = P.bias && (MODE == CONVT_ROWS_MID || MODE == CONVT_ROWS_PLANES);  // a per-plane constant does not change a softmax
     int nb = 0;
-    for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int b = PER_BAND ? item / nbands : item;
       float mx[CR_CLS], sm[CR_CLS];
 #pragma unroll
       for (int o = 0; o < CR_CLS; ++o) {
         mx[o] = -1.0e30f;
         sm[o] = 0.f;
       }
+      if constexpr (MODE == CONVT_ROWS_SOFTMAX_P1) {
+        // merge the frame's per-band partials (written by the P0 launch) into (shift, 1 / sum) per plane
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // previous item's readers of fin are done
+        if (tid - 64 < ncls) {
+          const int o = tid - 64;
+          const float* pp = P.partials + ((size_t)b * nbands * CR_CLS + o) * 2;
+          float M = -1.0e30f;
+          for (int j = 0; j < nbands; ++j) M = fmaxf(M, pp[(size_t)j * CR_CLS * 2]);
+          float S = 0.f;
+          for (int j = 0; j < nbands; ++j) S += pp[(size_t)j * CR_CLS * 2 + 1] * fast_exp2((pp[(size_t)j * CR_CLS * 2] - M) * L2E);
+          fin[2 * o] = M * L2E;
+          fin[2 * o + 1] = 1.0f / S;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       for (int pass = 0; pass < npass; ++pass) {
-        const bool write = (pass == npass - 1);
-        for (int band = 0; band < nbands; ++band, ++nb) {
+        const bool write = MODE == CONVT_ROWS_SOFTMAX_P0 ? false : (pass == npass - 1);
+        for (int bi = 0; bi < bands_per_item; ++bi, ++nb) {
+          const int band = PER_BAND ? item - b * nbands : bi;
           const int y0 = band * R, rb = min(R, Hi - y0), tiles = (rb * Pp + 127) / 128;
           mbar_wait_idle(t_full, nb & 1, P.backoff);
           tc::fence_after_sync();
@@ -244,7 +270,7 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
                 return;
               }
               float* dst = P.out + ((size_t)b * P.cout * Ho + y) * Wo + x;  // plane o adds o * Ho * Wo
-              if constexpr (V2 && MODE == CONVT_ROWS_SOFTMAX) {
+              if constexpr (V2 && (MODE == CONVT_ROWS_SOFTMAX || MODE == CONVT_ROWS_SOFTMAX_P0 || MODE == CONVT_ROWS_SOFTMAX_P1)) {
                 if (!write) {
                   // ---- pass 0: per-thread online (max, sum) per plane; the rescale is rare after the first tiles ----
                   bool need = false;
@@ -306,7 +332,7 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
                   }
                 } else if (valid) {
                   float p0 = l0, p1 = l1;
-                  if (MODE == CONVT_ROWS_SOFTMAX) {
+                  if (MODE == CONVT_ROWS_SOFTMAX || MODE == CONVT_ROWS_SOFTMAX_P1) {
                     const float mL = fin[2 * o], inv = fin[2 * o + 1];
                     p0 = fast_exp2(fmaf(l0, L2E, -mL)) * inv;
                     p1 = fast_exp2(fmaf(l1, L2E, -mL)) * inv;
@@ -321,7 +347,7 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
           tc::fence_before_sync();
           tc::mbar_arrive(t_empty);
         }
-        if (npass == 2 && pass == 0) {
+        if ((npass == 2 && pass == 0) || MODE == CONVT_ROWS_SOFTMAX_P0) {
           // merge the online-softmax states: lanes -> warp (shuffles) -> 8 epilogue warps (smem)
 #pragma unroll
           for (int o = 0; o < CR_CLS; ++o) {
@@ -342,8 +368,14 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
             float S = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) S += stat[(CR_CLS + o) * 8 + i] * fast_exp2((stat[o * 8 + i] - M) * L2E);
-            fin[2 * o] = M * L2E;
-            fin[2 * o + 1] = 1.0f / S;
+            if constexpr (MODE == CONVT_ROWS_SOFTMAX_P0) {
+              float* pp = P.partials + (((size_t)b * nbands + (item - b * nbands)) * CR_CLS + o) * 2;
+              pp[0] = M;
+              pp[1] = S;
+            } else {
+              fin[2 * o] = M * L2E;
+              fin[2 * o + 1] = 1.0f / S;
+            }
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
@@ -367,18 +399,26 @@ int launch_convt_rows(ConvtRowsParams p, int sms, cudaStream_t s) {
   if (p.rows_alloc < (p.R + 1) * Pp + 8) p.rows_alloc = ((p.R + 1) * Pp + 8 + 7) & ~7;
   const size_t smem = (size_t)CR_STAGES * (4 * p.rows_alloc * 16 + CR_BSTAGE) + (2 * CR_CLS * 8 + 2 * CR_CLS + 8) * sizeof(float) + 64;
   LPB_REQUIRE(smem <= 113 * 1024, "head_fwd_bf16: band stages need %zu B shared memory", smem);
-  const int grid = p.B < 2 * sms ? p.B : 2 * sms;
   p.backoff = g_tuning[LPB_TUNE_WAIT_BACKOFF];
-  auto run = [&](auto kern) -> int {
+  const int nbands = (p.L.Hi + p.R - 1) / p.R;
+  auto run = [&](auto kern, long long nitems) -> int {
+    const int grid = (int)(nitems < 2 * sms ? nitems : 2 * sms);
     LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, CR_THREADS, smem, s>>>(p);
     return LPB_OK;
   };
   const bool v2 = g_tuning[LPB_TUNE_SOFTMAX_EPILOGUE_V2] != 0, k17 = p.cout == 17;
-  if (p.mode == CONVT_ROWS_MID) return run(convt_rows_kernel<CONVT_ROWS_MID, 0, false>);
-  if (p.mode == CONVT_ROWS_PLANES) return k17 ? run(convt_rows_kernel<CONVT_ROWS_PLANES, 17, false>) : run(convt_rows_kernel<CONVT_ROWS_PLANES, 0, false>);
-  if (v2) return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 17, true>) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 0, true>);
-  return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 17, false>) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 0, false>);
+  const long long per_band = (long long)p.B * nbands;
+  if (p.mode == CONVT_ROWS_MID) return run(convt_rows_kernel<CONVT_ROWS_MID, 0, false>, per_band);
+  if (p.mode == CONVT_ROWS_PLANES) return k17 ? run(convt_rows_kernel<CONVT_ROWS_PLANES, 17, false>, per_band) : run(convt_rows_kernel<CONVT_ROWS_PLANES, 0, false>, per_band);
+  if (v2 && p.partials && g_tuning[LPB_TUNE_SOFTMAX_SPLIT]) {
+    // split softmax: partial statistics per (frame, band), then the normalising pass -- both parallel over bands
+    int rc = k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P0, 17, true>, per_band) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P0, 0, true>, per_band);
+    if (rc != LPB_OK) return rc;
+    return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P1, 17, true>, per_band) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P1, 0, true>, per_band);
+  }
+  if (v2) return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 17, true>, p.B) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 0, true>, p.B);
+  return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 17, false>, p.B) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 0, false>, p.B);
 }
 
 }  // namespace lpb

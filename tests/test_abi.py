@@ -171,7 +171,7 @@ def test_round2_entry_points_validate_arguments_without_gpu():
     assert L.lpb_head_bf16_plan(100, 12, 12, 17, 17, C.byref(plan)) == -1                          # C % 128
     assert L.lpb_head_bf16_plan(2048, 12, 12, 20, 17, C.byref(plan)) == -1                         # c1 must leave the ones channel
     n = C.c_size_t(0)
-    assert L.lpb_head_bf16_workspace_bytes(2, 384, 16, 16, 17, 0, C.byref(n)) == 0 and n.value == 3 * 20480 + 20480  # no mid for one deconv
+    assert L.lpb_head_bf16_workspace_bytes(2, 384, 16, 16, 17, 0, C.byref(n)) == 0 and n.value == 3 * 20480 + 20480 + 1024  # no mid for one deconv; + split-softmax statistics (2 frames x 3 bands x 20 x 2 floats -> 1 KB)
     assert L.lpb_head_bwd_bf16_workspace_bytes(2, 384, 16, 16, 17, 0, C.byref(n)) == 0 and n.value > 0
     for rc in (
         L.lpb_convt_fwd_f32(None, 1, 4, 4, 4, 1, None, None, 2, None, None),
@@ -191,7 +191,7 @@ def test_round2_entry_points_validate_arguments_without_gpu():
         assert rc == -1, (rc, L.lpb_last_error())
     assert L.lpb_context_gather(C.c_void_p(16), 4, 24, 5, C.c_void_p(16), None) == -1  # items must be 16-byte multiples
     assert L.lpb_set_tuning(99, 1) == -1 and L.lpb_get_tuning(99) == -1
-    for k in range(7):
+    for k in range(8):
         assert L.lpb_get_tuning(k) in (0, 1)
 
 

@@ -1103,12 +1103,12 @@ def test_kernel_variants_agree(lpb, dev):
         ((kp * gk).sum() * 1e-3 + (hm * hm).sum()).backward()
         return hm.detach().clone(), kp.detach().clone(), cf.detach().clone(), f.grad.float().clone(), list(head.upsampling_layers)[1].weight.grad.clone()
 
-    saved = [lib.lpb_get_tuning(k) for k in range(7)]
+    saved = [lib.lpb_get_tuning(k) for k in range(8)]
     try:
-        for k in range(7):
+        for k in range(8):
             lib.lpb_set_tuning(k, 1)
         new = run()
-        for k in range(7):
+        for k in range(8):
             lib.lpb_set_tuning(k, 0)
         old = run()
     finally:
