@@ -157,14 +157,14 @@ BACKBONE_PARAMS = 23_508_032  # ResNet-50 trunk (94.4 MB of fp32 gr
 class HotPath:
     # our own kernel launches per step, counted from the committed ncu launch list (profiles/r02_launches_train_step.csv);
     # library kernels of torch (Adam, a dozen scalar element-wise ops, NCCL) are not counted
-    # per head call: preparation (packs + pads) + k1a + banded layer 2 + decode (warp kernel + queued CTA kernel) = 5;
-    # labeled: + fused targets/MSE (2);  unlabeled: + remap + unsupervised losses (2)
-    LAUNCHES_FWD = 2 * 5 + 2 + 2
+    # per head call: preparation (packs + pads) + k1a + banded layer 2 (softmax statistics + normalising launch) + decode
+    # (warp kernel + queued CTA kernel) = 6;  labeled: + fused targets/MSE (2);  unlabeled: + remap + unsupervised losses (2)
+    LAUNCHES_FWD = 2 * 6 + 2 + 2
     # unlabeled: unsup bwd, remap bwd, decode windows + dense fallback, then per head backward: preparation, plane dots,
     # G2 front end, wgrad2, dgrad2, wgrad1, dgrad1 = 7;  labeled: targets/MSE bwd + the same 7
     LAUNCHES_BWD = (4 + 7) + (1 + 7)
 
-    def __init__(self, prob, device, fwd_only: bool, world: int = 1, ddp_payload_floats: int = 0):
+    def __init__(self, prob, device, fwd_only: bool, world: int = 1, ddp_payload_floats: int = 0, two_streams: bool = True):
         from lightning_pose_b200 import ops
         from lightning_pose_b200.ddp import FlatGradAllReducer
         from lightning_pose_b200.models.heads.heatmap import HeatmapHead
@@ -185,6 +185,11 @@ class HotPath:
         self.teps = torch.full((K_PTS,), 20.0, device=device)
         self.w_unsup = 1.0 / (2.0 * np.exp(5.0))
         self.reducer = None
+        self.two_streams = two_streams
+        self.side = torch.cuda.Stream(device=device) if two_streams else None
+        if two_streams and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            # the head's parameters receive gradients from two streams on purpose (the engine orders them with events)
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         if not fwd_only:
             self.opt = torch.optim.Adam(self.head.parameters(), lr=1e-5, fused=True, capturable=True)
             if world > 1:
@@ -199,13 +204,26 @@ class HotPath:
         if not self.fwd_only:
             f_lab.requires_grad_(True)  # d loss / d features feeds the backbone's backward
             f_unl.requires_grad_(True)
+        cur = torch.cuda.current_stream(self.dev)
         with torch.set_grad_enabled(not self.fwd_only):
-            hm_lab, _kp_lab, _cf_lab = self.head.forward_with_keypoints(f_lab)  # (n*16, 17, 96, 96); keypoints -> rmse metric
-            l_sup = ops.heatmap_mse_from_keypoints(self.kp_lab, hm_lab, IMG, IMG, visibility=self.vis)
+            if self.two_streams:
+                # the labeled and the unlabeled chain share nothing until the loss sum: fork the labeled one onto a second
+                # stream (autograd replays each node's backward on its forward stream, so the two backward chains overlap too)
+                self.side.wait_stream(cur)
+                with torch.cuda.stream(self.side):
+                    hm_lab, _kp_lab, _cf_lab = self.head.forward_with_keypoints(f_lab)
+                    l_sup = ops.heatmap_mse_from_keypoints(self.kp_lab, hm_lab, IMG, IMG, visibility=self.vis)
+            else:
+                hm_lab, _kp_lab, _cf_lab = self.head.forward_with_keypoints(f_lab)  # (n*16, 17, 96, 96); keypoints -> rmse metric
+                l_sup = ops.heatmap_mse_from_keypoints(self.kp_lab, hm_lab, IMG, IMG, visibility=self.vis)
             _hm_unl, kp, cf = self.head.forward_with_keypoints(f_unl)  # (n*32, ...)
             kp_unl = ops.remap_keypoints(kp, self.tf, self.bbox, IMG, IMG)
             per_clip = ops.unsup_losses(kp_unl.reshape(n, T_UNLABELED, 2 * K_PTS), cf.reshape(n, T_UNLABELED, K_PTS),
                                         temporal_eps=self.teps, prob_threshold=0.05, pca_singleview=self.sv)
+            if self.two_streams:
+                cur.wait_stream(self.side)
+                for t in (hm_lab, l_sup, f_lab):
+                    t.record_stream(cur)
             total = 0.5 * l_sup + self.w_unsup * per_clip[:, :2].sum()
         scalars = [total.detach(), l_sup.detach(), per_clip[:, 0].mean().detach(), per_clip[:, 1].mean().detach()]
         if not self.fwd_only:
@@ -399,7 +417,7 @@ def run_ours(args):
 
     prob = make_problem(args.clips, seed=1234 + rank, device=dev, regime=args.regime)
     payload = int(args.ddp_payload_mb * 1e6 / 4) if (world > 1 and not args.fwd_only) else 0
-    hp = HotPath(prob, dev, args.fwd_only, world, ddp_payload_floats=payload)
+    hp = HotPath(prob, dev, args.fwd_only, world, ddp_payload_floats=payload, two_streams=not args.serial_chains)
     tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     feats_host = prob["feats"].to(tdt).pin_memory()
     feats = feats_host.to(dev, non_blocking=True)
@@ -478,11 +496,11 @@ def run_ours(args):
         return
     pk, pk_src = peaks()
     # single-GPU stage timings: a fresh single-rank HotPath (no collective inside), peers idle
-    hp_b = HotPath(prob, dev, args.fwd_only) if world > 1 else hp
+    hp_b = HotPath(prob, dev, args.fwd_only, two_streams=not args.serial_chains) if world > 1 else hp
     br = kernel_breakdown(hp_b, feats)
     fwd_only_value = None
     if not args.fwd_only:
-        hp_fwd = HotPath(prob, dev, True)
+        hp_fwd = HotPath(prob, dev, True, two_streams=not args.serial_chains)
         fwd_fn = GraphedStep(hp_fwd, feats) if graphed else (lambda: hp_fwd.step(feats))
         ms_f = time_steps(fwd_fn, args.steps, 3)
         fwd_alg = n_frames * (FEAT_C * FEAT_HW * FEAT_HW * esz + HM_BYTES + KP_BYTES)  # SURVEY 8(d) "fused path total, training fwd"
@@ -493,14 +511,15 @@ def run_ours(args):
         # secondary regime: the reference's own initialiser (xavier gain 0.01) on randn features -> flat heatmaps ->
         # the decode cannot prune and evaluates the whole 384x384 field (SURVEY 7 "hard parts" 1)
         prob_f = make_problem(args.clips, seed=4321 + rank, device=dev, regime="fresh")
-        hp_f = HotPath(prob_f, dev, args.fwd_only)
+        hp_f = HotPath(prob_f, dev, args.fwd_only, two_streams=not args.serial_chains)
         feats_f = prob_f["feats"].to(tdt).to(dev)
         nst = max(2, args.steps // 2)
-        ms_flat = time_steps(lambda: hp_f.step(feats_f), nst, 3)
-        flat = {"value": n_frames * nst / (ms_flat / 1e3), "unit": "frames/s",
+        flat_fn = GraphedStep(hp_f, feats_f) if graphed else (lambda: hp_f.step(feats_f))
+        ms_flat = time_steps(flat_fn, nst, 3)
+        flat = {"value": n_frames * nst / (ms_flat / 1e3), "unit": "frames/s", "ms_per_step": ms_flat / nst,
                 "regime": "fresh init: reference initialiser (xavier gain 0.01) on randn*0.5 features; flat heatmaps, dense decode",
                 "stages": {k: round(v["ms"], 4) for k, v in kernel_breakdown(hp_f, feats_f, reps=5).items()}}
-        del hp_f, feats_f, prob_f
+        del flat_fn, hp_f, feats_f, prob_f
     # roofline: the stage with the largest measured share of the step
     dom = max(br, key=lambda k: br[k]["ms"])
     traffic = None
@@ -521,7 +540,8 @@ def run_ours(args):
             "backward": "all native: loss stack, remap, sparse soft-argmax windows, target+mse, fused softmax-backward/G2 front end, tcgen05 dgrad+wgrad of both transposed convolutions; torch library: fused Adam on the head parameters",
             "frames_per_step_per_gpu": n_frames, "regime": ("trained-like synthetic response (unimodal Gaussian-like heatmaps; planted features + bilinear per-keypoint deconvs, see bench.make_problem); fresh_init_regime = reference initialiser"
                                                                                   if args.regime == "trained" else "fresh init (reference initialiser, flat heatmaps)"),
-            "launch": "whole step replayed from one CUDA graph" if graphed else "eager launches",
+            "launch": ("whole step replayed from one CUDA graph" if graphed else "eager launches")
+                      + ("; labeled and unlabeled chains forked onto two streams" if not args.serial_chains else "; one stream"),
             "l2_policy": f"step: inputs larger than L2 ({feats.numel() * esz / 2**20:.0f} MiB of features per step); stages: L2 flushed (256 MiB write) before each of 20 timed repetitions",
             "parallelism": f"dp{world}",
             "ddp": (f"2 NCCL all-reduces per step: a {payload * 4 / 1e6:.1f} MB synthetic backbone-gradient bucket (stands in for ResNet-50's {BACKBONE_PARAMS:,} parameters, which this "
@@ -629,6 +649,7 @@ def main():
     ap.add_argument("--no-flat", action="store_true", help="skip the secondary fresh-init (flat heatmap) regime")
     ap.add_argument("--fwd-only", action="store_true", help="time the forward pass only (default: full training step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial-chains", action="store_true", help="run the labeled and the unlabeled chain on one stream (default: two streams, forked and joined inside the step)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--ddp-payload-mb", type=float, default=BACKBONE_PARAMS * 4 / 1e6,
                     help="N>1: size of the synthetic backbone-gradient bucket all-reduced every step (0 = head gradients only)")

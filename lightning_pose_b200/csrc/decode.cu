@@ -47,6 +47,7 @@ struct DecodeParams {
   float lipw;         // max row sum of |horizontal taps|
   float wabs[W];      // max over rows / phases of |vertical tap| per offset (row pruning in the warp kernel)
   float phase[F][W];  // interior rows (constant bank operands)
+  float2 phase2[F / 2][W];  // {phase[2q][t], phase[2q+1][t]}: packed-pair operands of the strip evaluation
 };
 
 __host__ __device__ inline int dec_padl(int R) { return (R + 3) & ~3; }
@@ -78,28 +79,69 @@ __device__ float eval_point(const float* tile, int pitch, int padl, const float*
   return acc;
 }
 
-// one coarse row of the vertical pass: F fine values from the W-row window `t`
+// one coarse row of the vertical pass: F fine values from the W-row window `t`, as F/2 packed pairs of phases
+// (fma.rn.f32x2: the same fp32 roundings as the scalar chain, half the issue slots)
 template <int DS>
-__device__ __forceinline__ void column_pass(const DecodeParams<DS>& P, int a, int h, const float* t, float* v) {
-  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
-  if (a >= R && a <= h - 1 - R) {  // interior: phase-periodic weights are constant-bank operands
+__device__ __forceinline__ void column_pass(const DecodeParams<DS>& P, int a, int h, const float* t, f32x2* v2) {
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1, HP = F / 2;
+  if (a >= R && a <= h - 1 - R) {  // interior: phase-periodic weights are kernel-parameter constants (uniform registers)
 #pragma unroll
-    for (int p = 0; p < F; ++p) {
-      float r = 0.f;
+    for (int q = 0; q < HP; ++q) {
+      f32x2 r = pack2(0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < W; ++k) r = fmaf(P.phase[p][k], t[k], r);
-      v[p] = r;
+      for (int k = 0; k < W; ++k) r = fma2(pack2(P.phase2[q][k].x, P.phase2[q][k].y), dup2(t[k]), r);
+      v2[q] = r;
     }
   } else {  // border rows: per-row table (edge-clamped bicubic taps, zero-padded blur)
     const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
 #pragma unroll
-    for (int p = 0; p < F; ++p) {
-      float r = 0.f;
+    for (int q = 0; q < HP; ++q) {
+      f32x2 r = pack2(0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < W; ++k) r = fmaf(__ldg(tr + p * W + k), t[k], r);
-      v[p] = r;
+      for (int k = 0; k < W; ++k) r = fma2(pack2(__ldg(tr + (2 * q) * W + k), __ldg(tr + (2 * q + 1) * W + k)), dup2(t[k]), r);
+      v2[q] = r;
     }
   }
+}
+
+// online-softmax update of one lane's column with the F fine values of one coarse row (yrow = fine row index of phase 0):
+//   s += sum_p e_p,  sy += sum_p (yrow + p) e_p,  e_p = 2^((v_p - m) c);  m is raised (and s, sy rescaled) warp-wide
+template <int DS>
+__device__ __forceinline__ void softmax_row(const f32x2* v2, float yrow, float c, float kill, float& m, float& mc, float& s_it,
+                                            float& sy_it) {
+  constexpr int HP = (1 << DS) / 2;
+  float vm = -3.0e38f;
+#pragma unroll
+  for (int q = 0; q < HP; ++q) {
+    float lo, hi;
+    unpack2(v2[q], lo, hi);
+    vm = fmaxf(vm, fmaxf(lo, hi));
+  }
+  vm += kill;
+  if (__any_sync(0xffffffffu, vm > m)) {
+    const float mn = fmaxf(m, vm);
+    const float sc = fast_exp2((m - mn) * c);
+    s_it *= sc;
+    sy_it *= sc;
+    m = mn;
+    mc = mn * c;
+  }
+  const f32x2 c2 = dup2(c), nmc2 = dup2(-mc), kill2 = dup2(kill);
+  f32x2 rs2 = pack2(0.f, 0.f), pw2 = pack2(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < HP; ++q) {
+    float x0, x1;
+    unpack2(add2(fma2(v2[q], c2, nmc2), kill2), x0, x1);
+    const f32x2 e2 = pack2(fast_exp2(x0), fast_exp2(x1));
+    rs2 = add2(rs2, e2);
+    pw2 = fma2(e2, pack2((float)(2 * q), (float)(2 * q + 1)), pw2);
+  }
+  float r0, r1, p0, p1;
+  unpack2(rs2, r0, r1);
+  unpack2(pw2, p0, p1);
+  const float rs = r0 + r1;
+  s_it += rs;
+  sy_it = fmaf(yrow, rs, sy_it) + (p0 + p1);
 }
 
 template <int DS>
@@ -368,39 +410,15 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
     float m = M, mc = M * c, s_it = 0.f, sy_it = 0.f;
     const float kill = ok ? 0.f : -3.0e38f;
 
-    auto accumulate = [&](const float* v, float yrow) {
-      float vm = v[0];
-#pragma unroll
-      for (int p = 1; p < F; ++p) vm = fmaxf(vm, v[p]);
-      vm += kill;
-      if (__any_sync(0xffffffffu, vm > m)) {
-        const float mn = fmaxf(m, vm);
-        const float sc = fast_exp2((m - mn) * c);
-        s_it *= sc;
-        sy_it *= sc;
-        m = mn;
-        mc = mn * c;
-      }
-      float rs = 0.f, pw = 0.f;
-#pragma unroll
-      for (int p = 0; p < F; ++p) {
-        const float e = fast_exp2(fmaf(v[p], c, -mc) + kill);
-        rs += e;
-        if (p > 0) pw = fmaf(e, (float)p, pw);
-      }
-      s_it += rs;
-      sy_it = fmaf(yrow, rs, sy_it) + pw;
-    };
-
     int a = r0;
     float yrow = (float)(r0 * F);
     for (; a + 1 < r1; a += 2, yrow += (float)(2 * F)) {
       tmp[W] = dot_w<W>(colbase + (a + 1 + 2 * R) * pitch, wc);  // coarse row a+1+R
-      float v[F];
-      column_pass<DS>(P, a, h, tmp, v);
-      accumulate(v, yrow);
-      column_pass<DS>(P, a + 1, h, tmp + 1, v);
-      accumulate(v, yrow + (float)F);
+      f32x2 v2[F / 2];
+      column_pass<DS>(P, a, h, tmp, v2);
+      softmax_row<DS>(v2, yrow, c, kill, m, mc, s_it, sy_it);
+      column_pass<DS>(P, a + 1, h, tmp + 1, v2);
+      softmax_row<DS>(v2, yrow + (float)F, c, kill, m, mc, s_it, sy_it);
       if (a + 2 < r1) {
 #pragma unroll
         for (int t = 0; t < W - 1; ++t) tmp[t] = tmp[t + 2];
@@ -408,9 +426,9 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
       }
     }
     if (a < r1) {
-      float v[F];
-      column_pass<DS>(P, a, h, tmp, v);
-      accumulate(v, yrow);
+      f32x2 v2[F / 2];
+      column_pass<DS>(P, a, h, tmp, v2);
+      softmax_row<DS>(v2, yrow, c, kill, m, mc, s_it, sy_it);
     }
     {  // fold the item into the lane's running state
       const float Mn = fmaxf(M, m);
@@ -711,34 +729,11 @@ __device__ void decode_plane_warp(const DecodeParams<DS>& P, long long plane, co
     for (int t = 0; t < W; ++t) tmp[t] = dot_w<W>(colbase + (tr0 + t) * DECW_WP, wc);
     float m = M, mc = M * c, s_it = 0.f, sy_it = 0.f;
     const float kill = ok ? 0.f : -3.0e38f;
-    auto accumulate = [&](const float* v, float yrow) {
-      float vm = v[0];
-#pragma unroll
-      for (int p = 1; p < F; ++p) vm = fmaxf(vm, v[p]);
-      vm += kill;
-      if (__any_sync(0xffffffffu, vm > m)) {
-        const float mn = fmaxf(m, vm);
-        const float sc = fast_exp2((m - mn) * c);
-        s_it *= sc;
-        sy_it *= sc;
-        m = mn;
-        mc = mn * c;
-      }
-      float rs = 0.f, pw = 0.f;
-#pragma unroll
-      for (int p = 0; p < F; ++p) {
-        const float e = fast_exp2(fmaf(v[p], c, -mc) + kill);
-        rs += e;
-        if (p > 0) pw = fmaf(e, (float)p, pw);
-      }
-      s_it += rs;
-      sy_it = fmaf(yrow, rs, sy_it) + pw;
-    };
     float yrow = (float)(ra0 * F);
     for (int a = ra0; a <= ra1; ++a, yrow += (float)F) {
-      float v[F];
-      column_pass<DS>(P, a, h, tmp, v);
-      accumulate(v, yrow);
+      f32x2 v2[F / 2];
+      column_pass<DS>(P, a, h, tmp, v2);
+      softmax_row<DS>(v2, yrow, c, kill, m, mc, s_it, sy_it);
       if (a < ra1) {
 #pragma unroll
         for (int t = 0; t < W - 1; ++t) tmp[t] = tmp[t + 1];
@@ -880,6 +875,7 @@ struct DecodeBwdParams {
   int h, w, pitch, padl, bulk;
   float T;
   float phase[F][W];
+  float2 phase2[F / 2][W];  // {phase[2q][t], phase[2q+1][t]}: packed-pair operands of the strip evaluation
 };
 
 // Transposed horizontal pass for one coarse row of one 32-fine-column strip.  Lane j holds gv = (U_H^T G)[row][j]
@@ -911,7 +907,7 @@ template <int DS, bool ATOMIC>
 __device__ __forceinline__ void decode_bwd_strip(const DecodeBwdParams<DS>& P, const float* tile, float* gt, int pitch,
                                                  int trow0, int tcol0, int maxcols, int jf0, int J1, int r0, int r1, float M,
                                                  float c, float kscale, float xhat, float yhat, float gx, float gy, int lane) {
-  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1, HP = F / 2;
   const int h = P.h;
   const int jf = jf0 + lane;
   const bool ok = jf < J1;
@@ -920,45 +916,64 @@ __device__ __forceinline__ void decode_bwd_strip(const DecodeBwdParams<DS>& P, c
 #pragma unroll
   for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
   const float* colbase = tile + tcol0 + (jc / F - jf0 / F);
-  float tmp[W];   // horizontal pass of h, rows a-R .. a+R
-  float gacc[W];  // vertical-transpose accumulators: sum_i wr[i][t] * G[i][j] for coarse row a-R+t
+  // Register windows over the W coarse rows a-R .. a+R that the fine rows of coarse row a touch.  They are ROTATED, not
+  // shifted: the row loop is unrolled W times and in its `rot`-th copy tap t lives in slot (t + rot) % W, so advancing a
+  // row costs no register moves.  The F phases are processed as pairs (packed fp32, lpb_common.cuh): `gacc[slot]` holds
+  // the even-phase sum in its low half and the odd-phase sum in its high half.
+  float tmp[W];   // horizontal pass of h
+  f32x2 gacc[W];  // vertical-transpose accumulators: sum_i wr[i][t] * G[i][j]
 #pragma unroll
   for (int t = 0; t < W; ++t) {
     tmp[t] = dot_w<W>(colbase + (trow0 + t) * pitch, wc);
-    gacc[t] = 0.f;
+    gacc[t] = pack2(0.f, 0.f);
   }
-  const float dx = (float)jf - xhat;
-  for (int a = r0; a < r1; ++a) {
-    const int la = a - r0;
-    const bool interior = (a >= R && a <= h - 1 - R);
-    const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
+  const f32x2 ks2 = dup2(ok ? kscale : 0.f), c2 = dup2(c), nM2 = dup2(-M), nyh2 = dup2(-yhat), gx2 = dup2(gx), gy2 = dup2(gy);
+  const f32x2 dx2 = dup2((float)jf - xhat);
+  const int nrows = r1 - r0, nemit = nrows + W - 1;  // the last W-1 emissions flush the partial rows r1-R .. r1+R-1
+  for (int la0 = 0; la0 < nemit; la0 += W) {
+    static_for<0, W>([&](auto rot_c) {
+      constexpr int rot = decltype(rot_c)::value;
+      const int la = la0 + rot;
+      if (la >= nemit) return;  // warp-uniform
+      if (la < nrows) {
+        const int a = r0 + la;
+        const float af = (float)(a * F);
+        // one pair of phases (2q, 2q+1) with vertical taps w(t) = {wr[2q][t], wr[2q+1][t]}
+        auto phase_pair = [&](int q, auto&& w) {
+          f32x2 v2 = pack2(0.f, 0.f);
 #pragma unroll
-    for (int p = 0; p < F; ++p) {
-      float wr[W];
+          for (int t = 0; t < W; ++t) v2 = fma2(w(t), dup2(tmp[(t + rot) % W]), v2);
+          float e0, e1;
+          unpack2(mul2(add2(v2, nM2), c2), e0, e1);
+          const f32x2 pr2 = pack2(fast_exp2(e0), fast_exp2(e1));
+          const f32x2 y2 = add2(pack2(af + (float)(2 * q), af + (float)(2 * q + 1)), nyh2);
+          const f32x2 lin2 = fma2(dx2, gx2, mul2(y2, gy2));
+          const f32x2 g2 = mul2(mul2(ks2, pr2), lin2);
 #pragma unroll
-      for (int t = 0; t < W; ++t) wr[t] = interior ? P.phase[p][t] : __ldg(tr + p * W + t);
-      float v = 0.f;
+          for (int t = 0; t < W; ++t) gacc[(t + rot) % W] = fma2(w(t), g2, gacc[(t + rot) % W]);
+        };
+        if (a >= R && a <= h - 1 - R) {  // interior: phase-periodic weights are kernel-parameter constants
 #pragma unroll
-      for (int t = 0; t < W; ++t) v = fmaf(wr[t], tmp[t], v);
-      const float pr = fast_exp2((v - M) * c);
-      const float gval = ok ? kscale * pr * fmaf(dx, gx, ((float)(a * F + p) - yhat) * gy) : 0.f;
+          for (int q = 0; q < HP; ++q) phase_pair(q, [&](int t) { return pack2(P.phase2[q][t].x, P.phase2[q][t].y); });
+        } else {  // border rows: per-row table
+          const float* __restrict__ tr = P.tabH + (size_t)a * F * W;
 #pragma unroll
-      for (int t = 0; t < W; ++t) gacc[t] = fmaf(wr[t], gval, gacc[t]);
-    }
-    // coarse row a-R is complete for this lane's column
-    scatter_row<DS, ATOMIC>(gt + (trow0 + la) * pitch + tcol0, gacc[0], wc, lane, maxcols);
+          for (int q = 0; q < HP; ++q) {
+            f32x2 wr[W];
 #pragma unroll
-    for (int t = 0; t < W - 1; ++t) {
-      gacc[t] = gacc[t + 1];
-      tmp[t] = tmp[t + 1];
-    }
-    gacc[W - 1] = 0.f;
-    tmp[W - 1] = (a + 1 < r1) ? dot_w<W>(colbase + (trow0 + la + 1 + 2 * R) * pitch, wc) : 0.f;
+            for (int t = 0; t < W; ++t) wr[t] = pack2(__ldg(tr + (2 * q) * W + t), __ldg(tr + (2 * q + 1) * W + t));
+            phase_pair(q, [&](int t) { return wr[t]; });
+          }
+        }
+      }
+      // coarse row r0 + la - R is complete for this lane's column
+      float lo, hi;
+      unpack2(gacc[rot], lo, hi);
+      scatter_row<DS, ATOMIC>(gt + (trow0 + la) * pitch + tcol0, lo + hi, wc, lane, maxcols);
+      gacc[rot] = pack2(0.f, 0.f);
+      tmp[rot] = (la + 1 < nrows) ? dot_w<W>(colbase + (trow0 + la + 1 + 2 * R) * pitch, wc) : 0.f;
+    });
   }
-  // flush the remaining W-1 partial rows (coarse rows r1-R .. r1+R-1)
-#pragma unroll
-  for (int t = 0; t < W - 1; ++t)
-    scatter_row<DS, ATOMIC>(gt + (trow0 + (r1 - r0) + t) * pitch + tcol0, gacc[t], wc, lane, maxcols);
 }
 
 // Dense form: one CTA per plane (grid = n_planes), or -- queue mode -- per (plane, row segment) unit of the planes
@@ -983,18 +998,22 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_co
     __syncthreads();
   }
   uint32_t phase = 0;
-  const long long nunits = P.queue ? (long long)P.queue[0] * DEC_BWD_SEGS : P.n_planes;
+  // queue mode: a few left-over planes are split into row segments so that every resident CTA has work (their partial
+  // rows meet through global atomics in the gradient the window kernel cleared); when the queue alone fills the grid
+  // (flat heatmaps of a freshly initialised network: every plane is dense) a unit is a whole plane and stores plainly
+  const int nseg = P.queue ? max(1, min(DEC_BWD_SEGS, (int)gridDim.x / max(P.queue[0], 1))) : 1;
+  const long long nunits = P.queue ? (long long)P.queue[0] * nseg : P.n_planes;
   for (long long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
-    const size_t plane = P.queue ? (size_t)P.queue[1 + unit / DEC_BWD_SEGS] : (size_t)unit;
+    const size_t plane = P.queue ? (size_t)P.queue[1 + unit / nseg] : (size_t)unit;
     const float* st = P.stats + 8 * plane;
     const float M = st[0], S = st[1], xhat = st[2], yhat = st[3];
     const int A0 = (int)st[4], A1 = (int)st[5], B0 = (int)st[6], B1 = (int)st[7];
     const float gx = P.gxy[2 * plane], gy = P.gxy[2 * plane + 1];
     const int nrows = A1 - A0 + 1;
     int useg0 = A0, useg1 = A1 + 1;  // coarse rows this unit evaluates
-    if (P.queue) {
-      const int sg = (nrows + DEC_BWD_SEGS - 1) / DEC_BWD_SEGS;
-      useg0 = A0 + (int)(unit % DEC_BWD_SEGS) * sg;
+    if (nseg > 1) {
+      const int sg = (nrows + nseg - 1) / nseg;
+      useg0 = A0 + (int)(unit % nseg) * sg;
       useg1 = min(useg0 + sg, A1 + 1);
       if (useg0 >= useg1) continue;  // uniform per CTA
     }
@@ -1059,7 +1078,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_co
     }
     __syncthreads();
     float* __restrict__ dst = P.gheat + plane * (size_t)h * w;
-    if (P.queue) {  // rows this unit touched: [useg0 - R, useg1 + R)
+    if (nseg > 1) {  // rows this unit touched: [useg0 - R, useg1 + R)
       const int a0 = max(useg0 - R, 0), a1 = min(useg1 + R, h);
       for (int a = a0 + warp; a < a1; a += DEC_WARPS) {
         const float* row = gtile + (a + R) * pitch + padl;
@@ -1223,6 +1242,8 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
   P.offset = (DS == 1) ? 0.5f : (DS == 2 ? 1.5f : 2.5f);  // lightning_pose/models/heads/heatmap.py:131-136
   for (int p = 0; p < G::F; ++p)
     for (int t = 0; t < G::W; ++t) P.phase[p][t] = th->host.phase[(size_t)p * G::W + t];
+  for (int q = 0; q < G::F / 2; ++q)
+    for (int t = 0; t < G::W; ++t) P.phase2[q][t] = make_float2(P.phase[2 * q][t], P.phase[2 * q + 1][t]);
   const size_t smem = ((size_t)(h + 2 * G::R) * P.pitch + 64 + 112) * sizeof(float) + 16;
   int dev = 0, max_smem = 0;
   LPB_CUDA(cudaGetDevice(&dev));
@@ -1322,6 +1343,8 @@ static int launch_decode_bwd(const float* heat, const float* stats, const float*
   P.T = T;
   for (int p = 0; p < G::F; ++p)
     for (int t = 0; t < G::W; ++t) P.phase[p][t] = th->host.phase[(size_t)p * G::W + t];
+  for (int q = 0; q < G::F / 2; ++q)
+    for (int t = 0; t < G::W; ++t) P.phase2[q][t] = make_float2(P.phase[2 * q][t], P.phase[2 * q + 1][t]);
   if (win) {  // sparse windows first; the dense kernel below then only runs the planes they queued
     LPB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int), stream));
     decode_bwd_window_kernel<DS><<<(unsigned)((n_planes + 3) / 4), 128, 0, stream>>>(P, win, meta, queue);

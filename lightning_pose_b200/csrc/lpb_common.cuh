@@ -1,5 +1,6 @@
 // Shared helpers for the lpb200 CUDA library (sm_100a only).
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
@@ -54,6 +55,45 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2) ---------------------------------------------
+// Two IEEE fp32 operations per instruction: the same roundings as the scalar forms and the same FMA rate
+// (measured: 127 FMA/clk/SM either way, scripts/ubench/ffma.cu), but half the issue slots.  Operands that
+// are the same scalar in both halves (`dup2`) or a pair of kernel-parameter constants fold into the
+// instruction's broadcast / uniform-register operand forms, so they cost no extra moves.
+struct f32x2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 dup2(float x) { return pack2(x, x); }
+__device__ __forceinline__ void unpack2(f32x2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+// compile-time loop: fn(std::integral_constant<int, I>{}) for I in [0, N)
+template <int I, int N, class Fn>
+__device__ __forceinline__ void static_for(Fn&& fn) {
+  if constexpr (I < N) {
+    fn(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(fn);
+  }
 }
 
 // ---- mbarrier + 1-D bulk async copy (TMA engine, no tensor map needed) -------------------------
