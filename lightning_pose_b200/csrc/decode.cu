@@ -144,6 +144,56 @@ __device__ __forceinline__ void softmax_row(const f32x2* v2, float yrow, float c
   sy_it = fmaf(yrow, rs, sy_it) + (p0 + p1);
 }
 
+// One strip of the forward evaluation: the lane's fine column over coarse rows [r0, r1).  `base` points at the lane's first
+// horizontal tap in the tile row of coarse row r0 - R ("window row" 0); window row k is `base + k * pitch`.
+// The horizontal pass of W + 1 window rows lives in a ROTATING register window of packed pairs (no shifting moves): two
+// coarse rows are evaluated per step and the two window rows they free are refilled by one paired horizontal pass
+// (fma.rn.f32x2 over two tile rows).  In the round-2 capture of the dense kernel the shifting moves and their integer
+// bookkeeping were 40 % of the loop's instructions.
+template <int DS>
+__device__ __forceinline__ void fwd_strip(const DecodeParams<DS>& P, const float* base, int pitch, const float (&wc)[2 * (DS + 2) + 1],
+                                          int r0, int r1, float c, float kill, float& m, float& mc, float& s_it, float& sy_it) {
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1, NS = W + 1, NP2 = NS / 2, HP = F / 2;
+  const int h = P.h, nrows = r1 - r0, kmax = nrows - 1 + 2 * R;  // last window row a valid coarse row uses
+  auto hpair = [&](int k) -> f32x2 {  // horizontal pass of window rows k, k+1 (clamped to the rows that exist)
+    const float* ra = base + min(k, kmax) * pitch;
+    const float* rb = base + min(k + 1, kmax) * pitch;
+    f32x2 acc = pack2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < W; ++u) acc = fma2(dup2(wc[u]), pack2(ra[u], rb[u]), acc);
+    return acc;
+  };
+  f32x2 win[NP2];  // window rows la .. la+W; row la+j sits in slot (2i + j) % NS of pair-step i
+#pragma unroll
+  for (int i = 0; i < NP2; ++i) win[i] = hpair(2 * i);
+  for (int la0 = 0; la0 < nrows; la0 += NS) {
+    static_for<0, NP2>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      const int la = la0 + 2 * i;
+      if (la >= nrows) return;  // warp-uniform
+      float sl[NS];
+#pragma unroll
+      for (int j = 0; j < NP2; ++j) unpack2(win[j], sl[2 * j], sl[2 * j + 1]);
+      f32x2 v2[HP];
+      {
+        float t[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) t[k] = sl[(2 * i + k) % NS];
+        column_pass<DS>(P, r0 + la, h, t, v2);
+        softmax_row<DS>(v2, (float)((r0 + la) * F), c, kill, m, mc, s_it, sy_it);
+      }
+      if (la + 1 < nrows) {
+        float t[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) t[k] = sl[(2 * i + 1 + k) % NS];
+        column_pass<DS>(P, r0 + la + 1, h, t, v2);
+        softmax_row<DS>(v2, (float)((r0 + la + 1) * F), c, kill, m, mc, s_it, sy_it);
+      }
+      win[i] = hpair(la + NS);  // window rows la+W+1, la+W+2 take the slots of la, la+1
+    });
+  }
+}
+
 template <int DS>
 __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kernel(const __grid_constant__ DecodeParams<DS> P) {
   constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
@@ -404,32 +454,9 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
 #pragma unroll
     for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
     const float* colbase = tile + padl + (jc / F - R);  // add (a + R) * pitch for coarse row a
-    float tmp[W + 1];  // rows a-R .. a+R+1: two coarse rows are produced per iteration
-#pragma unroll
-    for (int t = 0; t < W; ++t) tmp[t] = dot_w<W>(colbase + (r0 + t) * pitch, wc);  // rows r0-R .. r0+R
     float m = M, mc = M * c, s_it = 0.f, sy_it = 0.f;
     const float kill = ok ? 0.f : -3.0e38f;
-
-    int a = r0;
-    float yrow = (float)(r0 * F);
-    for (; a + 1 < r1; a += 2, yrow += (float)(2 * F)) {
-      tmp[W] = dot_w<W>(colbase + (a + 1 + 2 * R) * pitch, wc);  // coarse row a+1+R
-      f32x2 v2[F / 2];
-      column_pass<DS>(P, a, h, tmp, v2);
-      softmax_row<DS>(v2, yrow, c, kill, m, mc, s_it, sy_it);
-      column_pass<DS>(P, a + 1, h, tmp + 1, v2);
-      softmax_row<DS>(v2, yrow + (float)F, c, kill, m, mc, s_it, sy_it);
-      if (a + 2 < r1) {
-#pragma unroll
-        for (int t = 0; t < W - 1; ++t) tmp[t] = tmp[t + 2];
-        tmp[W - 1] = dot_w<W>(colbase + (a + 2 + 2 * R) * pitch, wc);  // coarse row a+2+R
-      }
-    }
-    if (a < r1) {
-      f32x2 v2[F / 2];
-      column_pass<DS>(P, a, h, tmp, v2);
-      softmax_row<DS>(v2, yrow, c, kill, m, mc, s_it, sy_it);
-    }
+    fwd_strip<DS>(P, colbase + r0 * pitch, pitch, wc, r0, r1, c, kill, m, mc, s_it, sy_it);
     {  // fold the item into the lane's running state
       const float Mn = fmaxf(M, m);
       const float a1 = fast_exp2((M - Mn) * c), a2 = fast_exp2((m - Mn) * c);
@@ -724,22 +751,9 @@ __device__ void decode_plane_warp(const DecodeParams<DS>& P, long long plane, co
     for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
     const float* colbase = tile + (jc / F - R - c0w);  // add (a - R - r0w + t) * WP for coarse row a - R + t
     const int tr0 = ra0 - R - r0w;
-    float tmp[W + 1];
-#pragma unroll
-    for (int t = 0; t < W; ++t) tmp[t] = dot_w<W>(colbase + (tr0 + t) * DECW_WP, wc);
     float m = M, mc = M * c, s_it = 0.f, sy_it = 0.f;
     const float kill = ok ? 0.f : -3.0e38f;
-    float yrow = (float)(ra0 * F);
-    for (int a = ra0; a <= ra1; ++a, yrow += (float)F) {
-      f32x2 v2[F / 2];
-      column_pass<DS>(P, a, h, tmp, v2);
-      softmax_row<DS>(v2, yrow, c, kill, m, mc, s_it, sy_it);
-      if (a < ra1) {
-#pragma unroll
-        for (int t = 0; t < W - 1; ++t) tmp[t] = tmp[t + 1];
-        tmp[W - 1] = dot_w<W>(colbase + (tr0 + (a - ra0) + 1 + 2 * R) * DECW_WP, wc);
-      }
-    }
+    fwd_strip<DS>(P, colbase + tr0 * DECW_WP, DECW_WP, wc, ra0, ra1 + 1, c, kill, m, mc, s_it, sy_it);
     {
       const float Mn = fmaxf(M, m);
       const float a1 = fast_exp2((M - Mn) * c), a2 = fast_exp2((m - Mn) * c);
@@ -878,25 +892,56 @@ struct DecodeBwdParams {
   float2 phase2[F / 2][W];  // {phase[2q][t], phase[2q+1][t]}: packed-pair operands of the strip evaluation
 };
 
-// Transposed horizontal pass for one coarse row of one 32-fine-column strip.  Lane j holds gv = (U_H^T G)[row][j]
-// for its fine column; the F lanes of a coarse column share the W horizontal taps wc.  Coarse output column
-// c = group + tap; lane c gathers its W contributions by shuffle, so the row costs ONE shared-memory update per
-// output column (shared-memory float atomics are CAS loops on this architecture -- 9 of them per row before).
-template <int DS, bool ATOMIC>
-__device__ __forceinline__ void scatter_row(float* grow0, float gv, const float (&wc)[2 * (DS + 2) + 1], int lane, int maxcols) {
-  constexpr int F = 1 << DS, W = 2 * (DS + 2) + 1, NG = 32 / F;
-  float acc = 0.f;
+// Transposed horizontal pass for one coarse row of one 32-fine-column strip: out[oc] = sum_jj gv[jj] * tabW[jj][oc - jj/F]
+// over the strip's fine columns jj, for the NOUT = 32/F + W - 1 coarse columns the strip touches.  Every lane drops its
+// gv = (U_H^T G)[row][jj] into a 32-float row buffer in shared memory; the output columns then GATHER: lane (oc, part) reads
+// 16 consecutive values (four 16-byte loads) and multiplies them with weights it fetched once per strip (`ScatterPlan`),
+// the two parts of a column meet in one shuffle, and the row costs ONE shared-memory update per output column.  (The
+// first version reduced the F lanes of a coarse column with shuffles, tap by tap: 27 shuffles + 36 adds per row, the
+// largest share of the backward's instructions in the round-2 capture.)
+template <int DS>
+struct ScatterPlan {
+  static constexpr int F = 1 << DS, W = 2 * (DS + 2) + 1, NG = 32 / F, NOUT = NG + W - 1, SPLIT = NOUT <= 16 ? 2 : 1;
+  float wt[16];  // weight of fine column jstart + i for this lane's output column (0 outside the band / the strip)
+  int oc, jstart;
+  bool writer;
+  __device__ __forceinline__ void init(const float* __restrict__ tabW, int jf0, int J1, int lane) {
+    const int part = SPLIT == 2 ? (lane & 1) : 0;
+    oc = SPLIT == 2 ? (lane >> 1) : lane;
+    if (SPLIT == 2) {
+      jstart = 16 * part;
+    } else {
+      int js = ((oc - (W - 1)) * F) & ~3;
+      jstart = js < 0 ? 0 : (js > 16 ? 16 : js);
+    }
+    writer = oc < NOUT && part == 0;
 #pragma unroll
-  for (int u = 0; u < W; ++u) {
-    float v = gv * wc[u];
-#pragma unroll
-    for (int o = 1; o < F; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const float got = __shfl_sync(0xffffffffu, v, ((lane - u) * F) & 31);
-    if ((unsigned)(lane - u) < (unsigned)NG) acc += got;
+    for (int i = 0; i < 16; ++i) {
+      const int jj = jstart + i, u = oc - jj / F;
+      wt[i] = (oc < NOUT && u >= 0 && u < W && jf0 + jj < J1) ? __ldg(tabW + (size_t)(jf0 + jj) * W + u) : 0.f;
+    }
   }
-  if (lane < NG + W - 1 && lane < maxcols && acc != 0.f) {
-    if (ATOMIC) atomicAdd(grow0 + lane, acc);
-    else grow0[lane] += acc;
+};
+
+template <int DS, bool ATOMIC>
+__device__ __forceinline__ void scatter_row(float* grow0, float gv, const ScatterPlan<DS>& sp, float* srow, int lane, int maxcols) {
+  srow[lane] = gv;
+  __syncwarp();
+  const float4* s4 = reinterpret_cast<const float4*>(srow + sp.jstart);
+  f32x2 acc2 = pack2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 x = s4[i];
+    acc2 = fma2(pack2(x.x, x.y), pack2(sp.wt[4 * i], sp.wt[4 * i + 1]), acc2);
+    acc2 = fma2(pack2(x.z, x.w), pack2(sp.wt[4 * i + 2], sp.wt[4 * i + 3]), acc2);
+  }
+  float lo, hi;
+  unpack2(acc2, lo, hi);
+  float acc = lo + hi;
+  if (ScatterPlan<DS>::SPLIT == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (sp.writer && sp.oc < maxcols && acc != 0.f) {
+    if (ATOMIC) atomicAdd(grow0 + sp.oc, acc);
+    else grow0[sp.oc] += acc;
   }
 }
 
@@ -906,7 +951,8 @@ __device__ __forceinline__ void scatter_row(float* grow0, float gv, const float 
 template <int DS, bool ATOMIC>
 __device__ __forceinline__ void decode_bwd_strip(const DecodeBwdParams<DS>& P, const float* tile, float* gt, int pitch,
                                                  int trow0, int tcol0, int maxcols, int jf0, int J1, int r0, int r1, float M,
-                                                 float c, float kscale, float xhat, float yhat, float gx, float gy, int lane) {
+                                                 float c, float kscale, float xhat, float yhat, float gx, float gy, int lane,
+                                                 float* srow) {
   constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1, HP = F / 2;
   const int h = P.h;
   const int jf = jf0 + lane;
@@ -916,6 +962,8 @@ __device__ __forceinline__ void decode_bwd_strip(const DecodeBwdParams<DS>& P, c
 #pragma unroll
   for (int t = 0; t < W; ++t) wc[t] = __ldg(P.tabW + jc * W + t);
   const float* colbase = tile + tcol0 + (jc / F - jf0 / F);
+  ScatterPlan<DS> sp;
+  sp.init(P.tabW, jf0, J1, lane);
   // Register windows over the W coarse rows a-R .. a+R that the fine rows of coarse row a touch.  They are ROTATED, not
   // shifted: the row loop is unrolled W times and in its `rot`-th copy tap t lives in slot (t + rot) % W, so advancing a
   // row costs no register moves.  The F phases are processed as pairs (packed fp32, lpb_common.cuh): `gacc[slot]` holds
@@ -969,7 +1017,7 @@ __device__ __forceinline__ void decode_bwd_strip(const DecodeBwdParams<DS>& P, c
       // coarse row r0 + la - R is complete for this lane's column
       float lo, hi;
       unpack2(gacc[rot], lo, hi);
-      scatter_row<DS, ATOMIC>(gt + (trow0 + la) * pitch + tcol0, lo + hi, wc, lane, maxcols);
+      scatter_row<DS, ATOMIC>(gt + (trow0 + la) * pitch + tcol0, lo + hi, sp, srow + 32 * (la & 1), lane, maxcols);
       gacc[rot] = pack2(0.f, 0.f);
       tmp[rot] = (la + 1 < nrows) ? dot_w<W>(colbase + (trow0 + la + 1 + 2 * R) * pitch, wc) : 0.f;
     });
@@ -988,7 +1036,8 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_co
   const int tile_floats = (h + 2 * R) * pitch;
   float* tile = reinterpret_cast<float*>(smem_raw);
   float* gtile = tile + tile_floats;  // same padded geometry, accumulates U_H^T G U_W
-  uint64_t* bar = reinterpret_cast<uint64_t*>(gtile + tile_floats);
+  float* srows = gtile + tile_floats;  // [DEC_WARPS][2][32] row buffers of the transposed horizontal pass
+  uint64_t* bar = reinterpret_cast<uint64_t*>(srows + DEC_WARPS * 64);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (P.bulk) {
     if (tid == 0) {
@@ -1073,7 +1122,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_bwd_kernel(const __grid_co
         const int jf0 = J0 + sidx * 32;
         const int tcol0 = padl + (jf0 / F - R);
         decode_bwd_strip<DS, true>(P, tile, gtile, pitch, r0, tcol0, pitch - tcol0, jf0, J1, r0, r1, M, c, kscale, xhat, yhat, gx, gy,
-                                   lane);
+                                   lane, srows + warp * 64);
       }
     }
     __syncthreads();
@@ -1111,6 +1160,7 @@ __global__ void __launch_bounds__(128) decode_bwd_window_kernel(const __grid_con
   constexpr int F = 1 << DS, R = DS + 2;
   __shared__ float tile_s[4][DEC_WIN * DEC_WP];
   __shared__ float g_s[4][DEC_WIN * DEC_WP];
+  __shared__ __align__(16) float srow_s[4][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long plane = (long long)blockIdx.x * 4 + warp;
   if (plane >= P.n_planes) return;
@@ -1180,7 +1230,7 @@ __global__ void __launch_bounds__(128) decode_bwd_window_kernel(const __grid_con
     const int jf0 = J0 + sidx * 32;
     const int tcol0 = jf0 / F - B0;  // window column of coarse column jf0/F - R
     decode_bwd_strip<DS, false>(P, tile, gt, DEC_WP, ra0 - A0, tcol0, DEC_WIN - tcol0, jf0, J1, ra0, ra1 + 1, M, c, kscale, xhat, yhat, gx,
-                                gy, lane);
+                                gy, lane, srow_s[warp]);
     __syncwarp();
   }
   float dot = 0.f;
@@ -1349,7 +1399,7 @@ static int launch_decode_bwd(const float* heat, const float* stats, const float*
     LPB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int), stream));
     decode_bwd_window_kernel<DS><<<(unsigned)((n_planes + 3) / 4), 128, 0, stream>>>(P, win, meta, queue);
   }
-  const size_t smem = ((size_t)2 * (h + 2 * G::R) * P.pitch) * sizeof(float) + 16;
+  const size_t smem = ((size_t)2 * (h + 2 * G::R) * P.pitch + DEC_WARPS * 64) * sizeof(float) + 16;
   int dev = 0, max_smem = 0;
   LPB_CUDA(cudaGetDevice(&dev));
   LPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
