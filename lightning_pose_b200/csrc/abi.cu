@@ -21,6 +21,8 @@ int g_tuning[LPB_TUNE_COUNT] = {
     1,  // LPB_TUNE_DECODE_L2_HINTS
     1,  // LPB_TUNE_B3A_PREFETCH
     1,  // LPB_TUNE_SOFTMAX_SPLIT
+    0,  // LPB_TUNE_DECODE_WARP_CTAS
+    0,  // LPB_TUNE_DECODE_REVERSE
 };
 }
 extern "C" int lpb_set_tuning(int key, int value) {

@@ -41,6 +41,7 @@ struct DecodeParams {
   int64_t n_planes;
   float T, lip, offset;
   int l2_hints;       // warp kernel: L2 eviction-priority hints on its two sweeps (LPB_TUNE_DECODE_L2_HINTS)
+  int reverse;        // warp kernel: planes are taken last-to-first (LPB_TUNE_DECODE_REVERSE)
   const int* queue;   // CTA kernel, queue mode: {count, plane ids ...} left over by the warp-per-plane kernel
   int* qcounter;      // [n_planes] arrival counters (zeroed) and
   float* qscratch;    // [n_planes][DEC_MAX_PARTS][4] partial softmax states of a plane split over several CTAs
@@ -808,8 +809,9 @@ template <int DS>
 __global__ void __launch_bounds__(128) decode_fwd_warp_kernel(const __grid_constant__ DecodeParams<DS> P, int* __restrict__ queue) {
   __shared__ float tile_s[4][DECW_WIN * DECW_WP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long plane = (long long)blockIdx.x * 4 + warp;
+  long long plane = (long long)blockIdx.x * 4 + warp;
   if (plane >= P.n_planes) return;
+  if (P.reverse) plane = P.n_planes - 1 - plane;
   decode_plane_warp<DS, false>(P, plane, P.heat + (size_t)plane * P.h * P.w, tile_s[warp], queue, lane);
 }
 
@@ -1311,6 +1313,7 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
   P.qcounter = nullptr;
   P.qscratch = nullptr;
   P.l2_hints = g_tuning[LPB_TUNE_DECODE_L2_HINTS];
+  P.reverse = g_tuning[LPB_TUNE_DECODE_REVERSE];
   P.lipw = tw->host.lip;
   for (int t = 0; t < G::W; ++t) {
     float m = 0.f;
@@ -1348,7 +1351,16 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
       LPB_CUDA(cudaFuncSetAttribute(decode_fwd_ring_kernel<DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
       decode_fwd_ring_kernel<DS><<<(unsigned)(n_planes < sms ? n_planes : sms), 32 * (DECR_WARPS + 1), rsm, stream>>>(P, queue, nslots);
     } else {
-      decode_fwd_warp_kernel<DS><<<(unsigned)((n_planes + 3) / 4), 128, 0, stream>>>(P, queue);
+      // optional occupancy cap: unused dynamic shared memory keeps the resident planes (4 per CTA) within L2's reach
+      size_t pad = 0;
+      const int cap = g_tuning[LPB_TUNE_DECODE_WARP_CTAS];
+      if (cap > 0) {
+        const size_t per_cta = ((size_t)max_smem + 1024) / (size_t)(cap + 1) + 1024, stat = sizeof(float) * 4 * DECW_WIN * DECW_WP + 1024;
+        pad = per_cta > stat ? per_cta - stat : 0;
+        if (pad + stat > (size_t)max_smem) pad = (size_t)max_smem - stat;
+        LPB_CUDA(cudaFuncSetAttribute(decode_fwd_warp_kernel<DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+      }
+      decode_fwd_warp_kernel<DS><<<(unsigned)((n_planes + 3) / 4), 128, pad, stream>>>(P, queue);
     }
     P.queue = queue;
     P.qcounter = queue + 1 + n_planes;

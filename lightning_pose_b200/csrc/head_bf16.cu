@@ -157,6 +157,7 @@ constexpr int K1A_TW = 4;                      // transposer warps
 constexpr int K1A_THREADS = 32 * (K1A_TW + 6);  // + MMA warp, 4 epilogue warps, TMA loader warp
 constexpr int K1A_ASTAGES = 2;  // K-major operand stages (A + packed weights)
 constexpr int K1A_RSTAGES = 2;  // raw NCHW stages filled by the TMA engine
+constexpr int K1A_MAXPAD = 6;   // pad rows of the saved copy a transposer thread writes per stage (host falls back to head_prep beyond)
 
 struct K1aParams {
   const __nv_bfloat16* feat;  // [B][C][H*W]
@@ -170,6 +171,7 @@ struct K1aParams {
   int row_transposer;         // 1: row-per-lane transposer (coalesced operand-copy stores); 0: 8x8 register-block transposer
   int backoff;                // idle warps sleep between barrier polls
   int xs_bulk;                // 1: the saved operand copy is written by TMA bulk stores straight from the operand stage
+  int xs_pads;                // 1: the block transposers also write the saved copy's pad rows (else head_prep cleared them)
   HeadGeom g;
 };
 
@@ -330,6 +332,27 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
     }
     const uint32_t chan_stride = (uint32_t)(4 * P.HW * 2);       // next shuffled channel e -> 4 source channels on
     const uint32_t wrap_jump = (uint32_t)((2 * g.P - 2 * P.W) * 16);  // extra bytes once the position wraps to row i + 1
+    // The saved copy's pad rows (the zero column of every image row, the lead / trail rows) are written here as well, next
+    // to the real rows that share their 32-byte sectors: a separate clearing pass over those scattered 16-byte pieces
+    // cost 35 us per 512 frames in the preparation launch.  Per stage: 4 K-chunks x npad rows over the 128 transposer threads.
+    constexpr int MAXP = K1A_MAXPAD;
+    uint32_t t_pad[MAXP];
+    int npd = 0;
+    {
+      const RowLayout L = P.Lxs;
+      const int body1 = L.lead + L.Hi * L.Pp, ntail = L.rows - body1, npad = L.lead + ntail + L.Hi;
+#pragma unroll
+      for (int k = 0; k < MAXP; ++k) {
+        const int e = tid + k * 32 * K1A_TW;
+        t_pad[k] = 0;
+        if (e < 4 * npad) {
+          const int kc = e / npad, i = e - kc * npad;
+          const int row = i < L.lead ? i : (i < L.lead + ntail ? body1 + (i - L.lead) : L.lead + (i - L.lead - ntail) * L.Pp + L.Wi);
+          t_pad[k] = (uint32_t)((kc * L.rows + row) * 16);
+          npd = k + 1;
+        }
+      }
+    }
     for (int it = 0; it < total_it; ++it) {
       const int s = it % K1A_ASTAGES, r = it % K1A_RSTAGES;
       mbar_wait(&raw_full[r], (it / K1A_RSTAGES) & 1);
@@ -366,6 +389,11 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
             if (xs_st) *reinterpret_cast<uint4*>(xs_st + t_x[k] + delta) = o;
           }
         }
+      }
+      if (xs_st && P.xs_pads) {
+#pragma unroll
+        for (int k = 0; k < MAXP; ++k)
+          if (k < npd) *reinterpret_cast<uint4*>(xs_st + t_pad[k]) = make_uint4(0, 0, 0, 0);
       }
       fence_proxy_async();
       tc::mbar_arrive(&full[s]);
@@ -784,6 +812,9 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   __nv_bfloat16* mid = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES);
   float* partials = reinterpret_cast<float*>(ws + (size_t)(nst + 1) * HB_BSTAGE_BYTES + (c2 > 0 ? (size_t)B * 4 * Lmid.rows * 16 : 0));
   const bool fast = head_fast_path(C, H, W, c2, max_smem);
+  // k1a's block transposers write the saved copy's pad rows themselves when a thread's share fits its registers
+  const int xs_npad = Lxs.lead + (Lxs.rows - (Lxs.lead + Lxs.Hi * Lxs.Pp)) + Lxs.Hi;
+  const bool k1a_pads = fast && !g_tuning[LPB_TUNE_K1A_ROW_TRANSPOSER] && !g_tuning[LPB_TUNE_K1A_BULK_XS] && 4 * xs_npad <= K1A_MAXPAD * 32 * K1A_TW;
   {
     // one launch: both operand packs + the pad rows of the fresh row-layout buffers
     PrepJobs jobs{};
@@ -794,7 +825,8 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
       jobs.fpack[1] = {w2, final_softmax ? nullptr : b2, c1, c2, 1, wp2};
       jobs.pads[0] = {mid, Lmid, (long long)B * 4};
     }
-    if (fast && saved_xs && !g_tuning[LPB_TUNE_K1A_BULK_XS]) jobs.pads[1] = {static_cast<__nv_bfloat16*>(saved_xs), Lxs, (long long)B * (C / 32)};  // (the banded path's shuffle kernel writes its own pads)
+    // (the block transposer of k1a writes the saved copy's pads itself; the row-form variant does not)
+    if (fast && saved_xs && !g_tuning[LPB_TUNE_K1A_BULK_XS] && !k1a_pads) jobs.pads[1] = {static_cast<__nv_bfloat16*>(saved_xs), Lxs, (long long)B * (C / 32)};  // (the banded path's shuffle kernel writes its own pads)
     launch_head_prep(jobs, s);
   }
   if (!fast) {
@@ -860,6 +892,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   pa.row_transposer = g_tuning[LPB_TUNE_K1A_ROW_TRANSPOSER];
   pa.backoff = g_tuning[LPB_TUNE_WAIT_BACKOFF];
   pa.xs_bulk = g_tuning[LPB_TUNE_K1A_BULK_XS];
+  pa.xs_pads = k1a_pads ? 1 : 0;
   pa.g = g1;
   LPB_CUDA(cudaFuncSetAttribute(k1a_shuffle_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
   k1a_shuffle_convt_kernel<<<B < sms ? B : sms, K1A_THREADS, s1, s>>>(pa);

@@ -1103,12 +1103,13 @@ def test_kernel_variants_agree(lpb, dev):
         ((kp * gk).sum() * 1e-3 + (hm * hm).sum()).backward()
         return hm.detach().clone(), kp.detach().clone(), cf.detach().clone(), f.grad.float().clone(), list(head.upsampling_layers)[1].weight.grad.clone()
 
-    saved = [lib.lpb_get_tuning(k) for k in range(8)]
+    nkeys = 10
+    saved = [lib.lpb_get_tuning(k) for k in range(nkeys)]
     try:
-        for k in range(8):
-            lib.lpb_set_tuning(k, 1)
+        for k in range(nkeys):
+            lib.lpb_set_tuning(k, 3 if k == 8 else 1)  # key 8 is a count (resident decode CTAs per SM), the others are switches
         new = run()
-        for k in range(8):
+        for k in range(nkeys):
             lib.lpb_set_tuning(k, 0)
         old = run()
     finally:
