@@ -156,13 +156,13 @@ BACKBONE_PARAMS = 23_508_032  # ResNet-50 trunk (94.4 MB of fp32 gr
 
 class HotPath:
     # our own kernel launches per step, counted from the committed ncu launch list (profiles/r02_launches_train_step.csv);
-    # library kernels of torch (Adam, a dozen scalar element-wise ops, NCCL) are not counted
+    # library kernels of torch (a dozen scalar element-wise ops, NCCL) are not counted
     # per head call: preparation (packs + pads) + k1a + banded layer 2 (softmax statistics + normalising launch) + decode
     # (warp kernel + queued CTA kernel) = 6;  labeled: + fused targets/MSE (2);  unlabeled: + remap + unsupervised losses (2)
     LAUNCHES_FWD = 2 * 6 + 2 + 2
     # unlabeled: unsup bwd, remap bwd, decode windows + dense fallback, then per head backward: preparation, plane dots,
     # G2 front end, wgrad2, dgrad2, wgrad1, dgrad1 = 7;  labeled: targets/MSE bwd + the same 7
-    LAUNCHES_BWD = (4 + 7) + (1 + 7)
+    LAUNCHES_BWD = (4 + 7) + (1 + 7) + 1  # + the Adam step
 
     def __init__(self, prob, device, fwd_only: bool, world: int = 1, ddp_payload_floats: int = 0, two_streams: bool = True):
         from lightning_pose_b200 import ops
@@ -191,7 +191,8 @@ class HotPath:
             # the head's parameters receive gradients from two streams on purpose (the engine orders them with events)
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         if not fwd_only:
-            self.opt = torch.optim.Adam(self.head.parameters(), lr=1e-5, fused=True, capturable=True)
+            from lightning_pose_b200.optim import FusedAdam
+            self.opt = FusedAdam(self.head.parameters(), lr=1e-5)  # torch.optim.Adam semantics, one native launch
             if world > 1:
                 self.reducer = FlatGradAllReducer(self.head.parameters(), n_scalars=4, extra_floats=ddp_payload_floats)
 
@@ -537,7 +538,7 @@ def run_ours(args):
         "config": {
             "workload": f"BASELINE configs[1] hot path on ResNet-50 features (B,2048,12,12): {args.clips} clips/step/GPU x (16 labeled + 32 unlabeled) frames, "
                         f"K=17, heatmaps 96x96, decode field 384x384; pass = {'forward' if args.fwd_only else 'forward + backward + Adam step on the head (+ gradient all-reduce when N>1)'}",
-            "backward": "all native: loss stack, remap, sparse soft-argmax windows, target+mse, fused softmax-backward/G2 front end, tcgen05 dgrad+wgrad of both transposed convolutions; torch library: fused Adam on the head parameters",
+            "backward": "all native: loss stack, remap, sparse soft-argmax windows, target+mse, fused softmax-backward/G2 front end, tcgen05 dgrad+wgrad of both transposed convolutions; Adam step on the head parameters: one native launch (lpb_adam_step)",
             "frames_per_step_per_gpu": n_frames, "regime": ("trained-like synthetic response (unimodal Gaussian-like heatmaps; planted features + bilinear per-keypoint deconvs, see bench.make_problem); fresh_init_regime = reference initialiser"
                                                                                   if args.regime == "trained" else "fresh init (reference initialiser, flat heatmaps)"),
             "launch": ("whole step replayed from one CUDA graph" if graphed else "eager launches")

@@ -50,7 +50,8 @@ const char* lpb_build_arch(void);     /* "sm_100a" */
 #define LPB_TUNE_SOFTMAX_SPLIT 7         /* 1 (default): plane softmax as two launches parallel over (frame, band) instead of one per-frame two-pass kernel */
 #define LPB_TUNE_DECODE_WARP_CTAS 8     /* > 0: resident CTAs per SM of the warp-per-plane decode are capped (fewer planes in flight than L2 holds); 0: no cap */
 #define LPB_TUNE_DECODE_REVERSE 9       /* 1: the decode walks the planes last-to-first (the producer's most recent writes are still in L2) */
-#define LPB_TUNE_COUNT 10
+#define LPB_TUNE_B3A_TMA_STORE 10       /* 1 (default): b3a stages d features in shared memory and a TMA tensor store scatters them to NCHW; 0: direct 16-byte stores */
+#define LPB_TUNE_COUNT 11
 int lpb_set_tuning(int key, int value);
 int lpb_get_tuning(int key);
 
@@ -235,6 +236,19 @@ int lpb_frames_normalize(const uint8_t* frames_u8, int F, int H, int W, int out_
  * (padding frames of the last chunk) are dropped. */
 int lpb_pack_predictions(const float* keypoints, const float* confidences, int n_frames, int K, float* table,
                          int64_t n_rows, int64_t* cursor, int64_t row0, void* stream);
+
+/* ---- optimizer step (the tail of a training step) ---------------------------------------------------
+ * replaces torch.optim.Adam / AdamW as configured by configure_optimizers  lightning_pose/models/base.py:458-477
+ * (no amsgrad).  One launch over up to 16 fp32 tensors; params / grads / exp_avg / exp_avg_sq / numel are HOST arrays
+ * of n_tensors device pointers / element counts.  step: device float, the number of steps taken so far (advanced by
+ * the launch, so a captured graph replays correctly); block_counter: device uint32 initialised to 0.
+ * lr_dev: optional device float overriding lr (learning-rate schedules under graph replay).
+ * beta1 / beta2 are doubles: 1 - beta^t is evaluated in fp64 (fp32 loses five digits at beta2 = 0.999).
+ * decoupled = 0: Adam (weight_decay is an L2 term added to the gradient), 1: AdamW. */
+int lpb_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const int64_t* numel, float* step, uint32_t* block_counter, float lr,
+                  const float* lr_dev, double beta1, double beta2, float eps, float weight_decay, int decoupled,
+                  void* stream);
 
 /* backward of the head's final spatial softmax: grad_logits = p * (g - sum(g * p)) per plane
  * (reference: autograd of spatial_softmax2d, lightning_pose/models/heads/heatmap.py:211) */

@@ -754,7 +754,22 @@ __device__ void decode_plane_warp(const DecodeParams<DS>& P, long long plane, co
     const int tr0 = ra0 - R - r0w;
     float m = M, mc = M * c, s_it = 0.f, sy_it = 0.f;
     const float kill = ok ? 0.f : -3.0e38f;
-    fwd_strip<DS>(P, colbase + tr0 * DECW_WP, DECW_WP, wc, ra0, ra1 + 1, c, kill, m, mc, s_it, sy_it);
+    // a window holds a handful of rows: the shifting register window (small code, 64 registers) beats the rotating
+    // one of fwd_strip here (measured: 0.185 vs 0.201 ms per 768 frames; the dense CTA kernel is the other way round)
+    float tmp[W];
+#pragma unroll
+    for (int t = 0; t < W; ++t) tmp[t] = dot_w<W>(colbase + (tr0 + t) * DECW_WP, wc);
+    float yrow = (float)(ra0 * F);
+    for (int a = ra0; a <= ra1; ++a, yrow += (float)F) {
+      f32x2 v2[F / 2];
+      column_pass<DS>(P, a, h, tmp, v2);
+      softmax_row<DS>(v2, yrow, c, kill, m, mc, s_it, sy_it);
+      if (a < ra1) {
+#pragma unroll
+        for (int t = 0; t < W - 1; ++t) tmp[t] = tmp[t + 1];
+        tmp[W - 1] = dot_w<W>(colbase + (tr0 + (a - ra0) + 1 + 2 * R) * DECW_WP, wc);
+      }
+    }
     {
       const float Mn = fmaxf(M, m);
       const float a1 = fast_exp2((M - Mn) * c), a2 = fast_exp2((m - Mn) * c);

@@ -14,6 +14,9 @@
 
 #include "../../include/lpb200.h"
 #include "head_prep.cuh"
+#include <cstring>
+#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
+
 #include "lpb_common.cuh"
 #include "row_layout.cuh"
 #include "tcgen05.cuh"
@@ -116,21 +119,25 @@ __global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B
     // wtile[o][yl][lx] = win[o][2*m0 + yl - row0][lx] (0 outside the window / for planes without one)
     // one window row (32 floats) per warp and step, all steps unrolled: the predicated loads are independent
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    constexpr int NROW = GB_CLS * 2 * G2B_MROWS, NSTEP = NROW / (G2B_THREADS / 32);
-    float stage[NSTEP];
+    constexpr int NROW = GB_CLS * 2 * G2B_MROWS, NSTEP = NROW / (G2B_THREADS / 32), NB = 10;  // NB loads in flight per thread
+    static_assert(NSTEP % NB == 0, "window staging batches");
+#pragma unroll 1
+    for (int k0 = 0; k0 < NSTEP; k0 += NB) {
+      float stage[NB];
 #pragma unroll
-    for (int k = 0; k < NSTEP; ++k) {
-      const int r = wq + k * (G2B_THREADS / 32), o = r / (2 * G2B_MROWS), yl = r - o * (2 * G2B_MROWS);
-      float v = 0.f;
-      if (o < C && ((shit >> o) & 1u)) {
-        const int4 mt = smeta[o];
-        const int ly = 2 * m0 + yl - mt.x;
-        if (mt.z == 1 && (unsigned)ly < 32u) v = __ldg(S.win + ((size_t)b * C + o) * 1024 + ly * 32 + lane);
+      for (int k = 0; k < NB; ++k) {
+        const int r = wq + (k0 + k) * (G2B_THREADS / 32), o = r / (2 * G2B_MROWS), yl = r - o * (2 * G2B_MROWS);
+        float v = 0.f;
+        if (o < C && ((shit >> o) & 1u)) {
+          const int4 mt = smeta[o];
+          const int ly = 2 * m0 + yl - mt.x;
+          if (mt.z == 1 && (unsigned)ly < 32u) v = __ldg(S.win + ((size_t)b * C + o) * 1024 + ly * 32 + lane);
+        }
+        stage[k] = v;
       }
-      stage[k] = v;
-    }
 #pragma unroll
-    for (int k = 0; k < NSTEP; ++k) wtile[(wq + k * (G2B_THREADS / 32)) * 32 + lane] = stage[k];
+      for (int k = 0; k < NB; ++k) wtile[(wq + (k0 + k) * (G2B_THREADS / 32)) * 32 + lane] = stage[k];
+    }
   }
   __syncthreads();
   if (t >= Hi * Wi) return;
@@ -416,12 +423,25 @@ struct B3aParams {
   int Hh;                    // image rows per band (multiple of 4)
   int ncols;                 // TMEM columns per band = Hh * (Wi + 1) rounded up to 16 (<= 304; <= 256: double-buffered)
   int backoff, prefetch;
+  int tma_store;             // 1: the epilogue stages bf16 rows in shared memory and a TMA tensor store writes them (below)
 };
+
+// TMA tensor store of d features.  The tensor map views the NCHW gradient as [b][c'][pl][px] (source plane 4c' + pl,
+// px = H*W pixels); a box is {2 feature rows, one pl, 128 c', one frame}: in shared memory 128 rows of 4*WS2 bytes, so
+// thread c' writes at a 4*WS2-byte stride (conflict-free for WS2 = 12) and the copy engine does the 1152-byte-strided
+// scatter that cost the epilogue 32 half-used sectors per store instruction.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* smem_src, int x0, int x1, int x2, int x3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm), "r"(smem_u32(smem_src)), "r"(x0),
+               "r"(x1), "r"(x2), "r"(x3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // A frame is processed in bands of Hh image rows (the accumulator of a band, N = Hh * (Wi + 1) pixels, must fit TMEM next
 // to nothing else; the band's gradient rows plus the halo row above are double-buffered in shared memory).
 template <int WS2>
-__global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_constant__ B3aParams P) {
+__global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_constant__ B3aParams P, const __grid_constant__ CUtensorMap TM) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Wi = P.Wi, Hi = P.Hi, Pp = Wi + 1, LEAD = Pp + 1;
   const int Hh = P.Hh, nbands = (Hi + Hh - 1) / Hh;
@@ -437,6 +457,8 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
   uint64_t* t_full = bars + 5;   // [2]
   uint64_t* t_empty = bars + 7;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  // staging slices of the TMA store: [ip & 1][pl][128 lanes][4 * WS2 bytes]
+  unsigned char* Ss = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(bars + 12) + 127) & ~(uintptr_t)127);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntile = (P.C4 + 127) / 128;
   // accumulator buffers: two when a band's columns fit twice into the 512 TMEM columns (the MMAs of band i + 1 then
@@ -530,7 +552,7 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
     const int c = mt * 128 + 32 * q + lane;
     const int HW = (Hi / 2) * WS2;
     constexpr int NCH = (2 * WS2 + 15) / 16;  // 16-column TMEM loads per accumulator row
-    int it = 0;
+    int it = 0, tma_cnt = 0;
     for (int b = slot; b < P.B; b += nslot)
       for (int band = 0; band < nbands; ++band, ++it) {
         const int y0 = band * Hh, hb = min(Hh, Hi - y0);
@@ -570,7 +592,44 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
           }
         };
         const int nitems = 2 * npairs;
-        if (NCH <= 2 && P.prefetch) {
+        if (P.tma_store) {
+          // warps with the same e (= di) form a group of 128 lanes that owns the slices pl = 2e, 2e + 1; per item:
+          //   the group's issuer makes sure the copy that last read these slices is done, the group writes its
+          //   2 x (2 * WS2 / 8) 16-byte pieces per lane, and the issuer launches one tensor store per plane class
+          constexpr int PB = 4 * WS2, SLICE = 128 * PB;  // bytes per lane and slice / per slice
+          const bool issuer = (q == 0 && lane == 0);
+          float va[2][NCH * 16];
+          for (int item = e; item < nitems; item += 2, ++tma_cnt) {
+            issue(item, va);
+            const int ip = item >> 1, par = tma_cnt & 1;  // the group's slices alternate item by item
+            unsigned char* sl = Ss + (size_t)(par * 4 + 2 * e) * SLICE + (size_t)(32 * q + lane) * PB;
+            if (issuer) bulk_wait_group_read1();  // at most the previous item's stores (the other ip parity) still read smem
+            named_bar_sync(1 + e, 128);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int dj = 0; dj < 2; ++dj) {
+#pragma unroll
+              for (int s4 = 0; s4 < (2 * WS2) / 8; ++s4) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  const int x0 = 8 * s4 + 2 * e2, x1 = x0 + 1;
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(va[x0 / WS2][2 * (x0 % WS2) + dj], va[x1 / WS2][2 * (x1 % WS2) + dj]);
+                  pk[e2] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                *reinterpret_cast<uint4*>(sl + dj * SLICE + 16 * s4) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+            fence_proxy_async();
+            named_bar_sync(1 + e, 128);
+            if (issuer) {
+              const int px0 = (y0 / 2 + 2 * ip) * WS2;
+              tma_store_4d(&TM, Ss + (size_t)(par * 4 + 2 * e) * SLICE, px0, 2 * e, mt * 128, b);
+              tma_store_4d(&TM, Ss + (size_t)(par * 4 + 2 * e + 1) * SLICE, px0, 2 * e + 1, mt * 128, b);
+              bulk_commit_group();
+            }
+          }
+        } else if (NCH <= 2 && P.prefetch) {
           // the TMEM loads of the next item are in flight while the current item is converted and stored (the
           // epilogue was TMEM-load-latency bound: ~55 % of its stall samples sat behind tcgen05.wait::ld)
           float va[2][NCH * 16], vb[2][NCH * 16];
@@ -596,6 +655,7 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
         tc::fence_before_sync();
         tc::mbar_arrive(&t_empty[tb]);
       }
+    if (P.tma_store && q == 0 && lane == 0) bulk_wait_group0();  // the stores have landed before the kernel ends
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -824,6 +884,30 @@ static int b3a_band_rows(int Hi1, int Wi1) {
   return hh;
 }
 
+// d features [B][4*C4][HW] bf16 viewed as [b][c'][pl][px]; box = {box_px pixels, one pl, 128 c', one frame}.
+// The encoder is a driver entry point; it is looked up once (no link-time dependency on libcuda).
+static bool make_dfeat_tensor_map(CUtensorMap* tm, void* dfeat, int B, int C4, int HW, int box_px) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static bool looked_up = false;
+  if (!looked_up) {
+    looked_up = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeFn>(fn);
+    (void)cudaGetLastError();
+  }
+  if (!encode || (HW * 2) % 16 != 0 || (box_px * 2) % 16 != 0 || box_px > 256) return false;
+  const cuuint64_t gdim[4] = {(cuuint64_t)HW, 4, (cuuint64_t)C4, (cuuint64_t)B};
+  const cuuint64_t gstride[3] = {(cuuint64_t)HW * 2, (cuuint64_t)HW * 2 * 4, (cuuint64_t)HW * 2 * 4 * (cuuint64_t)C4};  // bytes, dims 1..3
+  const cuuint32_t box[4] = {(cuuint32_t)box_px, 1, 128, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dfeat, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace lpb
 
 // workspace: [W1 dgrad pack][W2 dgrad pack][G2][G1][plane dots]   (G2 / G1: padded row layouts, row_layout.cuh);
@@ -975,14 +1059,26 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
     p.backoff = g_tuning[LPB_TUNE_WAIT_BACKOFF];
     p.prefetch = g_tuning[LPB_TUNE_B3A_PREFETCH];
     const int rows_alloc = (Wi1 + 2 + p.ncols + 7) & ~7;
-    const size_t smem = (size_t)2 * GB_KC * rows_alloc * 16 + (size_t)4 * GB_KC * 128 * 16 + 160;
+    size_t smem = (size_t)2 * GB_KC * rows_alloc * 16 + (size_t)4 * GB_KC * 128 * 16 + 160;
     LPB_REQUIRE(smem <= 225 * 1024, "head_bwd_bf16: layer-1 operands need %zu B shared memory", smem);
+    // TMA tensor store of d features when its staging slices (2 x 4 x 128 lanes x 4W bytes) still fit
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    p.tma_store = 0;
+    {
+      const size_t stage = (size_t)2 * 4 * 128 * 4 * W + 128;
+      if (g_tuning[LPB_TUNE_B3A_TMA_STORE] && smem + stage <= 225 * 1024 && (reinterpret_cast<uintptr_t>(dfeat) % 16) == 0 &&
+          make_dfeat_tensor_map(&tmap, dfeat, B, C4, H * W, 2 * W)) {
+        p.tma_store = 1;
+        smem += stage;
+      }
+    }
     int slots = sms / ntile1;
     if (slots < 1) slots = 1;
     if (slots > B) slots = B;
     auto run = [&](auto kern) -> int {
       LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<slots * ntile1, B3A_THREADS, smem, s>>>(p);
+      kern<<<slots * ntile1, B3A_THREADS, smem, s>>>(p, tmap);
       return LPB_OK;
     };
     int rc = LPB_ERR_UNSUPPORTED;

@@ -185,13 +185,15 @@ def test_round2_entry_points_validate_arguments_without_gpu():
         L.lpb_context_gather(None, 4, 64, 5, None, None),
         L.lpb_frames_normalize(None, 1, 8, 8, 8, 8, None, None, 0, 0, None, None),
         L.lpb_pack_predictions(None, None, 1, 2, None, 4, None, 0, None),
+        L.lpb_adam_step(1, None, None, None, None, None, None, None, 1e-3, None, 0.9, 0.999, 1e-8, 0.0, 0, None),
+        L.lpb_adam_step(17, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 1e-3, None, 0.9, 0.999, 1e-8, 0.0, 0, None),
         L.lpb_head_fwd_bf16(None, 1, 384, 16, 16, None, None, 17, None, None, 0, 1, None, None, None, None),
         L.lpb_head_bwd_bf16(None, None, None, None, None, None, None, 1, 384, 16, 16, None, 17, None, 0, None, None, None, None, None, None, None),
     ):
         assert rc == -1, (rc, L.lpb_last_error())
     assert L.lpb_context_gather(C.c_void_p(16), 4, 24, 5, C.c_void_p(16), None) == -1  # items must be 16-byte multiples
     assert L.lpb_set_tuning(99, 1) == -1 and L.lpb_get_tuning(99) == -1
-    for k in range(10):
+    for k in range(11):
         assert 0 <= L.lpb_get_tuning(k) <= 8
 
 

@@ -1103,7 +1103,7 @@ def test_kernel_variants_agree(lpb, dev):
         ((kp * gk).sum() * 1e-3 + (hm * hm).sum()).backward()
         return hm.detach().clone(), kp.detach().clone(), cf.detach().clone(), f.grad.float().clone(), list(head.upsampling_layers)[1].weight.grad.clone()
 
-    nkeys = 10
+    nkeys = 11
     saved = [lib.lpb_get_tuning(k) for k in range(nkeys)]
     try:
         for k in range(nkeys):
@@ -1120,3 +1120,58 @@ def test_kernel_variants_agree(lpb, dev):
     close(new[2], old[2], atol=1e-5, rtol=1e-4)   # confidences
     for a, b in zip(new[3:], old[3:]):
         assert float((a - b).abs().max()) <= 2e-3 * float(b.abs().max()) + 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("decoupled,wd", [(False, 0.0), (False, 0.01), (True, 0.05)])
+def test_fused_adam_matches_torch(lpb, dev, decoupled, wd):
+    """lpb_adam_step vs torch.optim.Adam / AdamW (the optimizers of configure_optimizers, models/base.py:458-477):
+    same trajectories over several steps, shared step counter, state keys of torch's own Adam."""
+    from lightning_pose_b200.optim import FusedAdam
+
+    g = torch.Generator().manual_seed(7)
+    shapes = [(512, 17, 3, 3), (17,), (17, 17, 3, 3), (17,)]
+    ours = [torch.nn.Parameter(torch.randn(s, generator=g).to(dev)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    opt = FusedAdam(ours, lr=3e-3, weight_decay=wd, decoupled_weight_decay=decoupled)
+    topt = (torch.optim.AdamW if decoupled else torch.optim.Adam)(ref, lr=3e-3, weight_decay=wd)
+    for it in range(6):
+        for p, q in zip(ours, ref):
+            gr = torch.randn(p.shape, generator=g).to(dev) * (1.0 + it)
+            p.grad, q.grad = gr.clone(), gr.clone()
+        opt.step()
+        topt.step()
+    for p, q in zip(ours, ref):
+        close(p, q, atol=1e-6, rtol=2e-5)
+    assert float(opt.state[ours[0]]["step"]) == 6.0 and opt.state[ours[1]]["step"] is opt.state[ours[0]]["step"]
+    close(opt.state[ours[2]]["exp_avg_sq"], topt.state[ref[2]]["exp_avg_sq"], atol=1e-9, rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_fused_adam_graph_replay(lpb, dev):
+    """The step counter lives on the device: a captured step replays as consecutive optimizer steps."""
+    from lightning_pose_b200.optim import FusedAdam
+
+    g = torch.Generator().manual_seed(3)
+    p = torch.nn.Parameter(torch.randn(1000, generator=g).to(dev))
+    q = torch.nn.Parameter(p.detach().clone())
+    gr = torch.randn(1000, generator=g).to(dev)
+    p.grad, q.grad = gr.clone(), gr.clone()
+    opt, topt = FusedAdam([p], lr=1e-2), torch.optim.Adam([q], lr=1e-2)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        opt.step()  # state allocation outside the capture
+    torch.cuda.current_stream(dev).wait_stream(side)
+    topt.step()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        opt.step()
+    topt.step()  # capture only records: ours = 1 eager + 3 replays, torch = 4 eager steps
+    for _ in range(3):
+        graph.replay()
+    for _ in range(2):
+        topt.step()
+    torch.cuda.synchronize(dev)
+    assert float(opt.state[p]["step"]) == 4.0
+    close(p, q, atol=1e-6, rtol=2e-5)
