@@ -24,6 +24,7 @@ int g_tuning[LPB_TUNE_COUNT] = {
     0,  // LPB_TUNE_DECODE_WARP_CTAS
     0,  // LPB_TUNE_DECODE_REVERSE
     1,  // LPB_TUNE_B3A_TMA_STORE
+    1,  // LPB_TUNE_WGRAD_SWAP
 };
 }
 extern "C" int lpb_set_tuning(int key, int value) {

@@ -690,6 +690,9 @@ struct WgParams {
   int Cin, Cout, ones_c;
   int stack;                  // 1: the four shifted copies of X are stacked along N in smem -> one MMA per K step
                               // (small channel counts: an N = 32 MMA costs as much operand fetch as an N = 128 one)
+  int swap;                   // 1: operands swapped: A = X (M = 128 channels, the shift is A's row offset), B = G (N = 80):
+                              // D_sh[channel][(cls, o)].  An MMA's time goes with N, so 80 columns instead of 128 (of which the
+                              // A = G form wastes the 48 lanes above the 80 real rows) is 0.63x the tensor time.  Needs kcx = 16.
   int smem_bytes;
 };
 
@@ -709,7 +712,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   const int ngroups = P.kcx_total / P.kcx;  // kcx_total may include K-chunks beyond the last group (ignored)
   const int grp = blockIdx.x % ngroups, slot = blockIdx.x / ngroups, nslot = gridDim.x / ngroups;
   const int nchunk = Hi / R, nunits = P.B * nchunk;  // R divides Hi (host)
-  const uint32_t ncols = 4 * N <= 32 ? 32 : (4 * N <= 64 ? 64 : (4 * N <= 128 ? 128 : (4 * N <= 256 ? 256 : 512)));
+  const uint32_t ncols = P.swap ? 512u : (4 * N <= 32 ? 32 : (4 * N <= 64 ? 64 : (4 * N <= 128 ? 128 : (4 * N <= 256 ? 256 : 512))));
 
   for (int i = tid; i < (P.smem_bytes - 64) / 16; i += WG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = tc::make_idesc_bf16_f32(128, P.stack ? 4 * N : N) | (1u << 15) | (1u << 16);  // both operands MN-major
+    const uint32_t idesc = tc::make_idesc_bf16_f32(128, P.swap ? GB_K : (P.stack ? 4 * N : N)) | (1u << 15) | (1u << 16);  // both operands MN-major
     const uint32_t g0 = smem_u32(Gs), x0 = smem_u32(Xs);
     int j = 0;
     for (int u = slot; u < nunits; u += nslot, ++j) {
@@ -767,7 +770,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           for (int sh = 0; sh < 4; ++sh) {
             const int shift_rows = (sh >> 1) * Pp + (sh & 1);
             const uint64_t xd = tc::make_smem_desc(x0 + s * x_bytes + (k16 * 16 + shift_rows) * 16, 128, XR * 16);
-            tc::umma_bf16(tmem_base + sh * N, gd, xd, idesc, (j | k16) != 0 ? 1u : 0u);
+            if (P.swap) tc::umma_bf16(tmem_base + sh * GB_K, xd, gd, idesc, (j | k16) != 0 ? 1u : 0u);
+            else tc::umma_bf16(tmem_base + sh * N, gd, xd, idesc, (j | k16) != 0 ? 1u : 0u);
           }
         }
         tc::umma_commit(&empty[s]);
@@ -776,6 +780,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     }
     if (lane == 0 && j > 0) tc::umma_commit(t_done);
     __syncwarp();
+  } else if (slot < nunits && P.swap) {
+    // swapped form: lane = channel, column = (cls, o) of shift sh
+    const int q = warp & 3;
+    mbar_wait(t_done, 0);
+    tc::fence_after_sync();
+    const int c = grp * N + 32 * q + lane;
+#pragma unroll 1
+    for (int sh = 0; sh < 4; ++sh) {
+      const int dm = sh >> 1, dn = sh & 1;
+#pragma unroll
+      for (int k0 = 0; k0 < GB_K; k0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + sh * GB_K + k0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int k = k0 + i, cls = k / GB_CLS, o = k - cls * GB_CLS, py = cls >> 1, px = cls & 1;  // compile-time
+          const bool valid = o < P.Cout && !(py == 0 && dm == 1) && !(px == 0 && dn == 1) && c < P.Cin;
+          const int ky = py == 0 ? 1 : (dm ? 0 : 2), kx = px == 0 ? 1 : (dn ? 0 : 2);
+          if (valid) atomicAdd(P.dW + ((size_t)c * P.Cout + o) * 9 + ky * 3 + kx, v[i]);
+        }
+      }
+    }
   } else if (slot < nunits) {
     const int q = warp & 3;
     if (32 * q < GB_K) {
@@ -834,6 +860,7 @@ static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, float* d
   p.KR = (R * (Wi + 1) + 15) & ~15;
   p.XR = stack ? p.KR : ((p.KR + Wi + 2 + 7) & ~7);
   p.stack = stack;
+  p.swap = (!stack && kcx == 16 && g_tuning[LPB_TUNE_WGRAD_SWAP]) ? 1 : 0;
   p.kcx = kcx;
   p.kcx_total = kcx_total;
   p.Cin = Cin;

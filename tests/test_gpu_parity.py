@@ -1103,7 +1103,7 @@ def test_kernel_variants_agree(lpb, dev):
         ((kp * gk).sum() * 1e-3 + (hm * hm).sum()).backward()
         return hm.detach().clone(), kp.detach().clone(), cf.detach().clone(), f.grad.float().clone(), list(head.upsampling_layers)[1].weight.grad.clone()
 
-    nkeys = 11
+    nkeys = 12
     saved = [lib.lpb_get_tuning(k) for k in range(nkeys)]
     try:
         for k in range(nkeys):
