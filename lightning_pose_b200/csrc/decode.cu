@@ -25,7 +25,7 @@ namespace lpb {
 constexpr int DEC_THREADS = 256;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr float DEC_CUT = 40.0f;  // dropped pixels have weight < exp(-40) = 4e-18 of the peak pixel
-constexpr int DEC_MAX_PARTS = 8;  // CTAs a queued (dense) plane can be split over
+constexpr int DEC_MAX_PARTS = 16;  // CTAs a queued (dense) plane can be split over
 constexpr int DEC_CONF_R = 2;     // floor(1.25 * 2), lightning_pose/data/heatmaps.py:111
 
 template <int DS>
@@ -78,6 +78,35 @@ __device__ float eval_point(const float* tile, int pitch, int padl, const float*
     acc = fmaf(__ldg(tabH + i * W + t), r, acc);
   }
   return acc;
+}
+
+// exact field values at up to F*F fine pixels (scratch: npts * W floats), spread over the CTA: thread (pt, t) evaluates one horizontal tap row, the W rows
+// of a point meet in shared memory.  (One thread per point walked W x W dependent table loads: ~3 us per call, twice per
+// plane -- a fifth of a queued plane's latency.)  Returns the value of point `tid` for tid < npts; contains a __syncthreads().
+template <int DS, class CoordFn>
+__device__ __forceinline__ float eval_points_cta(const float* tile, int pitch, int padl, const float* __restrict__ tabH,
+                                                 const float* __restrict__ tabW, int npts, CoordFn coord, float* scratch, int tid) {
+  constexpr int F = 1 << DS, R = DS + 2, W = 2 * R + 1;
+  for (int idx = tid; idx < npts * W; idx += DEC_THREADS) {
+    const int pt = idx / W, t = idx - pt * W;
+    int i = 0, j = 0;
+    float val = 0.f;
+    if (coord(pt, i, j)) {
+      const float* row = tile + (i / F + t) * pitch + padl + (j / F - R);
+      float r = 0.f;
+#pragma unroll
+      for (int u = 0; u < W; ++u) r = fmaf(__ldg(tabW + j * W + u), row[u], r);
+      val = __ldg(tabH + i * W + t) * r;
+    }
+    scratch[idx] = val;
+  }
+  __syncthreads();
+  float out = 0.f;
+  if (tid < npts) {
+#pragma unroll
+    for (int t = 0; t < W; ++t) out += scratch[tid * W + t];
+  }
+  return out;
 }
 
 // one coarse row of the vertical pass: F fine values from the W-row window `t`, as F/2 packed pairs of phases
@@ -204,7 +233,8 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
   float* tile = reinterpret_cast<float*>(smem_raw);  // (h + 2R) x pitch; logical (a,b) at [(a+R)*pitch + padl + b]
   float* red = tile + (h + 2 * R) * pitch;           // 64 floats of reduction scratch
   int* redi = reinterpret_cast<int*>(red + 64);      // 112 ints
-  uint64_t* bar = reinterpret_cast<uint64_t*>(redi + 112);
+  float* evs = reinterpret_cast<float*>(redi + 112);  // 704 floats (F*F*W at ds = 3): tap rows of eval_points_cta
+  uint64_t* bar = reinterpret_cast<uint64_t*>(evs + 704);
   unsigned* smask = reinterpret_cast<unsigned*>(redi + 48);  // [32] per-strip bitmask of active row chunks
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -323,8 +353,12 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
   }
 
   // ---- lower bound on the field maximum: exact values in the F x F block of the coarse arg max --
-  float lb = -3.0e38f;
-  if (tid < F * F) lb = eval_point<DS>(tile, pitch, padl, P.tabH, P.tabW, besta * F + tid / F, bestb * F + tid % F);
+  float lb = eval_points_cta<DS>(tile, pitch, padl, P.tabH, P.tabW, F * F, [&](int pt, int& i, int& j) {
+    i = besta * F + pt / F;
+    j = bestb * F + pt % F;
+    return true;
+  }, evs, tid);
+  if (tid >= F * F) lb = -3.0e38f;
   lb = warp_max(lb);
   if (lane == 0) red[8 + warp] = lb;
   __syncthreads();
@@ -406,13 +440,17 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
     q1 = min((st + (len < 0 ? 32 - st : len)) * CH, h);
     m = (len < 0 || st + len >= 32) ? 0u : (m & ~(((1u << len) - 1u) << st));
   };
+  // rows per work item: at most 48 (a full-height strip is split in two) when planes fill the grid; the few planes of
+  // queue mode are cut finer, so that all warps of all the CTAs a plane is split over have an item (latency, not throughput)
+  const int per_strip = max(1, (NP * DEC_WARPS) / nstrips);  // row segments a strip can have with one item per warp
+  const int seg_cap = P.queue ? min(48, max(8, (h + per_strip - 1) / per_strip)) : 48;
   int nmine = 0;
   {
     unsigned m = my_mask;
     while (m) {
       int q0, q1;
       next_run(m, q0, q1);
-      nmine += (q1 - q0 > 48) ? 2 : 1;
+      nmine += (q1 - q0 + seg_cap - 1) / seg_cap;
     }
   }
   int istart = nmine;  // exclusive prefix sum over lanes
@@ -438,7 +476,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
     while (rm) {
       int q0, q1;
       next_run(rm, q0, q1);
-      const int ns = (q1 - q0 > 48) ? 2 : 1;
+      const int ns = (q1 - q0 + seg_cap - 1) / seg_cap;
       if (k < ns) {
         const int seglen = (q1 - q0 + ns - 1) / ns;
         r0 = q0 + k * seglen;
@@ -531,13 +569,15 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
   // ---- confidence: softmax mass of the (2r+1)^2 window around (trunc y, trunc x) -----------------
   constexpr int CW = 2 * DEC_CONF_R + 1;
   float cw = 0.f;
-  if (tid < CW * CW) {
-    const int i = (int)yhat + tid / CW - DEC_CONF_R;
-    const int j = (int)xhat + tid % CW - DEC_CONF_R;
-    if (i >= 0 && i < h * F && j >= 0 && j < w * F) {
-      const float v = eval_point<DS>(tile, pitch, padl, P.tabH, P.tabW, i, j);
-      cw = fast_exp2((v - M) * c) / S;
-    }
+  {
+    auto wcoord = [&](int pt, int& i, int& j) {
+      i = (int)yhat + pt / CW - DEC_CONF_R;
+      j = (int)xhat + pt % CW - DEC_CONF_R;
+      return i >= 0 && i < h * F && j >= 0 && j < w * F;
+    };
+    const float v = eval_points_cta<DS>(tile, pitch, padl, P.tabH, P.tabW, CW * CW, wcoord, evs, tid);
+    int i, j;
+    if (tid < CW * CW && wcoord(tid, i, j)) cw = fast_exp2((v - M) * c) / S;
   }
   cw = warp_sum(cw);  // CW*CW = 25 <= 32: all in warp 0
   if (tid == 0) {
@@ -1311,7 +1351,7 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
     for (int t = 0; t < G::W; ++t) P.phase[p][t] = th->host.phase[(size_t)p * G::W + t];
   for (int q = 0; q < G::F / 2; ++q)
     for (int t = 0; t < G::W; ++t) P.phase2[q][t] = make_float2(P.phase[2 * q][t], P.phase[2 * q + 1][t]);
-  const size_t smem = ((size_t)(h + 2 * G::R) * P.pitch + 64 + 112) * sizeof(float) + 16;
+  const size_t smem = ((size_t)(h + 2 * G::R) * P.pitch + 64 + 112 + 704) * sizeof(float) + 16;
   int dev = 0, max_smem = 0;
   LPB_CUDA(cudaGetDevice(&dev));
   LPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
