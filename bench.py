@@ -428,6 +428,16 @@ def run_ours(args):
 
     step_fn = lambda: hp.step(feats)
     graphed = False
+    if args.profile_step:
+        # for a run under ncu: W + K eager steps and nothing else (no stage breakdown, no e2e leg) -- not a bench line
+        for _ in range(args.warmup + args.steps):
+            step_fn()
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(json.dumps({"profile_step": True, "steps": args.steps, "warmup": args.warmup}))
+        if dist:
+            _teardown(dist, rank, world)
+        return
     if not args.no_graph:
         try:
             step_fn = GraphedStep(hp, feats)
@@ -650,6 +660,7 @@ def main():
     ap.add_argument("--no-flat", action="store_true", help="skip the secondary fresh-init (flat heatmap) regime")
     ap.add_argument("--fwd-only", action="store_true", help="time the forward pass only (default: full training step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="profiling aid: run W + K eager steps and exit (use under ncu; prints no bench line)")
     ap.add_argument("--serial-chains", action="store_true", help="run the labeled and the unlabeled chain on one stream (default: two streams, forked and joined inside the step)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--ddp-payload-mb", type=float, default=BACKBONE_PARAMS * 4 / 1e6,

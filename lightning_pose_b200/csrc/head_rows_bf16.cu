@@ -411,8 +411,11 @@ int launch_convt_rows(ConvtRowsParams p, int sms, cudaStream_t s) {
   const long long per_band = (long long)p.B * nbands;
   if (p.mode == CONVT_ROWS_MID) return run(convt_rows_kernel<CONVT_ROWS_MID, 0, false>, per_band);
   if (p.mode == CONVT_ROWS_PLANES) return k17 ? run(convt_rows_kernel<CONVT_ROWS_PLANES, 17, false>, per_band) : run(convt_rows_kernel<CONVT_ROWS_PLANES, 0, false>, per_band);
-  if (v2 && p.partials && g_tuning[LPB_TUNE_SOFTMAX_SPLIT]) {
-    // split softmax: partial statistics per (frame, band), then the normalising pass -- both parallel over bands
+  // split softmax (statistics launch + normalising launch, both parallel over (frame, band)) when one CTA per frame would
+  // leave SMs idle; with >= one frame per resident CTA the single two-pass kernel is faster (768-frame step: 1.768 vs
+  // 1.802 ms), because a frame's second pass re-reads operands its first pass left in L2.  Key value 2 forces the split.
+  const int split_key = g_tuning[LPB_TUNE_SOFTMAX_SPLIT];
+  if (v2 && p.partials && (split_key == 2 || (split_key == 1 && p.B < 2 * sms))) {
     int rc = k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P0, 17, true>, per_band) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P0, 0, true>, per_band);
     if (rc != LPB_OK) return rc;
     return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P1, 17, true>, per_band) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P1, 0, true>, per_band);
