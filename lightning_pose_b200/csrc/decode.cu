@@ -293,7 +293,10 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
   //  possibly partial, group is safe to read)
   const int w4 = (w + 3) >> 2;
   const int band = (h + DEC_WARPS - 1) / DEC_WARPS;
-  const int ab0 = warp * band, ab1 = min(h, ab0 + band);
+  // Queue mode skips both scans: the planes that arrive here are the ones pruning cannot help (diffuse / multi-modal /
+  // NaN), and every CTA a plane is split over would repeat them -- they were half of the queued kernel's instructions.
+  // The online softmax starts from a low finite maximum instead of the arg-max bound and the whole plane is evaluated.
+  const int ab0 = warp * band, ab1 = P.queue ? ab0 : min(h, ab0 + band);
   float best = -1.f;
   int bpos = 0;
   if (w4 <= 32) {  // common case: one 16-byte group per lane and row, no inner loop
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
   }
 
   // ---- lower bound on the field maximum: exact values in the F x F block of the coarse arg max --
-  float lb = eval_points_cta<DS>(tile, pitch, padl, P.tabH, P.tabW, F * F, [&](int pt, int& i, int& j) {
+  float lb = eval_points_cta<DS>(tile, pitch, padl, P.tabH, P.tabW, P.queue ? 0 : F * F, [&](int pt, int& i, int& j) {
     i = besta * F + pt / F;
     j = bestb * F + pt % F;
     return true;
@@ -365,6 +368,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
   float mlb = red[8];
 #pragma unroll
   for (int k = 1; k < DEC_WARPS; ++k) mlb = fmaxf(mlb, red[8 + k]);
+  if (P.queue) mlb = -1.0e30f;
 
   // ---- scan 2: candidates (|h| >= theta) -> per-strip candidate row range + hull ---------------------
   // a fine pixel can carry weight > exp(-CUT) only if a candidate lies within R coarse samples of it
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DS == 3 ? 2 : 4) decode_fwd_kerne
   const int nstrips = (w * F + 31) >> 5;  // <= 32 (checked on the host)
   int amin = h, amax = -1, bmin = w, bmax = -1;
   const int CH = max(4, (h + 31) >> 5);  // coarse rows per chunk (<= 32 chunks per plane)
-  if (bandmax >= theta) {
+  if (!P.queue && bandmax >= theta) {
     unsigned cmask = 0u;  // lane s owns strip s: chunks whose rows lie within R of a candidate
     const int nit = (w4 + 31) >> 5;
     unsigned long long gmask = 0;  // 4-column groups that can reach strip `lane`
