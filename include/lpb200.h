@@ -51,8 +51,9 @@ const char* lpb_build_arch(void);     /* "sm_100a" */
 #define LPB_TUNE_DECODE_WARP_CTAS 8     /* > 0: resident CTAs per SM of the warp-per-plane decode are capped (fewer planes in flight than L2 holds); 0: no cap */
 #define LPB_TUNE_DECODE_REVERSE 9       /* 1: the decode walks the planes last-to-first (the producer's most recent writes are still in L2) */
 #define LPB_TUNE_B3A_TMA_STORE 10       /* 1 (default): b3a stages d features in shared memory and a TMA tensor store scatters them to NCHW; 0: direct 16-byte stores */
-#define LPB_TUNE_WGRAD_SWAP 11          /* 1 (default): layer-1 weight gradient with A = features (M = 128 channels), B = gradient rows (N = 80) */
-#define LPB_TUNE_COUNT 12
+#define LPB_TUNE_WGRAD_SWAP 11          /* layer-1 weight gradient: 1: A = features (M = 128 channels), B = gradient rows (N = 80); 2 (default): the same with the gradient rows staged twice, one row apart, side by side along N (N = 160: two shifts per MMA); 0: A = gradient rows */
+#define LPB_TUNE_G2_PATCH 12            /* 1 (default): decode windows enter the gradient rows in a patch pass (one warp per plane) after a look-up-free streaming pass; 0: look-ups fused into the streaming pass */
+#define LPB_TUNE_COUNT 13
 int lpb_set_tuning(int key, int value);
 int lpb_get_tuning(int key);
 

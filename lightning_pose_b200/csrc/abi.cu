@@ -24,7 +24,8 @@ int g_tuning[LPB_TUNE_COUNT] = {
     0,  // LPB_TUNE_DECODE_WARP_CTAS
     0,  // LPB_TUNE_DECODE_REVERSE
     1,  // LPB_TUNE_B3A_TMA_STORE
-    1,  // LPB_TUNE_WGRAD_SWAP
+    2,  // LPB_TUNE_WGRAD_SWAP (2: swapped + two shifts per MMA along N)
+    1,  // LPB_TUNE_G2_PATCH
 };
 }
 extern "C" int lpb_set_tuning(int key, int value) {

@@ -202,8 +202,10 @@ __global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B
   }
 }
 
-// Fallback for narrow images (a CTA's 128 pixels span more than G2B_MROWS rows): one warp per plane re-evaluates
-// the pixels under its window and overwrites those bf16 entries after a window-less g2_build pass.
+// Window patch: after a window-less g2_build pass (which already folds each window's dot into the softmax term), one warp
+// per plane re-evaluates the <= 32 x 32 pixels under its window and overwrites those bf16 entries.  The streaming pass then
+// runs at the DRAM roofline with no look-ups in it, and this pass touches 4 KB of probabilities per plane (a ninth of it).
+// Window rows go eight at a time: 8 independent window loads, then 8 independent probability loads per lane.
 template <bool HAS_G, bool HAS_P>
 __global__ void __launch_bounds__(128) g2_patch_kernel(G2Src S, long long n_planes, int C, int Hi, int Wi,
                                                       __nv_bfloat16* __restrict__ G, RowLayout L) {
@@ -217,15 +219,45 @@ __global__ void __launch_bounds__(128) g2_patch_kernel(G2Src S, long long n_plan
   float dot = 0.f;
   if (HAS_P) dot = (mt.z == 1 ? __int_as_float(mt.w) : 0.f) + (S.ddot ? S.ddot[plane] : 0.f);
   const size_t poff = (size_t)plane * Ho * Wo;
-  const bool win = mt.z == 1;
-  const int n_it = win ? 1024 : Ho * Wo;
-  for (int i = lane; i < n_it; i += 32) {
-    const float gw = __ldg((win ? S.win + (size_t)plane * 1024 : S.gov + poff) + i);
-    const int y = win ? mt.x + (i >> 5) : i / Wo, x = win ? mt.y + (i & 31) : i % Wo;
-    if (gw == 0.f || (unsigned)y >= (unsigned)Ho || (unsigned)x >= (unsigned)Wo) continue;
+  if (mt.z == 1) {
+    const float* wp = S.win + (size_t)plane * 1024 + lane;
+    const int x = mt.y + lane;
+    const bool xin = (unsigned)x < (unsigned)Wo;
+    // k = cls * 20 + o with cls = 2 (y & 1) + (x & 1): the K-chunk / element of this lane for even and odd rows
+    const int kx = (x & 1) * GB_CLS + o;
+    __nv_bfloat16* gcol = G + ((size_t)b * GB_KC * L.rows + L.lead + (x >> 1)) * 8;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+      float gw[8], pv[8], go[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gw[k] = __ldg(wp + (r0 + k) * 32);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int y = mt.x + r0 + k;
+        const bool ok = xin && gw[k] != 0.f && (unsigned)y < (unsigned)Ho;
+        pv[k] = (HAS_P && ok) ? __ldg(S.probs + poff + (size_t)y * Wo + x) : 0.f;
+        go[k] = (HAS_G && ok) ? __ldg(S.g_out + poff + (size_t)y * Wo + x) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int y = mt.x + r0 + k;
+        if (!(xin && gw[k] != 0.f && (unsigned)y < (unsigned)Ho)) continue;
+        float g = gw[k] + go[k];
+        if (HAS_P) g = pv[k] * (g - dot);
+        const int kk = kx + 2 * GB_CLS * (y & 1);
+        gcol[((size_t)(kk >> 3) * L.rows + (size_t)(y >> 1) * L.Pp) * 8 + (kk & 7)] = __float2bfloat16_rn(g);
+      }
+    }
+    return;
+  }
+  // flag 2: the plane's decode gradient is dense (gov); rare
+  for (int i = lane; i < Ho * Wo; i += 32) {
+    const float gw = __ldg(S.gov + poff + i);
+    const int y = i / Wo, x = i % Wo;
+    if (gw == 0.f) continue;
     float g = gw;
-    if (HAS_G) g += __ldg(S.g_out + poff + (size_t)y * Wo + x);
-    if (HAS_P) g = __ldg(S.probs + poff + (size_t)y * Wo + x) * (g - dot);
+    if (HAS_G) g += __ldg(S.g_out + poff + i);
+    if (HAS_P) g = __ldg(S.probs + poff + i) * (g - dot);
     const int k = (((y & 1) << 1) | (x & 1)) * GB_CLS + o;
     G[(((size_t)b * GB_KC + (k >> 3)) * L.rows + L.lead + (size_t)(y >> 1) * L.Pp + (x >> 1)) * 8 + (k & 7)] = __float2bfloat16_rn(g);
   }
@@ -235,7 +267,7 @@ template <bool HAS_G, bool HAS_P>
 static void launch_g2_build(const G2Src& S, int B, int C, int Hi, int Wi, __nv_bfloat16* G, RowLayout L, cudaStream_t s) {
   const int cpf = (Hi * Wi + G2B_THREADS - 1) / G2B_THREADS;
   const bool fits = (G2B_THREADS + Wi - 1) / Wi + 1 <= G2B_MROWS;  // rows m a CTA's pixels can span
-  if (S.win && fits) {
+  if (S.win && fits && !g_tuning[LPB_TUNE_G2_PATCH]) {
     g2_build_kernel<HAS_G, HAS_P, true><<<(unsigned)(B * cpf), G2B_THREADS, 0, s>>>(S, B, C, Hi, Wi, cpf, G, L);
     return;
   }
@@ -693,13 +725,18 @@ struct WgParams {
   int swap;                   // 1: operands swapped: A = X (M = 128 channels, the shift is A's row offset), B = G (N = 80):
                               // D_sh[channel][(cls, o)].  An MMA's time goes with N, so 80 columns instead of 128 (of which the
                               // A = G form wastes the 48 lanes above the 80 real rows) is 0.63x the tensor time.  Needs kcx = 16.
+                              // 2: swapped AND the gradient rows staged twice, the second copy one raster row late, side by side
+                              // along N: B = [G[r] | G[r-1]] (N = 160), so ONE MMA covers the shifts (dm, 0) and (dm, 1) --
+                              // sum_r X[r+s]G[r-1] = sum_r X[r+s+1]G[r] because the rows that enter / leave the sum are pad
+                              // columns (zero).  Below N ~ 144 an MMA's time is its operand fetch whatever N is: half the MMAs.
   int smem_bytes;
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Wi = P.Wi, Hi = P.Hi, Pp = Wi + 1, R = P.R, KR = P.KR, XR = P.XR;
-  const int g_bytes = GB_KC * KR * 16, x_bytes = (P.stack ? 4 : 1) * P.kcx * XR * 16;
+  const int gcp = P.swap == 2 ? 2 : 1;  // copies of the gradient rows per stage
+  const int g_bytes = gcp * GB_KC * KR * 16, x_bytes = (P.stack ? 4 : 1) * P.kcx * XR * 16;
   unsigned char* Gs = smem;
   unsigned char* Xs = smem + 2 * g_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P.smem_bytes - 64);
@@ -738,12 +775,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       // one copy per K-chunk: R image rows of G; R + 1 rows of X (the row below is the shifts' halo)
       const uint32_t gbytes = (uint32_t)(R * Pp * 16), xbytes = P.stack ? gbytes : (uint32_t)((R + 1) * Pp * 16);
       const int nx = (P.stack ? 4 : 1) * P.kcx;  // X copies: stacked mode loads each K-chunk once per shift, pre-shifted
-      if (lane == 0) mbar_expect_tx(&full[s], GB_KC * gbytes + nx * xbytes);
+      if (lane == 0) mbar_expect_tx(&full[s], gcp * GB_KC * gbytes + nx * xbytes);
       __syncwarp();
       const size_t row0 = (size_t)P.L.lead + (size_t)y0 * Pp;
-      if (lane < GB_KC)
-        bulk_g2s(Gs + (size_t)s * g_bytes + (size_t)lane * KR * 16, P.G + (((size_t)b * GB_KC + lane) * P.L.rows + row0) * 8, gbytes,
+      if (lane < gcp * GB_KC) {
+        const int cp = lane / GB_KC, kc = lane - cp * GB_KC;  // copy 1 starts one row early: its smem row r holds G[r - 1]
+        bulk_g2s(Gs + (size_t)s * g_bytes + (size_t)lane * KR * 16, P.G + (((size_t)b * GB_KC + kc) * P.L.rows + row0 - cp) * 8, gbytes,
                  &full[s]);
+      }
       if (lane < nx) {
         const int sh = lane / P.kcx, kc = lane - sh * P.kcx;
         const size_t shift_rows = P.stack ? (size_t)((sh >> 1) * Pp + (sh & 1)) : 0;
@@ -752,7 +791,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = tc::make_idesc_bf16_f32(128, P.swap ? GB_K : (P.stack ? 4 * N : N)) | (1u << 15) | (1u << 16);  // both operands MN-major
+    const uint32_t idesc = tc::make_idesc_bf16_f32(128, P.swap ? gcp * GB_K : (P.stack ? 4 * N : N)) | (1u << 15) | (1u << 16);  // both operands MN-major
     const uint32_t g0 = smem_u32(Gs), x0 = smem_u32(Xs);
     int j = 0;
     for (int u = slot; u < nunits; u += nslot, ++j) {
@@ -764,6 +803,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           const uint64_t gd = tc::make_smem_desc(g0 + s * g_bytes + k16 * 256, 128, KR * 16);
           if (P.stack) {
             tc::umma_bf16(tmem_base, gd, tc::make_smem_desc(x0 + s * x_bytes + k16 * 256, 128, XR * 16), idesc, (j | k16) != 0 ? 1u : 0u);
+            continue;
+          }
+          if (P.swap == 2) {  // columns [160 dm, 160 dm + 80) = shift (dm, 0), the next 80 = shift (dm, 1): the same map as swap == 1
+#pragma unroll
+            for (int dm = 0; dm < 2; ++dm)
+              tc::umma_bf16(tmem_base + dm * 2 * GB_K, tc::make_smem_desc(x0 + s * x_bytes + (k16 * 16 + dm * Pp) * 16, 128, XR * 16), gd, idesc,
+                            (j | k16) != 0 ? 1u : 0u);
             continue;
           }
 #pragma unroll
@@ -837,11 +883,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
 static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, float* dW, float* dbias, int B, int Hi, int Wi,
                         int kcx, int kcx_total, int Cin, int Cout, int ones_c, int stack, int sms, cudaStream_t s) {
   // image rows per unit: the largest divisor of Hi (<= 8) whose two stages fit in shared memory
+  const int swap = (!stack && kcx == 16) ? g_tuning[LPB_TUNE_WGRAD_SWAP] : 0;
+  const int gcp = swap == 2 ? 2 : 1;
   int R = 0;
   for (int r = Hi < 8 ? Hi : 8; r >= 1; --r) {
     if (Hi % r) continue;
     const int kr = (r * (Wi + 1) + 15) & ~15, xr = stack ? kr : ((kr + Wi + 2 + 7) & ~7);
-    if ((size_t)2 * GB_KC * kr * 16 + (size_t)2 * (stack ? 4 : 1) * kcx * xr * 16 + 64 <= 225 * 1024) {
+    if ((size_t)2 * gcp * GB_KC * kr * 16 + (size_t)2 * (stack ? 4 : 1) * kcx * xr * 16 + 64 <= 225 * 1024) {
       R = r;
       break;
     }
@@ -860,13 +908,13 @@ static int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* G, float* d
   p.KR = (R * (Wi + 1) + 15) & ~15;
   p.XR = stack ? p.KR : ((p.KR + Wi + 2 + 7) & ~7);
   p.stack = stack;
-  p.swap = (!stack && kcx == 16 && g_tuning[LPB_TUNE_WGRAD_SWAP]) ? 1 : 0;
+  p.swap = swap;
   p.kcx = kcx;
   p.kcx_total = kcx_total;
   p.Cin = Cin;
   p.Cout = Cout;
   p.ones_c = ones_c;
-  const size_t gb = (size_t)GB_KC * p.KR * 16, xb = (size_t)(stack ? 4 : 1) * kcx * p.XR * 16;
+  const size_t gb = (size_t)gcp * GB_KC * p.KR * 16, xb = (size_t)(stack ? 4 : 1) * kcx * p.XR * 16;
   size_t body = 2 * gb + 2 * xb;
   const size_t phantom = gb + (size_t)16 * p.KR * 16;  // address range the 16-chunk A descriptor of stage 1 spans
   if (body < phantom) body = phantom;

@@ -1103,8 +1103,9 @@ def test_kernel_variants_agree(lpb, dev):
         ((kp * gk).sum() * 1e-3 + (hm * hm).sum()).backward()
         return hm.detach().clone(), kp.detach().clone(), cf.detach().clone(), f.grad.float().clone(), list(head.upsampling_layers)[1].weight.grad.clone()
 
-    nkeys = 12
+    nkeys = 13
     saved = [lib.lpb_get_tuning(k) for k in range(nkeys)]
+    cur = run()  # the defaults (some keys have more than two settings, e.g. 11 = 2)
     try:
         for k in range(nkeys):
             lib.lpb_set_tuning(k, 3 if k == 8 else 1)  # key 8 is a count (resident decode CTAs per SM), the others are switches
@@ -1118,8 +1119,10 @@ def test_kernel_variants_agree(lpb, dev):
     close(new[0], old[0], atol=1e-9, rtol=2e-5)   # heatmaps
     close(new[1], old[1], atol=2e-3, rtol=1e-5)   # keypoints (T = 1000 amplifies the last ulp of a heatmap)
     close(new[2], old[2], atol=1e-5, rtol=1e-4)   # confidences
-    for a, b in zip(new[3:], old[3:]):
+    for a, b in zip(new[3:] + cur[3:], old[3:] + old[3:]):
         assert float((a - b).abs().max()) <= 2e-3 * float(b.abs().max()) + 1e-12
+    close(cur[0], old[0], atol=1e-9, rtol=2e-5)
+    close(cur[1], old[1], atol=2e-3, rtol=1e-5)
 
 
 @pytest.mark.gpu
