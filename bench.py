@@ -430,11 +430,34 @@ def run_ours(args):
     graphed = False
     if args.profile_step:
         # for a run under ncu: W + K eager steps and nothing else (no stage breakdown, no e2e leg) -- not a bench line
-        for _ in range(args.warmup + args.steps):
+        for _ in range(args.warmup):
             step_fn()
         torch.cuda.synchronize()
+        kin = None
+        if args.kineto:
+            # in-situ kernel durations (CUPTI activity records: no replay, no cache flush, no serialisation beyond the
+            # stream order) -- the complement of the ncu launch list, whose per-launch times are cold-cache
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(args.steps):
+                    step_fn()
+                torch.cuda.synchronize()
+            kin = [{"kernel": e.key[:70], "calls": e.count, "us_per_step": round(e.device_time_total / args.steps, 2),
+                    "us_per_call": round(e.device_time_total / max(e.count, 1), 2)}
+                   for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total) if e.device_time_total > 0]
+            try:  # the last step's launches in time order (name, us)
+                from torch.autograd import DeviceType
+                evs = sorted([e for e in prof.events() if e.device_type == DeviceType.CUDA], key=lambda e: e.time_range.start)
+                per = len(evs) // args.steps
+                kin = {"by_kernel": kin, "last_step": [[e.name[:60], round(e.time_range.elapsed_us(), 2)] for e in evs[len(evs) - per:]]}
+            except Exception as exc:  # noqa: BLE001
+                kin = {"by_kernel": kin, "last_step_error": repr(exc)}
+        else:
+            for _ in range(args.steps):
+                step_fn()
+            torch.cuda.synchronize()
         if rank == 0:
-            print(json.dumps({"profile_step": True, "steps": args.steps, "warmup": args.warmup}))
+            print(json.dumps({"profile_step": True, "steps": args.steps, "warmup": args.warmup, "kineto": kin}))
         if dist:
             _teardown(dist, rank, world)
         return
@@ -661,6 +684,7 @@ def main():
     ap.add_argument("--fwd-only", action="store_true", help="time the forward pass only (default: full training step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true", help="profiling aid: run W + K eager steps and exit (use under ncu; prints no bench line)")
+    ap.add_argument("--kineto", action="store_true", help="with --profile-step: per-kernel device times of the timed steps from torch.profiler (CUPTI), in situ")
     ap.add_argument("--serial-chains", action="store_true", help="run the labeled and the unlabeled chain on one stream (default: two streams, forked and joined inside the step)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--ddp-payload-mb", type=float, default=BACKBONE_PARAMS * 4 / 1e6,

@@ -373,6 +373,7 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
               const int shift_rows = (sh >> 1) * Pp + (sh & 1);
 #pragma unroll
               for (int k16 = 0; k16 < GB_K / 16; ++k16) {
+                if (k16 < sh) continue;  // all-zero weight chunks of this shift (see b3a)
                 const uint32_t aa = a0 + (2 * k16) * lbo_a + (LEAD + t * 128 - shift_rows) * 16;
                 const uint32_t bb = b0 + (sh * GB_KC + 2 * k16) * lbo_b;
                 tc::umma_bf16(tmem_base + t * 32, tc::make_smem_desc(aa, lbo_a, 128), tc::make_smem_desc(bb, lbo_b, 128), idesc,
@@ -562,6 +563,10 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
             const int shift_rows = (sh >> 1) * Pp + (sh & 1);
 #pragma unroll
             for (int k16 = 0; k16 < GB_K / 16; ++k16) {
+              // K = (cls, o), cls = 2 py + px at stride 20: shift (dm, dn) has no tap for classes with py < dm or px < dn,
+              // so its packed weights are zero for k < 20 (dn), k < 40 (dm), k < 60 (both): the 16-wide chunks k16 < sh
+              // are all-zero and their MMAs are skipped (14 of 20 remain)
+              if (k16 < sh) continue;
               const uint32_t ww = w0 + ((sh * GB_KC + 2 * k16) * 128) * 16;
               const uint32_t gg = g0 + (2 * k16) * lbo_g + (LEAD - shift_rows) * 16;
               const uint64_t wd = tc::make_smem_desc(ww, lbo_w, 128);
