@@ -210,56 +210,79 @@ template <bool HAS_G, bool HAS_P>
 __global__ void __launch_bounds__(128) g2_patch_kernel(G2Src S, long long n_planes, int C, int Hi, int Wi,
                                                       __nv_bfloat16* __restrict__ G, RowLayout L) {
   const int lane = threadIdx.x & 31;
-  const long long plane = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (plane >= n_planes) return;
-  const int4 mt = reinterpret_cast<const int4*>(S.meta)[plane];
-  if (mt.z == 0) return;
   const int Wo = 2 * Wi, Ho = 2 * Hi;
-  const int b = (int)(plane / C), o = (int)(plane - (long long)b * C);
-  float dot = 0.f;
-  if (HAS_P) dot = (mt.z == 1 ? __int_as_float(mt.w) : 0.f) + (S.ddot ? S.ddot[plane] : 0.f);
-  const size_t poff = (size_t)plane * Ho * Wo;
-  if (mt.z == 1) {
-    const float* wp = S.win + (size_t)plane * 1024 + lane;
-    const int x = mt.y + lane;
-    const bool xin = (unsigned)x < (unsigned)Wo;
-    // k = cls * 20 + o with cls = 2 (y & 1) + (x & 1): the K-chunk / element of this lane for even and odd rows
-    const int kx = (x & 1) * GB_CLS + o;
-    __nv_bfloat16* gcol = G + ((size_t)b * GB_KC * L.rows + L.lead + (x >> 1)) * 8;
+  {
+    const long long plane = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    int4 mt = make_int4(0, 0, 0, 0);
+    if (plane < n_planes) mt = reinterpret_cast<const int4*>(S.meta)[plane];
+    if (mt.z == 1) {
+      const int b = (int)(plane / C), o = (int)(plane - (long long)b * C);
+      float dot = 0.f;
+      if (HAS_P) dot = __int_as_float(mt.w) + (S.ddot ? S.ddot[plane] : 0.f);
+      const size_t poff = (size_t)plane * Ho * Wo;
+      const float* wp = S.win + (size_t)plane * 1024 + lane;
+      const int x = mt.y + lane;
+      const bool xin = (unsigned)x < (unsigned)Wo;
+      // k = cls * 20 + o with cls = 2 (y & 1) + (x & 1): the K-chunk / element of this lane for even and odd rows
+      const int kx = (x & 1) * GB_CLS + o;
+      __nv_bfloat16* gcol = G + ((size_t)b * GB_KC * L.rows + L.lead + (x >> 1)) * 8;
 #pragma unroll 1
-    for (int r0 = 0; r0 < 32; r0 += 8) {
-      float gw[8], pv[8], go[8];
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        float gw[8], pv[8], go[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) gw[k] = __ldg(wp + (r0 + k) * 32);
+        for (int k = 0; k < 8; ++k) gw[k] = __ldg(wp + (r0 + k) * 32);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int y = mt.x + r0 + k;
-        const bool ok = xin && gw[k] != 0.f && (unsigned)y < (unsigned)Ho;
-        pv[k] = (HAS_P && ok) ? __ldg(S.probs + poff + (size_t)y * Wo + x) : 0.f;
-        go[k] = (HAS_G && ok) ? __ldg(S.g_out + poff + (size_t)y * Wo + x) : 0.f;
-      }
+        for (int k = 0; k < 8; ++k) {
+          const int y = mt.x + r0 + k;
+          const bool ok = xin && gw[k] != 0.f && (unsigned)y < (unsigned)Ho;
+          pv[k] = (HAS_P && ok) ? __ldg(S.probs + poff + (size_t)y * Wo + x) : 0.f;
+          go[k] = (HAS_G && ok) ? __ldg(S.g_out + poff + (size_t)y * Wo + x) : 0.f;
+        }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int y = mt.x + r0 + k;
-        if (!(xin && gw[k] != 0.f && (unsigned)y < (unsigned)Ho)) continue;
-        float g = gw[k] + go[k];
-        if (HAS_P) g = pv[k] * (g - dot);
-        const int kk = kx + 2 * GB_CLS * (y & 1);
-        gcol[((size_t)(kk >> 3) * L.rows + (size_t)(y >> 1) * L.Pp) * 8 + (kk & 7)] = __float2bfloat16_rn(g);
+        for (int k = 0; k < 8; ++k) {
+          const int y = mt.x + r0 + k;
+          if (!(xin && gw[k] != 0.f && (unsigned)y < (unsigned)Ho)) continue;
+          float g = gw[k] + go[k];
+          if (HAS_P) g = pv[k] * (g - dot);
+          const int kk = kx + 2 * GB_CLS * (y & 1);
+          gcol[((size_t)(kk >> 3) * L.rows + (size_t)(y >> 1) * L.Pp) * 8 + (kk & 7)] = __float2bfloat16_rn(g);
+        }
       }
     }
-    return;
   }
-  // flag 2: the plane's decode gradient is dense (gov); rare
-  for (int i = lane; i < Ho * Wo; i += 32) {
-    const float gw = __ldg(S.gov + poff + i);
-    const int y = i / Wo, x = i % Wo;
-    if (gw == 0.f) continue;
-    float g = gw;
-    if (HAS_G) g += __ldg(S.g_out + poff + i);
-    if (HAS_P) g = __ldg(S.probs + poff + i) * (g - dot);
-    const int k = (((y & 1) << 1) | (x & 1)) * GB_CLS + o;
-    G[(((size_t)b * GB_KC + (k >> 3)) * L.rows + L.lead + (size_t)(y >> 1) * L.Pp + (x >> 1)) * 8 + (k & 7)] = __float2bfloat16_rn(g);
+  // flag 2: the plane's decode gradient is dense (the decode's overflow buffer); rare.  The whole CTA takes each such
+  // plane of its four, eight independent loads per thread and round (one warp alone would be a 170 us tail).
+  for (int w = 0; w < 4; ++w) {
+    const long long plane = (long long)blockIdx.x * 4 + w;
+    if (plane >= n_planes) break;
+    const int4 mt = reinterpret_cast<const int4*>(S.meta)[plane];  // uniform over the CTA
+    if (mt.z != 2) continue;
+    const int b = (int)(plane / C), o = (int)(plane - (long long)b * C);
+    const float dot = HAS_P && S.ddot ? S.ddot[plane] : 0.f;
+    const size_t poff = (size_t)plane * Ho * Wo;
+    const int hw = Ho * Wo;
+#pragma unroll 1
+    for (int i0 = threadIdx.x; i0 < hw; i0 += 8 * 128) {
+      float gw[8], pv[8], go[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * 128;
+        const bool in = i < hw;
+        gw[k] = in ? __ldg(S.gov + poff + i) : 0.f;
+        pv[k] = (HAS_P && in) ? __ldg(S.probs + poff + i) : 0.f;
+        go[k] = (HAS_G && in) ? __ldg(S.g_out + poff + i) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * 128;
+        if (i >= hw || gw[k] == 0.f) continue;
+        const int y = i / Wo, x = i - y * Wo;
+        float g = gw[k] + go[k];
+        if (HAS_P) g = pv[k] * (g - dot);
+        const int kk = (((y & 1) << 1) | (x & 1)) * GB_CLS + o;
+        G[(((size_t)b * GB_KC + (kk >> 3)) * L.rows + L.lead + (size_t)(y >> 1) * L.Pp + (x >> 1)) * 8 + (kk & 7)] = __float2bfloat16_rn(g);
+      }
+    }
   }
 }
 
