@@ -73,6 +73,36 @@ __global__ void __launch_bounds__(256) plane_dot_kernel(G2Src S, int hw, float* 
   }
 }
 
+// Window-only form (no dense gradient): ddot is zero except for the few planes whose decode gradient is dense (flag 2).
+// A CTA looks after 8 planes and sweeps only the flagged ones, all 256 threads on one plane at a time -- an eighth of the
+// CTAs of the per-plane launch and no single-warp tail.
+__global__ void __launch_bounds__(256) plane_dot_sparse_kernel(G2Src S, long long n_planes, int hw, float* __restrict__ ddot) {
+  __shared__ float red[8];
+  const long long p0 = (long long)blockIdx.x * 8;
+  for (long long plane = p0; plane < p0 + 8 && plane < n_planes; ++plane) {
+    if (S.meta[4 * plane + 2] != 2) {  // uniform over the CTA
+      if (threadIdx.x == 0) ddot[plane] = 0.f;
+      continue;
+    }
+    const float4* p4 = reinterpret_cast<const float4*>(S.probs + plane * hw);
+    const float4* o4 = reinterpret_cast<const float4*>(S.gov + plane * hw);
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < hw / 4; i += 256) {
+      const float4 p = __ldg(p4 + i), o = __ldg(o4 + i);
+      acc += p.x * o.x + p.y * o.y + p.z * o.z + p.w * o.w;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      ddot[plane] = t;
+    }
+    __syncthreads();
+  }
+}
+
 // Thread t of a frame handles input-grid pixel (m, n) = divmod(t, Wi): the 2x2 output block x all channels.
 // Loads are issued as independent batches (probs, dense gradient) before any dependent work; the window
 // look-ups are rare (a 32x32 patch of a 96x96 plane) and come last.
@@ -83,7 +113,9 @@ constexpr int G2B_THREADS = 128;
 // adds them with branch-free shared-memory reads instead of divergent global gathers.
 constexpr int G2B_MROWS = 4;  // input-grid rows a CTA can touch: ceil(128 / Wi) + 1 for Wi >= 43 (host checks)
 
-template <bool HAS_G, bool HAS_P, bool HAS_WIN>
+// HAS_OV (window-less pass ahead of the patch kernel): planes whose decode gradient is dense (flag 2, the decode's overflow
+// buffer) are added here, in the streaming pass -- in the fresh-init regime that is every plane.
+template <bool HAS_G, bool HAS_P, bool HAS_WIN, bool HAS_OV = false>
 __global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B, int C, int Hi, int Wi, int ctas_per_frame,
                                                                __nv_bfloat16* __restrict__ G, RowLayout L) {
   const int b = blockIdx.x / ctas_per_frame, t0 = (blockIdx.x - b * ctas_per_frame) * G2B_THREADS, t = t0 + threadIdx.x;
@@ -91,7 +123,7 @@ __global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B
   __shared__ float sdot[GB_CLS];
   __shared__ int4 smeta[GB_CLS];
   __shared__ float wtile[HAS_WIN ? GB_CLS * 2 * G2B_MROWS * 32 : 1];
-  __shared__ unsigned shit;
+  __shared__ unsigned shit, sov;
   const int m0 = t0 / Wi;
   if (threadIdx.x < GB_CLS) {
     float d = 0.f;
@@ -106,6 +138,10 @@ __global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B
     }
     sdot[threadIdx.x] = d;
     smeta[threadIdx.x] = mt;
+    if (HAS_OV) {
+      const unsigned bov = __ballot_sync((1u << GB_CLS) - 1, mt.z == 2);
+      if (threadIdx.x == 0) sov = bov;
+    }
     if (HAS_WIN) {
       // does this plane's window (or its dense fallback) touch the CTA's output rows [2 m0, 2 m0 + 2 MROWS)?  A 32x32
       // window covers a ninth of a 96x96 plane: most (CTA, plane) pairs skip the look-ups altogether (uniform branch)
@@ -176,6 +212,16 @@ __global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B
         }
       }
     }
+    if (HAS_OV && sov) {  // uniform per frame
+      const unsigned ovm = sov;
+#pragma unroll
+      for (int o = 0; o < GB_CLS; ++o) {
+        if (o < C && ((ovm >> o) & 1u)) {
+          const float2 u = __ldg(reinterpret_cast<const float2*>(S.gov + off0 + o * pstride));
+          gv[o].x += u.x, gv[o].y += u.y;
+        }
+      }
+    }
     if (HAS_P) {
 #pragma unroll
       for (int o = 0; o < GB_CLS; ++o) {
@@ -202,9 +248,10 @@ __global__ void __launch_bounds__(G2B_THREADS, 4) g2_build_kernel(G2Src S, int B
   }
 }
 
-// Window patch: after a window-less g2_build pass (which already folds each window's dot into the softmax term), one warp
-// per plane re-evaluates the <= 32 x 32 pixels under its window and overwrites those bf16 entries.  The streaming pass then
-// runs at the DRAM roofline with no look-ups in it, and this pass touches 4 KB of probabilities per plane (a ninth of it).
+// Window patch: after a window-less g2_build pass (which already folds each window's dot into the softmax term and adds the
+// dense-overflow planes), one warp per plane re-evaluates the <= 32 x 32 pixels under its window and overwrites those
+// bf16 entries.  The streaming pass then runs at the DRAM roofline with no look-ups in it, and this pass touches 4 KB of
+// probabilities per plane (a ninth of it).
 // Window rows go eight at a time: 8 independent window loads, then 8 independent probability loads per lane.
 template <bool HAS_G, bool HAS_P>
 __global__ void __launch_bounds__(128) g2_patch_kernel(G2Src S, long long n_planes, int C, int Hi, int Wi,
@@ -250,40 +297,6 @@ __global__ void __launch_bounds__(128) g2_patch_kernel(G2Src S, long long n_plan
       }
     }
   }
-  // flag 2: the plane's decode gradient is dense (the decode's overflow buffer); rare.  The whole CTA takes each such
-  // plane of its four, eight independent loads per thread and round (one warp alone would be a 170 us tail).
-  for (int w = 0; w < 4; ++w) {
-    const long long plane = (long long)blockIdx.x * 4 + w;
-    if (plane >= n_planes) break;
-    const int4 mt = reinterpret_cast<const int4*>(S.meta)[plane];  // uniform over the CTA
-    if (mt.z != 2) continue;
-    const int b = (int)(plane / C), o = (int)(plane - (long long)b * C);
-    const float dot = HAS_P && S.ddot ? S.ddot[plane] : 0.f;
-    const size_t poff = (size_t)plane * Ho * Wo;
-    const int hw = Ho * Wo;
-#pragma unroll 1
-    for (int i0 = threadIdx.x; i0 < hw; i0 += 8 * 128) {
-      float gw[8], pv[8], go[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int i = i0 + k * 128;
-        const bool in = i < hw;
-        gw[k] = in ? __ldg(S.gov + poff + i) : 0.f;
-        pv[k] = (HAS_P && in) ? __ldg(S.probs + poff + i) : 0.f;
-        go[k] = (HAS_G && in) ? __ldg(S.g_out + poff + i) : 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int i = i0 + k * 128;
-        if (i >= hw || gw[k] == 0.f) continue;
-        const int y = i / Wo, x = i - y * Wo;
-        float g = gw[k] + go[k];
-        if (HAS_P) g = pv[k] * (g - dot);
-        const int kk = (((y & 1) << 1) | (x & 1)) * GB_CLS + o;
-        G[(((size_t)b * GB_KC + (kk >> 3)) * L.rows + L.lead + (size_t)(y >> 1) * L.Pp + (x >> 1)) * 8 + (kk & 7)] = __float2bfloat16_rn(g);
-      }
-    }
-  }
 }
 
 template <bool HAS_G, bool HAS_P>
@@ -294,8 +307,12 @@ static void launch_g2_build(const G2Src& S, int B, int C, int Hi, int Wi, __nv_b
     g2_build_kernel<HAS_G, HAS_P, true><<<(unsigned)(B * cpf), G2B_THREADS, 0, s>>>(S, B, C, Hi, Wi, cpf, G, L);
     return;
   }
-  g2_build_kernel<HAS_G, HAS_P, false><<<(unsigned)(B * cpf), G2B_THREADS, 0, s>>>(S, B, C, Hi, Wi, cpf, G, L);
-  if (S.win) {
+  if (!S.win) {
+    g2_build_kernel<HAS_G, HAS_P, false><<<(unsigned)(B * cpf), G2B_THREADS, 0, s>>>(S, B, C, Hi, Wi, cpf, G, L);
+    return;
+  }
+  g2_build_kernel<HAS_G, HAS_P, false, true><<<(unsigned)(B * cpf), G2B_THREADS, 0, s>>>(S, B, C, Hi, Wi, cpf, G, L);
+  {
     const long long np = (long long)B * C;
     g2_patch_kernel<HAS_G, HAS_P><<<(unsigned)((np + 3) / 4), 128, 0, s>>>(S, np, C, Hi, Wi, G, L);
   }
@@ -1106,7 +1123,10 @@ extern "C" int lpb_head_bwd_bf16(const float* g_out, const float* probs, const f
     src.ddot = nullptr;
     if (probs) {
       LPB_REQUIRE(((4 * Hio * Wio) % 4) == 0, "head_bwd_bf16: plane size");
-      plane_dot_kernel<<<(unsigned)(B * kout), 256, 0, s>>>(src, 4 * Hio * Wio, ddot);
+      if (!g_out && win)
+        plane_dot_sparse_kernel<<<(unsigned)(((long long)B * kout + 7) / 8), 256, 0, s>>>(src, (long long)B * kout, 4 * Hio * Wio, ddot);
+      else
+        plane_dot_kernel<<<(unsigned)(B * kout), 256, 0, s>>>(src, 4 * Hio * Wio, ddot);
       src.ddot = ddot;
     }
     if (g_out && probs) launch_g2_build<true, true>(src, B, kout, Hio, Wio, Gout, Lo, s);
