@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
     // ================= MMA issuer =================
     const uint32_t idesc = tc::make_idesc_bf16_f32(128, HB_NCOLS);
     const uint32_t lbo_a = g.rows_alloc * 16, lbo_b = HB_NCOLS * 16;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int it = 0;
     uint32_t fph = 0;
     for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
         const int s = it % K1A_ASTAGES;
         mbar_wait(&full[s], (it / K1A_ASTAGES) & 1);
         tc::fence_after_sync();
-        if (lane == 0) {
+        {  // the whole warp, convergent: one elected lane issues (tc::umma_bf16_e)
           const uint32_t a0 = smem_u32(stage_base + s * stage_bytes);
           const uint32_t b0 = a0 + a_stage_bytes;
           for (int t = 0; t < g.tiles; ++t) {
@@ -423,16 +424,16 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
               for (int k16 = 0; k16 < 2; ++k16) {
                 const uint32_t aa = a0 + (2 * k16) * lbo_a + (t * 128 + shift_rows) * 16;
                 const uint32_t bb = b0 + (sh * 4 + 2 * k16) * lbo_b;
-                tc::umma_bf16(tmem_base + t * HB_NCOLS, tc::make_smem_desc(aa, lbo_a, 128), tc::make_smem_desc(bb, lbo_b, 128),
-                              idesc, (st | sh | k16) != 0 ? 1u : 0u);
+                tc::umma_bf16_e(tmem_u + t * HB_NCOLS, tc::make_smem_desc(aa, lbo_a, 128), tc::make_smem_desc(bb, lbo_b, 128),
+                                idesc, (st | sh | k16) != 0 ? 1u : 0u);
               }
             }
           }
-          tc::umma_commit(&empty[s]);
+          tc::umma_commit_e(&empty[s]);
         }
         __syncwarp();
       }
-      if (lane == 0) tc::umma_commit(tmem_full);
+      tc::umma_commit_e(tmem_full);
       __syncwarp();
       fph ^= 1;
     }

@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
   } else if (warp == 1) {
     const uint32_t idesc = tc::make_idesc_bf16_f32(128, 32);
     const uint32_t lbo_a = rows_alloc * 16, lbo_b = 32 * 16;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t a0 = smem_u32(As), b0 = smem_u32(Ws);
     mbar_wait(w_full, 0);
     int it = 0;
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
         mbar_wait(a_full, it & 1);
         mbar_wait(t_empty, (it & 1) ^ 1);
         tc::fence_after_sync();
-        if (lane == 0) {
+        {  // whole warp, convergent; one elected lane issues (tcgen05.cuh)
           for (int t = 0; t < B2D_TILES; ++t) {
 #pragma unroll
             for (int sh = 0; sh < 4; ++sh) {
@@ -416,13 +417,13 @@ __global__ void __launch_bounds__(B2D_THREADS, 2) b2d_dgrad_kernel(const __grid_
                 if (k16 < sh) continue;  // all-zero weight chunks of this shift (see b3a)
                 const uint32_t aa = a0 + (2 * k16) * lbo_a + (LEAD + t * 128 - shift_rows) * 16;
                 const uint32_t bb = b0 + (sh * GB_KC + 2 * k16) * lbo_b;
-                tc::umma_bf16(tmem_base + t * 32, tc::make_smem_desc(aa, lbo_a, 128), tc::make_smem_desc(bb, lbo_b, 128), idesc,
-                              (sh | k16) != 0 ? 1u : 0u);
+                tc::umma_bf16_e(tmem_u + t * 32, tc::make_smem_desc(aa, lbo_a, 128), tc::make_smem_desc(bb, lbo_b, 128), idesc,
+                                (sh | k16) != 0 ? 1u : 0u);
               }
             }
           }
-          tc::umma_commit(t_full);
-          tc::umma_commit(a_empty);
+          tc::umma_commit_e(t_full);
+          tc::umma_commit_e(a_empty);
         }
         __syncwarp();
       }
@@ -586,17 +587,18 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
     const uint32_t idesc1 = n1 > 0 ? tc::make_idesc_bf16_f32(128, n1) : 0u;
     const uint32_t lbo_g = rows_alloc * 16, lbo_w = 128 * 16;
     const uint32_t w0 = smem_u32(Ws);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     mbar_wait(w_full, 0);
     int it = 0;
     for (int b = slot; b < P.B; b += nslot)
       for (int band = 0; band < nbands; ++band, ++it) {
         const int st = it & 1;
         const int tb = it % nbuf, tph = (it / nbuf) & 1;
-        const uint32_t dcol = tmem_base + tb * 256;
+        const uint32_t dcol = tmem_u + tb * 256;
         mbar_wait(&g_full[st], (it >> 1) & 1);
         mbar_wait(&t_empty[tb], tph ^ 1);
         tc::fence_after_sync();
-        if (lane == 0) {
+        {  // whole warp, convergent; one elected lane issues (tcgen05.cuh)
           const uint32_t g0 = smem_u32(Gs + (size_t)st * g_bytes);
 #pragma unroll
           for (int sh = 0; sh < 4; ++sh) {
@@ -610,13 +612,13 @@ __global__ void __launch_bounds__(B3A_THREADS, 1) b3a_dgrad_kernel(const __grid_
               const uint32_t ww = w0 + ((sh * GB_KC + 2 * k16) * 128) * 16;
               const uint32_t gg = g0 + (2 * k16) * lbo_g + (LEAD - shift_rows) * 16;
               const uint64_t wd = tc::make_smem_desc(ww, lbo_w, 128);
-              tc::umma_bf16(dcol, wd, tc::make_smem_desc(gg, lbo_g, 128), idesc0, (sh | k16) != 0 ? 1u : 0u);
+              tc::umma_bf16_e(dcol, wd, tc::make_smem_desc(gg, lbo_g, 128), idesc0, (sh | k16) != 0 ? 1u : 0u);
               if (n1 > 0)
-                tc::umma_bf16(dcol + n0, wd, tc::make_smem_desc(gg + n0 * 16, lbo_g, 128), idesc1, (sh | k16) != 0 ? 1u : 0u);
+                tc::umma_bf16_e(dcol + n0, wd, tc::make_smem_desc(gg + n0 * 16, lbo_g, 128), idesc1, (sh | k16) != 0 ? 1u : 0u);
             }
           }
-          tc::umma_commit(&t_full[tb]);
-          tc::umma_commit(&g_empty[st]);
+          tc::umma_commit_e(&t_full[tb]);
+          tc::umma_commit_e(&g_empty[st]);
         }
         __syncwarp();
       }
@@ -838,22 +840,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   } else if (warp == 1) {
     const uint32_t idesc = tc::make_idesc_bf16_f32(128, P.swap ? gcp * GB_K : (P.stack ? 4 * N : N)) | (1u << 15) | (1u << 16);  // both operands MN-major
     const uint32_t g0 = smem_u32(Gs), x0 = smem_u32(Xs);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int j = 0;
     for (int u = slot; u < nunits; u += nslot, ++j) {
       const int s = j & 1;
       mbar_wait(&full[s], (j >> 1) & 1);
       tc::fence_after_sync();
-      if (lane == 0) {
+      {  // whole warp, convergent; one elected lane issues (tcgen05.cuh)
         for (int k16 = 0; k16 < KR / 16; ++k16) {
           const uint64_t gd = tc::make_smem_desc(g0 + s * g_bytes + k16 * 256, 128, KR * 16);
           if (P.stack) {
-            tc::umma_bf16(tmem_base, gd, tc::make_smem_desc(x0 + s * x_bytes + k16 * 256, 128, XR * 16), idesc, (j | k16) != 0 ? 1u : 0u);
+            tc::umma_bf16_e(tmem_u, gd, tc::make_smem_desc(x0 + s * x_bytes + k16 * 256, 128, XR * 16), idesc, (j | k16) != 0 ? 1u : 0u);
             continue;
           }
           if (P.swap == 2) {  // columns [160 dm, 160 dm + 80) = shift (dm, 0), the next 80 = shift (dm, 1): the same map as swap == 1
 #pragma unroll
             for (int dm = 0; dm < 2; ++dm)
-              tc::umma_bf16(tmem_base + dm * 2 * GB_K, tc::make_smem_desc(x0 + s * x_bytes + (k16 * 16 + dm * Pp) * 16, 128, XR * 16), gd, idesc,
+              tc::umma_bf16_e(tmem_u + dm * 2 * GB_K, tc::make_smem_desc(x0 + s * x_bytes + (k16 * 16 + dm * Pp) * 16, 128, XR * 16), gd, idesc,
                             (j | k16) != 0 ? 1u : 0u);
             continue;
           }
@@ -861,15 +864,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           for (int sh = 0; sh < 4; ++sh) {
             const int shift_rows = (sh >> 1) * Pp + (sh & 1);
             const uint64_t xd = tc::make_smem_desc(x0 + s * x_bytes + (k16 * 16 + shift_rows) * 16, 128, XR * 16);
-            if (P.swap) tc::umma_bf16(tmem_base + sh * GB_K, xd, gd, idesc, (j | k16) != 0 ? 1u : 0u);
-            else tc::umma_bf16(tmem_base + sh * N, gd, xd, idesc, (j | k16) != 0 ? 1u : 0u);
+            if (P.swap) tc::umma_bf16_e(tmem_u + sh * GB_K, xd, gd, idesc, (j | k16) != 0 ? 1u : 0u);
+            else tc::umma_bf16_e(tmem_u + sh * N, gd, xd, idesc, (j | k16) != 0 ? 1u : 0u);
           }
         }
-        tc::umma_commit(&empty[s]);
+        tc::umma_commit_e(&empty[s]);
       }
       __syncwarp();
     }
-    if (lane == 0 && j > 0) tc::umma_commit(t_done);
+    if (j > 0) tc::umma_commit_e(t_done);
     __syncwarp();
   } else if (slot < nunits && P.swap) {
     // swapped form: lane = channel, column = (cls, o) of shift sh

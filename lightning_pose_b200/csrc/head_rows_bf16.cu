@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
     // ================= MMA issuer =================
     const uint32_t idesc = tc::make_idesc_bf16_f32(128, CR_NCOLS);
     const uint32_t lbo_a = P.rows_alloc * 16, lbo_b = CR_NCOLS * 16;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int it = 0, nb = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x)
       for (int pass = 0; pass < npass; ++pass)
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
             const int s = it % CR_STAGES;
             mbar_wait(&full[s], (it / CR_STAGES) & 1);
             tc::fence_after_sync();
-            if (lane == 0) {
+            {  // whole warp, convergent; one elected lane issues (tcgen05.cuh)
               const uint32_t a0 = smem_u32(smem + s * stage_bytes), b0 = a0 + a_bytes;
               for (int t = 0; t < tiles; ++t) {
 #pragma unroll
@@ -175,13 +176,13 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
                   for (int k16 = 0; k16 < 2; ++k16) {
                     const uint32_t aa = a0 + (2 * k16) * lbo_a + (t * 128 + shift_rows) * 16;
                     const uint32_t bb = b0 + (sh * 4 + 2 * k16) * lbo_b;
-                    tc::umma_bf16(tmem_base + t * CR_NCOLS, tc::make_smem_desc(aa, lbo_a, 128), tc::make_smem_desc(bb, lbo_b, 128),
-                                  idesc, (st | sh | k16) != 0 ? 1u : 0u);
+                    tc::umma_bf16_e(tmem_u + t * CR_NCOLS, tc::make_smem_desc(aa, lbo_a, 128), tc::make_smem_desc(bb, lbo_b, 128),
+                                    idesc, (st | sh | k16) != 0 ? 1u : 0u);
                   }
                 }
               }
-              tc::umma_commit(&empty[s]);
-              if (st == nst - 1) tc::umma_commit(t_full);
+              tc::umma_commit_e(&empty[s]);
+              if (st == nst - 1) tc::umma_commit_e(t_full);
             }
             __syncwarp();
           }

@@ -62,6 +62,31 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// Warp-convergent forms: the WHOLE warp executes the call with warp-uniform operands and one elected lane issues.  Inside an
+// `if (lane == 0)` region the compiler has to move every operand of every MMA into uniform registers through an
+// ELECT / R2UR.BROADCAST loop (~17 instructions per MMA in the issuing thread, which is what bounded the 4-shift kernels:
+// 40 MMAs per 32-channel stage); in convergent code the descriptor arithmetic stays in the uniform datapath.
+__device__ __forceinline__ void umma_bf16_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 // ---- TMEM -> registers: 32 lanes x 16 consecutive 32-bit columns per warp ---------------------------
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
