@@ -368,10 +368,22 @@ def kernel_breakdown(hp: "HotPath", feats, reps=20):
         out[name] = {"ms": med, "ms_mean": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / med / 1e6, "what": what}
 
     with torch.no_grad():
-        hm = hp.head(feats)
-        kp, cf = ops.decode_softargmax(hm, 2, 1000.0)
-        add("head_fwd", lambda: hp.head(feats), nf * (fb + HM_BYTES), "K1: features -> normalised heatmaps (k1a + k1b, inference form)")
-        add("decode_fwd", lambda: ops.decode_softargmax(hm, 2, 1000.0), nf * (HM_BYTES + KP_BYTES), "K2: heatmaps -> (x, y, confidence)")
+        # the two halves of HeatmapHead.forward_with_keypoints as the step runs them: on the bf16 path the head's softmax pass
+        # also writes the per-plane decode hints (16 B per plane) and the decode consumes them
+        hints = None
+        if feats.dtype == torch.bfloat16:
+            d1, d2 = list(hp.head.upsampling_layers)[1:]
+            wts, bss = [d1.weight, d2.weight], [d1.bias, d2.bias]
+            head_fn = lambda: ops._head_forward_bf16(feats, wts, bss, True, want_hints=True)
+            hm, hints = head_fn()
+        else:
+            head_fn = lambda: hp.head(feats)
+            hm = head_fn()
+        kp, cf, _ = ops.decode_forward_hinted(hm, 2, 1000.0, hints)
+        kp = kp.reshape(nf, -1)
+        add("head_fwd", head_fn, nf * (fb + HM_BYTES), "K1: features -> normalised heatmaps (+ decode hints), inference form (k1a + banded layer 2)")
+        add("decode_fwd", lambda: ops.decode_forward_hinted(hm, 2, 1000.0, hints), nf * (HM_BYTES + KP_BYTES),
+            "K2: heatmaps (+ hints) -> (x, y, confidence)")
         add("target_mse_fwd", lambda: ops.heatmap_mse_from_keypoints(hp.kp_lab, hm[:nl], IMG, IMG, visibility=hp.vis),
             nl * (HM_BYTES + KP_BYTES), "K3: fused Gaussian targets + heatmap MSE (labeled frames)")
         add("unsup_losses_fwd", lambda: ops.unsup_losses(kp[nl:].reshape(n, T_UNLABELED, -1), cf[nl:].reshape(n, T_UNLABELED, -1),

@@ -53,7 +53,9 @@ const char* lpb_build_arch(void);     /* "sm_100a" */
 #define LPB_TUNE_B3A_TMA_STORE 10       /* 1 (default): b3a stages d features in shared memory and a TMA tensor store scatters them to NCHW; 0: direct 16-byte stores */
 #define LPB_TUNE_WGRAD_SWAP 11          /* layer-1 weight gradient: 1: A = features (M = 128 channels), B = gradient rows (N = 80); 2 (default): the same with the gradient rows staged twice, one row apart, side by side along N (N = 160: two shifts per MMA); 0: A = gradient rows */
 #define LPB_TUNE_G2_PATCH 12            /* 1 (default): decode windows enter the gradient rows in a patch pass (one warp per plane) after a look-up-free streaming pass; 0: look-ups fused into the streaming pass */
-#define LPB_TUNE_COUNT 13
+#define LPB_TUNE_MMA_TILE_INNER 13      /* 1: k1a issues its MMAs tile-innermost (consecutive MMAs accumulate into different TMEM tiles); 0: tile-outermost */
+#define LPB_TUNE_DECODE_HINTS 14        /* 1: the fused two-pass softmax emits per-plane decode hints (arg max + largest value outside its 32x32 box) and the decode skips its plane sweeps when they allow; 0 (default): hints never produced (measured: what the decode saves, the issue-bound softmax epilogue pays) */
+#define LPB_TUNE_COUNT 15
 int lpb_set_tuning(int key, int value);
 int lpb_get_tuning(int key);
 
@@ -73,6 +75,13 @@ int lpb_get_tuning(int key);
 int lpb_decode_prepare(int h, int w, int ds);
 int lpb_decode_fwd(const float* heatmaps, int64_t n_planes, int h, int w, int ds, float temperature,
                    float* xy, float* conf, float* stats, void* stream);
+/* lpb_decode_fwd with optional per-plane hints (16 bytes per plane: int32 arg-max row, int32 arg-max column, float32 bits of
+ * the largest value outside the 32 x 32 box [row - 16, row + 15] x [col - 16, col + 15], int32 valid) as written by
+ * lpb_head_fwd_bf16_hinted for the SAME heatmaps: planes whose outside bound is below the pruning threshold are decoded
+ * from the window around the arg max alone (no sweep of the plane; identical candidate hull, identical results); planes
+ * with valid = 0 and hints = NULL take the plain route.  No reference counterpart: the reference materialises the field. */
+int lpb_decode_fwd_hinted(const float* heatmaps, int64_t n_planes, int h, int w, int ds, float temperature,
+                          float* xy, float* conf, float* stats, const void* hints, void* stream);
 /* d loss / d heatmaps given d loss / d xy (confidence carries no gradient: it only feeds `<`
  * comparisons, lightning_pose/losses/losses.py:636). grad_heatmaps [n_planes,h,w] is overwritten. */
 int lpb_decode_bwd(const float* heatmaps, const float* stats, const float* grad_xy, int64_t n_planes,
@@ -158,6 +167,11 @@ int lpb_head_bf16_workspace_bytes(int B, int C, int H, int W, int c1, int c2, si
 int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int W, const float* w1, const float* b1, int c1,
                       const float* w2, const float* b2, int c2, int final_softmax, float* out, void* saved_xs,
                       void* workspace, void* stream);
+/* lpb_head_fwd_bf16 that also fills `decode_hints` ([B * K] x 16 bytes, see lpb_decode_fwd_hinted; NULL = none) when the
+ * head ends in the plane softmax: the softmax pass knows each plane's maximum and what lies outside the box around it. */
+int lpb_head_fwd_bf16_hinted(const void* features, int B, int C, int H, int W, const float* w1, const float* b1, int c1,
+                             const float* w2, const float* b2, int c2, int final_softmax, float* out, void* saved_xs,
+                             void* workspace, void* decode_hints, void* stream);
 /* saved_xs: on the fast path NULL for inference; for training (and always on the banded path) a device buffer of lpb_head_bf16_saved_bytes() bytes; it
  * receives the pixel-shuffled features in the padded row layout the weight-gradient GEMM reads, and must stay
  * alive (together with `workspace`, which holds the activations between the two deconvs) until

@@ -26,6 +26,8 @@ int g_tuning[LPB_TUNE_COUNT] = {
     1,  // LPB_TUNE_B3A_TMA_STORE
     2,  // LPB_TUNE_WGRAD_SWAP (2: swapped + two shifts per MMA along N)
     1,  // LPB_TUNE_G2_PATCH
+    1,  // LPB_TUNE_MMA_TILE_INNER
+    0,  // LPB_TUNE_DECODE_HINTS (measured: decode 118 -> 52 us per 512 frames, but the bound costs the softmax epilogue +80 us: net zero)
 };
 }
 extern "C" int lpb_set_tuning(int key, int value) {

@@ -42,6 +42,8 @@ struct DecodeParams {
   float T, lip, offset;
   int l2_hints;       // warp kernel: L2 eviction-priority hints on its two sweeps (LPB_TUNE_DECODE_L2_HINTS)
   int reverse;        // warp kernel: planes are taken last-to-first (LPB_TUNE_DECODE_REVERSE)
+  const int4* hints;  // optional per-plane hints from the head's softmax pass (head_rows.cuh): {arg-max row, col, bits(largest
+                      // value outside the 32 x 32 box around it), valid} -- the warp kernel then needs no sweep of peaked planes
   const int* queue;   // CTA kernel, queue mode: {count, plane ids ...} left over by the warp-per-plane kernel
   int* qcounter;      // [n_planes] arrival counters (zeroed) and
   float* qscratch;    // [n_planes][DEC_MAX_PARTS][4] partial softmax states of a plane split over several CTAs
@@ -678,11 +680,27 @@ __device__ void decode_plane_warp(const DecodeParams<DS>& P, long long plane, co
     if (lane == 0) queue[1 + atomicAdd(queue, 1)] = (int)plane;
   };
 
+  // ---- hinted form: the producer of the plane (the head's softmax pass) already knows where its maximum is and how large
+  // the plane is OUTSIDE the 32 x 32 box around it; when that bound is below the candidate threshold, everything that can
+  // carry weight lies inside the first window and neither sweep of the plane is needed (same hull, same results)
+  bool hinted = false;
+  float hout = 0.f;
+  int besta = 0, bestb = 0;
+  if (!STAGED && P.hints) {
+    const int4 hv = __ldg(P.hints + plane);
+    if (hv.w == 1 && (unsigned)hv.x < (unsigned)h && (unsigned)hv.y < (unsigned)w) {
+      hinted = true;
+      besta = hv.x;
+      bestb = hv.y;
+      hout = __int_as_float(hv.z);
+    }
+  }
   // ---- pass 1: arg max of |h| ----------------------------------------------------------------------------
   float best = -1.f;
   int bidx = 0;
+  if (hinted) best = fabsf(__ldg(src + (size_t)besta * w + bestb));
 #pragma unroll 8
-  for (int idx = lane; idx < n4; idx += 32) {
+  for (int idx = hinted ? n4 : lane; idx < n4; idx += 32) {
     const float4 x = ld4h(idx, pol_keep);
     const float m4 = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
     if (m4 > best) {
@@ -703,9 +721,9 @@ __device__ void decode_plane_warp(const DecodeParams<DS>& P, long long plane, co
     to_queue();
     return;
   }
-  const int besta = bidx / w4;
-  int bestb = (bidx - besta * w4) * 4;
-  {
+  if (!hinted) {
+    besta = bidx / w4;
+    bestb = (bidx - besta * w4) * 4;
     const float4 x = ld4(bidx);
     bestb += (fabsf(x.x) == best) ? 0 : ((fabsf(x.y) == best) ? 1 : ((fabsf(x.z) == best) ? 2 : 3));
   }
@@ -721,7 +739,22 @@ __device__ void decode_plane_warp(const DecodeParams<DS>& P, long long plane, co
 
   // ---- pass 2: hull of the candidates (|h| >= theta), 4-column granularity like the CTA kernel -----------
   int amin = h, amax = -1, bmin = w, bmax = -1;
-  {
+  if (hinted && hout < theta) {
+    // candidates only inside the first window (still in `tile`): lane = window row, 4-column granularity as below
+    const int y = r0w + lane;
+    if (y >= 0 && y < h) {
+#pragma unroll 8
+      for (int cc = 0; cc < DECW_WIN; ++cc) {
+        const int x = c0w + cc;
+        if (x >= 0 && x < w && fabsf(tile[lane * DECW_WP + cc]) >= theta) {
+          amin = min(amin, y);
+          amax = max(amax, y);
+          bmin = min(bmin, x & ~3);
+          bmax = max(bmax, min((x & ~3) + 3, w - 1));
+        }
+      }
+    }
+  } else {
     int a = 0, g = lane;  // idx = a * w4 + g
     while (g >= w4) {
       g -= w4;
@@ -1330,7 +1363,7 @@ __global__ void __launch_bounds__(DEC_THREADS) upsample2x_kernel(const float* __
 // ------------------------------------------------------------------------------------------------
 template <int DS>
 static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, float T, float* xy, float* conf,
-                             float* stats, cudaStream_t stream) {
+                             float* stats, cudaStream_t stream, const void* hints = nullptr) {
   using G = UpsampleGeom<DS>;
   const DeviceTable* th = get_device_table(h, DS);
   const DeviceTable* tw = get_device_table(w, DS);
@@ -1371,6 +1404,7 @@ static int launch_decode_fwd(const float* heat, int64_t n_planes, int h, int w, 
   P.queue = nullptr;
   P.qcounter = nullptr;
   P.qscratch = nullptr;
+  P.hints = static_cast<const int4*>(hints);
   P.l2_hints = g_tuning[LPB_TUNE_DECODE_L2_HINTS];
   P.reverse = g_tuning[LPB_TUNE_DECODE_REVERSE];
   P.lipw = tw->host.lip;
@@ -1501,6 +1535,11 @@ extern "C" int lpb_decode_prepare(int h, int w, int ds) {
 
 extern "C" int lpb_decode_fwd(const float* heatmaps, int64_t n_planes, int h, int w, int ds, float temperature,
                               float* xy, float* conf, float* stats, void* stream) {
+  return lpb_decode_fwd_hinted(heatmaps, n_planes, h, w, ds, temperature, xy, conf, stats, nullptr, stream);
+}
+
+extern "C" int lpb_decode_fwd_hinted(const float* heatmaps, int64_t n_planes, int h, int w, int ds, float temperature,
+                                     float* xy, float* conf, float* stats, const void* hints, void* stream) {
   using namespace lpb;
   LPB_REQUIRE(heatmaps && xy && conf, "decode_fwd: null pointer");
   LPB_REQUIRE(h >= 1 && w >= 1 && ds >= 1 && ds <= 3, "decode_fwd: bad shape h=%d w=%d ds=%d", h, w, ds);
@@ -1512,9 +1551,9 @@ extern "C" int lpb_decode_fwd(const float* heatmaps, int64_t n_planes, int h, in
   if (n_planes == 0) return LPB_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (ds) {
-    case 1: return launch_decode_fwd<1>(heatmaps, n_planes, h, w, temperature, xy, conf, stats, s);
-    case 2: return launch_decode_fwd<2>(heatmaps, n_planes, h, w, temperature, xy, conf, stats, s);
-    default: return launch_decode_fwd<3>(heatmaps, n_planes, h, w, temperature, xy, conf, stats, s);
+    case 1: return launch_decode_fwd<1>(heatmaps, n_planes, h, w, temperature, xy, conf, stats, s, hints);
+    case 2: return launch_decode_fwd<2>(heatmaps, n_planes, h, w, temperature, xy, conf, stats, s, hints);
+    default: return launch_decode_fwd<3>(heatmaps, n_planes, h, w, temperature, xy, conf, stats, s, hints);
   }
 }
 

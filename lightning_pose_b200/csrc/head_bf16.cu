@@ -172,6 +172,7 @@ struct K1aParams {
   int backoff;                // idle warps sleep between barrier polls
   int xs_bulk;                // 1: the saved operand copy is written by TMA bulk stores straight from the operand stage
   int xs_pads;                // 1: the block transposers also write the saved copy's pad rows (else head_prep cleared them)
+  int tile_inner;             // 1: MMA issue order (shift, k16, tile) instead of (tile, shift, k16)
   HeadGeom g;
 };
 
@@ -416,6 +417,21 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
         {  // the whole warp, convergent: one elected lane issues (tc::umma_bf16_e)
           const uint32_t a0 = smem_u32(stage_base + s * stage_bytes);
           const uint32_t b0 = a0 + a_stage_bytes;
+          if (P.tile_inner) {
+            // issue order (shift, k16, tile): consecutive MMAs accumulate into different TMEM tiles
+#pragma unroll
+            for (int sh = 0; sh < 4; ++sh) {
+              const int shift_rows = (sh >> 1) * g.P + (sh & 1);
+#pragma unroll
+              for (int k16 = 0; k16 < 2; ++k16) {
+                const uint64_t bd = tc::make_smem_desc(b0 + (sh * 4 + 2 * k16) * lbo_b, lbo_b, 128);
+                const uint32_t aa0 = a0 + (2 * k16) * lbo_a + shift_rows * 16;
+                const uint32_t acc = (st | sh | k16) != 0 ? 1u : 0u;
+                for (int t = 0; t < g.tiles; ++t)
+                  tc::umma_bf16_e(tmem_u + t * HB_NCOLS, tc::make_smem_desc(aa0 + t * 2048, lbo_a, 128), bd, idesc, acc);
+              }
+            }
+          } else {
           for (int t = 0; t < g.tiles; ++t) {
 #pragma unroll
             for (int sh = 0; sh < 4; ++sh) {
@@ -428,6 +444,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
                                 idesc, (st | sh | k16) != 0 ? 1u : 0u);
               }
             }
+          }
           }
           tc::umma_commit_e(&empty[s]);
         }
@@ -794,6 +811,12 @@ extern "C" int lpb_head_bf16_workspace_bytes(int B, int C, int H, int W, int c1,
 extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int W, const float* w1, const float* b1, int c1,
                                  const float* w2, const float* b2, int c2, int final_softmax, float* out, void* saved_xs,
                                  void* workspace, void* stream) {
+  return lpb_head_fwd_bf16_hinted(features, B, C, H, W, w1, b1, c1, w2, b2, c2, final_softmax, out, saved_xs, workspace, nullptr, stream);
+}
+
+extern "C" int lpb_head_fwd_bf16_hinted(const void* features, int B, int C, int H, int W, const float* w1, const float* b1, int c1,
+                                        const float* w2, const float* b2, int c2, int final_softmax, float* out, void* saved_xs,
+                                        void* workspace, void* decode_hints, void* stream) {
   using namespace lpb;
   LPB_REQUIRE(features && w1 && b1 && out && workspace, "head_fwd_bf16: null pointer");
   LPB_REQUIRE(c2 == 0 || (w2 && b2), "head_fwd_bf16: a two-deconv head needs w2 and b2");
@@ -805,6 +828,10 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   int max_smem = 0, sms = 0;
   device_limits(&max_smem, &sms);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // decode hints are produced by the fused two-pass softmax of the banded kernel only (launch_convt_rows marks them invalid
+  // on its other routes); the routes that never reach it do so here
+  if (decode_hints && (!final_softmax || !g_tuning[LPB_TUNE_SOFTMAX_EPILOGUE_V2]))
+    LPB_CUDA(cudaMemsetAsync(decode_hints, 0, (size_t)16 * B * (c2 > 0 ? c2 : c1), s));
   const int nst = C / 4 / HB_KSTAGE;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   const RowLayout Lxs = make_row_layout(2 * H, 2 * W), Lmid = make_row_layout(4 * H, 4 * W);
@@ -848,6 +875,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
     p.out = out;
     p.partials = partials;
     if (c2 == 0) {
+      p.hints = final_softmax ? static_cast<int4*>(decode_hints) : nullptr;
       p.mode = final_softmax ? CONVT_ROWS_SOFTMAX : CONVT_ROWS_PLANES;
       rc = launch_convt_rows(p, sms, s);
       if (rc != LPB_OK) return rc;
@@ -867,6 +895,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
       p2.cout = c2;
       p2.out = out;
       p2.partials = partials;
+      p2.hints = final_softmax ? static_cast<int4*>(decode_hints) : nullptr;
       p2.mode = final_softmax ? CONVT_ROWS_SOFTMAX : CONVT_ROWS_PLANES;
       rc = launch_convt_rows(p2, sms, s);
       if (rc != LPB_OK) return rc;
@@ -893,6 +922,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
   pa.row_transposer = g_tuning[LPB_TUNE_K1A_ROW_TRANSPOSER];
   pa.backoff = g_tuning[LPB_TUNE_WAIT_BACKOFF];
   pa.xs_bulk = g_tuning[LPB_TUNE_K1A_BULK_XS];
+  pa.tile_inner = g_tuning[LPB_TUNE_MMA_TILE_INNER];
   pa.xs_pads = k1a_pads ? 1 : 0;
   pa.g = g1;
   LPB_CUDA(cudaFuncSetAttribute(k1a_shuffle_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
@@ -909,6 +939,7 @@ extern "C" int lpb_head_fwd_bf16(const void* features, int B, int C, int H, int 
     p2.cout = c2;
     p2.out = out;
     p2.partials = partials;
+    p2.hints = final_softmax ? static_cast<int4*>(decode_hints) : nullptr;
     p2.mode = final_softmax ? CONVT_ROWS_SOFTMAX : CONVT_ROWS_PLANES;
     const int rc = launch_convt_rows(p2, sms, s);
     if (rc != LPB_OK) return rc;

@@ -76,18 +76,22 @@ constexpr int CR_THREADS = 320;  // warp 0 loader, warp 1 MMA issuer (+TMEM owne
 constexpr int CR_EPI = 256;
 constexpr int CR_TILES = 3;      // M-tiles per band (3 * 80 = 240 of the CTA's 256 TMEM columns)
 constexpr int CR_STAGES = 2;
+constexpr int CR_NMASK = 64;     // (band, tile) pairs of a frame the decode hints can cover
+constexpr int CR_HBOX = 16;      // decode hints: the box is rows / columns [arg - 16, arg + 15] = decode.cu's first window
 
 // NPL: compile-time plane count (17 = the usual keypoint count) or 0 for a run-time count <= 20.
 // V2: softmax epilogue with one warp vote per tile (instead of one per plane), the running-max rescale out of the
 // common path, (shift, 1/sum) fetched as one 8-byte shared load and the output pointer advanced by addition.
-template <int MODE, int NPL, bool V2>
+template <int MODE, int NPL, bool V2, bool HINT = false>
 __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_constant__ ConvtRowsParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Pp = P.L.Pp, Wi = P.L.Wi, Hi = P.L.Hi;
   const int a_bytes = 4 * P.rows_alloc * 16, stage_bytes = a_bytes + CR_BSTAGE;
   float* stat = reinterpret_cast<float*>(smem + CR_STAGES * stage_bytes);  // [2][CR_CLS][8 warps]
   float* fin = stat + 2 * CR_CLS * 8;                                       // [CR_CLS][2] = (max * log2 e, 1 / sum)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fin + 2 * CR_CLS + 8);
+  int* finA = reinterpret_cast<int*>(fin + 2 * CR_CLS + 8);                 // [CR_CLS] decode hints: arg max (row << 16 | col)
+  unsigned* nmask = reinterpret_cast<unsigned*>(finA + CR_CLS);             // [CR_NMASK] per (band, tile): planes whose box the tile's rows meet
+  uint64_t* bars = reinterpret_cast<uint64_t*>(nmask + CR_NMASK);
   uint64_t* full = bars;       // [2]
   uint64_t* empty = bars + 2;  // [2]
   uint64_t* t_full = bars + 4;
@@ -123,6 +127,12 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
   const int nitems = PER_BAND ? P.B * nbands : P.B;
   const int bands_per_item = PER_BAND ? 1 : nbands;
   const int ncls = NPL ? NPL : P.cout;  // planes handled by the unrolled loops
+  // Decode hints (fused two-pass softmax only): the running max of pass 0 carries the pixel index in its 14 low mantissa
+  // bits (any value within 2^-9 of the max is as good a softmax shift, and every use of the shift is relative to the stored
+  // value), so the plane's arg max falls out of the existing max-merge; pass 1 tracks the largest probability OUTSIDE the
+  // 32 x 32 box around it.  decode.cu then needs no sweep of the plane when that bound is below its pruning threshold.
+  // (HINT instantiation: the launch has checked planes <= 128 x 128 and nbands * CR_TILES <= CR_NMASK)
+  constexpr bool hint_on = HINT && V2 && MODE == CONVT_ROWS_SOFTMAX;
 
   if (warp == 0) {
     // ================= loader: one bulk copy per K-chunk (band rows + the halo row below) + the stage's weights ====
@@ -235,6 +245,7 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
             const int ml = row / Pp, n = row - ml * Pp;
             const bool valid = (ml < rb) && (n < Wi);
             const int y = 2 * (y0 + ml) + e, x = 2 * n;
+            const unsigned near = (hint_on && write) ? nmask[bi * CR_TILES + t] : 0u;
             auto body = [&](auto ec) {
               constexpr int E = decltype(ec)::value;
               if constexpr (MODE == CONVT_ROWS_MID) {
@@ -285,8 +296,10 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
 #pragma unroll
                       for (int o = 0; o < CR_CLS; ++o) {
                         if (o >= ncls) break;
-                        const float tm = fmaxf(d[8 * E + o], d[8 * E + CR_CLS + o]);
+                        float tm = fmaxf(d[8 * E + o], d[8 * E + CR_CLS + o]);
                         if (tm > mx[o]) {
+                          if (hint_on)
+                            tm = __int_as_float((__float_as_int(tm) & ~0x3FFF) | (y * Wo + x + (d[8 * E + CR_CLS + o] > d[8 * E + o] ? 1 : 0)));
                           sm[o] *= fast_exp2((mx[o] - tm) * L2E);
                           mx[o] = tm;
                         }
@@ -311,6 +324,16 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
                     const float p1 = fast_exp2(fmaf(d[8 * E + CR_CLS + o], L2E, -f.x)) * f.y;
                     *reinterpret_cast<float2*>(dst) = make_float2(p0, p1);
                     dst += plane_stride;
+                    if (hint_on) {
+                      if ((near >> o) & 1u) {  // this tile's rows meet plane o's box: per-pixel test (uniform branch)
+                        const int a = finA[o];
+                        const bool iny = (unsigned)(y - (a >> 16) + CR_HBOX) < 2u * CR_HBOX;
+                        const int dx = x - (a & 0xffff) + CR_HBOX;
+                        mx[o] = fmaxf(mx[o], fmaxf((iny && (unsigned)dx < 2u * CR_HBOX) ? 0.f : p0, (iny && (unsigned)(dx + 1) < 2u * CR_HBOX) ? 0.f : p1));
+                      } else {
+                        mx[o] = fmaxf(mx[o], fmaxf(p0, p1));
+                      }
+                    }
                   }
                 }
                 return;
@@ -376,10 +399,49 @@ __global__ void __launch_bounds__(CR_THREADS, 2) convt_rows_kernel(const __grid_
             } else {
               fin[2 * o] = M * L2E;
               fin[2 * o + 1] = 1.0f / S;
+              if (hint_on) {
+                const int loc = __float_as_int(M) & 0x3FFF, ay = loc / Wo;
+                finA[o] = (ay << 16) | (loc - ay * Wo);
+              }
             }
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (hint_on) {
+            // per (band, tile): the planes whose box rows [ay - 16, ay + 15] the tile's output rows can meet
+            if (tid - 64 < nbands * CR_TILES) {
+              const int bj = (tid - 64) / CR_TILES, tj = (tid - 64) - bj * CR_TILES;
+              const int ylo = 2 * (bj * R + (tj * 128) / Pp), yhi = 2 * (bj * R + (tj * 128 + 127) / Pp) + 1;
+              unsigned m = 0;
+              for (int o = 0; o < ncls; ++o) {
+                const int ay = finA[o] >> 16;
+                if (yhi >= ay - CR_HBOX && ylo <= ay + CR_HBOX - 1) m |= 1u << o;
+              }
+              nmask[tid - 64] = m;
+            }
+#pragma unroll
+            for (int o = 0; o < CR_CLS; ++o) mx[o] = 0.f;  // pass 1 reuses mx[] for the largest probability outside the box
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+          }
         }
+      }
+      if (hint_on) {
+        // merge the outside-the-box maxima: lanes -> warp -> 8 epilogue warps, then one 16-byte hint per plane
+#pragma unroll
+        for (int o = 0; o < CR_CLS; ++o) {
+          if (o >= ncls) break;
+          const float M = warp_max(mx[o]);
+          if (lane == 0) stat[o * 8 + ew] = M;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid - 64 < ncls) {
+          const int o = tid - 64;
+          float M = stat[o * 8];
+#pragma unroll
+          for (int i = 1; i < 8; ++i) M = fmaxf(M, stat[o * 8 + i]);
+          const int a = finA[o];
+          P.hints[(size_t)b * ncls + o] = make_int4(a >> 16, a & 0xffff, __float_as_int(M), 1);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // stat / finA are free for the next frame
       }
     }
   }
@@ -398,7 +460,7 @@ int launch_convt_rows(ConvtRowsParams p, int sms, cudaStream_t s) {
   const int tiles = (p.R * Pp + 127) / 128;
   p.rows_alloc = (tiles * 128 + Pp + 1 + 7) & ~7;
   if (p.rows_alloc < (p.R + 1) * Pp + 8) p.rows_alloc = ((p.R + 1) * Pp + 8 + 7) & ~7;
-  const size_t smem = (size_t)CR_STAGES * (4 * p.rows_alloc * 16 + CR_BSTAGE) + (2 * CR_CLS * 8 + 2 * CR_CLS + 8) * sizeof(float) + 64;
+  const size_t smem = (size_t)CR_STAGES * (4 * p.rows_alloc * 16 + CR_BSTAGE) + (2 * CR_CLS * 8 + 2 * CR_CLS + 8 + CR_CLS + CR_NMASK) * sizeof(float) + 64;
   LPB_REQUIRE(smem <= 113 * 1024, "head_fwd_bf16: band stages need %zu B shared memory", smem);
   p.backoff = g_tuning[LPB_TUNE_WAIT_BACKOFF];
   const int nbands = (p.L.Hi + p.R - 1) / p.R;
@@ -410,6 +472,16 @@ int launch_convt_rows(ConvtRowsParams p, int sms, cudaStream_t s) {
   };
   const bool v2 = g_tuning[LPB_TUNE_SOFTMAX_EPILOGUE_V2] != 0, k17 = p.cout == 17;
   const long long per_band = (long long)p.B * nbands;
+  if (p.hints) {
+    // decode hints come from the fused two-pass softmax only (same condition as the kernel's hint_on); every other route
+    // marks them invalid
+    const bool fused = p.mode == CONVT_ROWS_SOFTMAX && v2 &&
+                       !(p.partials && (g_tuning[LPB_TUNE_SOFTMAX_SPLIT] == 2 || (g_tuning[LPB_TUNE_SOFTMAX_SPLIT] == 1 && p.B < 2 * sms)));
+    if (!fused || 4 * p.L.Hi * p.L.Wi > 16384 || nbands * CR_TILES > CR_NMASK || !g_tuning[LPB_TUNE_DECODE_HINTS]) {
+      LPB_CUDA(cudaMemsetAsync(p.hints, 0, sizeof(int4) * (size_t)p.B * p.cout, s));
+      p.hints = nullptr;
+    }
+  }
   if (p.mode == CONVT_ROWS_MID) return run(convt_rows_kernel<CONVT_ROWS_MID, 0, false>, per_band);
   if (p.mode == CONVT_ROWS_PLANES) return k17 ? run(convt_rows_kernel<CONVT_ROWS_PLANES, 17, false>, per_band) : run(convt_rows_kernel<CONVT_ROWS_PLANES, 0, false>, per_band);
   // split softmax (statistics launch + normalising launch, both parallel over (frame, band)) when one CTA per frame would
@@ -421,6 +493,7 @@ int launch_convt_rows(ConvtRowsParams p, int sms, cudaStream_t s) {
     if (rc != LPB_OK) return rc;
     return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P1, 17, true>, per_band) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P1, 0, true>, per_band);
   }
+  if (v2 && p.hints) return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 17, true, true>, p.B) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 0, true, true>, p.B);
   if (v2) return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 17, true>, p.B) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 0, true>, p.B);
   return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 17, false>, p.B) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX, 0, false>, p.B);
 }

@@ -66,6 +66,19 @@ def _decode_fwd(heatmaps: torch.Tensor, ds: int, temperature: float) -> tuple[to
     return xy, conf, stats
 
 
+def decode_forward_hinted(heatmaps: torch.Tensor, ds: int, temperature: float, hints):
+    """``_decode_fwd`` with the per-plane hints the bf16 head's softmax pass wrote for these very heatmaps (or None):
+    peaked planes are decoded from the window around their maximum without a sweep of the plane; same results.
+    No autograd node of its own (``_HeadFunction`` owns the backward)."""
+    b, k, h, w = heatmaps.shape
+    xy = torch.empty((b, k, 2), device=heatmaps.device, dtype=torch.float32)
+    conf = torch.empty((b, k), device=heatmaps.device, dtype=torch.float32)
+    stats = torch.empty((b, k, 8), device=heatmaps.device, dtype=torch.float32)
+    with torch.cuda.device(heatmaps.device):
+        check(lib.lpb_decode_fwd_hinted(_ptr(heatmaps), b * k, h, w, ds, temperature, _ptr(xy), _ptr(conf), _ptr(stats), _ptr(hints), _stream()))
+    return xy, conf, stats
+
+
 @_decode_fwd.register_fake
 def _(heatmaps, ds, temperature):
     b, k, _, _ = heatmaps.shape
@@ -202,7 +215,7 @@ def head_bf16_supported(shape, channels, train: bool) -> bool:
     return True
 
 
-def _head_forward_bf16(f, weights, biases, final_softmax, train=False):
+def _head_forward_bf16(f, weights, biases, final_softmax, train=False, want_hints=False):
     """tcgen05 path (one- or two-deconv heads); the caller checks ``head_bf16_supported`` first.
 
     ``train=True`` returns ``(out, saved)`` where ``saved`` carries what ``head_backward_bf16`` needs
@@ -226,8 +239,14 @@ def _head_forward_bf16(f, weights, biases, final_softmax, train=False):
     if train or plan.value == 0:  # row-layout copy of the shuffled features: the banded path's operand / the wgrad's input
         check(lib.lpb_head_bf16_saved_bytes(b, c, h, w, C.byref(nbytes)))
         xs = torch.empty((nbytes.value,), device=f.device, dtype=torch.uint8)
+    # decode hints (want_hints: a soft-argmax decode of `out` follows): 16 bytes per plane, see lpb_decode_fwd_hinted
+    hints = None
+    if want_hints and final_softmax and lib.lpb_get_tuning(14) == 1:  # LPB_TUNE_DECODE_HINTS
+        hints = torch.empty((b * out.shape[1], 4), device=f.device, dtype=torch.int32)
     with torch.cuda.device(f.device):
-        check(lib.lpb_head_fwd_bf16(_ptr(f), b, c, h, w, _ptr(w1), _ptr(b1), c1, _ptr(w2), _ptr(b2), c2, int(bool(final_softmax)), _ptr(out), _ptr(xs), _ptr(ws), _stream()))
+        check(lib.lpb_head_fwd_bf16_hinted(_ptr(f), b, c, h, w, _ptr(w1), _ptr(b1), c1, _ptr(w2), _ptr(b2), c2, int(bool(final_softmax)), _ptr(out), _ptr(xs), _ptr(ws), _ptr(hints), _stream()))
+    if want_hints:
+        return (out, (xs, ws), hints) if train else (out, hints)
     if train:
         return out, (xs, ws)
     return out
