@@ -55,7 +55,8 @@ const char* lpb_build_arch(void);     /* "sm_100a" */
 #define LPB_TUNE_G2_PATCH 12            /* 1 (default): decode windows enter the gradient rows in a patch pass (one warp per plane) after a look-up-free streaming pass; 0: look-ups fused into the streaming pass */
 #define LPB_TUNE_MMA_TILE_INNER 13      /* 1: k1a issues its MMAs tile-innermost (consecutive MMAs accumulate into different TMEM tiles); 0: tile-outermost */
 #define LPB_TUNE_DECODE_HINTS 14        /* 1: the fused two-pass softmax emits per-plane decode hints (arg max + largest value outside its 32x32 box) and the decode skips its plane sweeps when they allow; 0 (default): hints never produced (measured: what the decode saves, the issue-bound softmax epilogue pays) */
-#define LPB_TUNE_COUNT 15
+#define LPB_TUNE_K1A_XS_COPY 15         /* k1a's saved operand copy: 2 (default): a dedicated extra warp sends each finished operand stage out with TMA bulk stores (the transposers store nothing); 1: streamed out of the finished stage by the transposer threads (whole sectors); 0: each transposer thread stores the rows it produced */
+#define LPB_TUNE_COUNT 16
 int lpb_set_tuning(int key, int value);
 int lpb_get_tuning(int key);
 

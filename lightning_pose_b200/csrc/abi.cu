@@ -28,6 +28,7 @@ int g_tuning[LPB_TUNE_COUNT] = {
     1,  // LPB_TUNE_G2_PATCH
     1,  // LPB_TUNE_MMA_TILE_INNER
     0,  // LPB_TUNE_DECODE_HINTS (measured: decode 118 -> 52 us per 512 frames, but the bound costs the softmax epilogue +80 us: net zero)
+    2,  // LPB_TUNE_K1A_XS_COPY (2: a dedicated warp sends the finished stage to the saved copy with TMA bulk stores)
 };
 }
 extern "C" int lpb_set_tuning(int key, int value) {

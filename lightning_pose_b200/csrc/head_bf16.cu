@@ -173,10 +173,17 @@ struct K1aParams {
   int xs_bulk;                // 1: the saved operand copy is written by TMA bulk stores straight from the operand stage
   int xs_pads;                // 1: the block transposers also write the saved copy's pad rows (else head_prep cleared them)
   int tile_inner;             // 1: MMA issue order (shift, k16, tile) instead of (tile, shift, k16)
+  int xs_copy;                // 1: the saved copy is streamed out of the finished operand stage by all transposer threads (coalesced)
   HeadGeom g;
 };
 
-__global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const __grid_constant__ K1aParams P) {
+// XS (compile time, block transposers): 0 = no saved copy (inference); 1 = the run-time forms (direct stores with / without
+// pad rows, bulk stores, the row-form transposer); 2 = copy-out of the finished operand stage.  Forms 0 and 2 carry none of
+// form 1's per-task address arithmetic (it cost the hot loop predicated-off instructions and local-memory spills).
+// 3 = a dedicated extra warp (block of K1A_THREADS + 32) sends each finished operand stage to the saved copy with TMA bulk
+// stores: the transposers store nothing, and unlike the loader-issued bulk form (xs_bulk) nothing else waits on the stores.
+template <int XS>
+__global__ void __launch_bounds__(K1A_THREADS + 32, 1) k1a_shuffle_convt_kernel(const __grid_constant__ K1aParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const HeadGeom g = P.g;
   const int a_stage_bytes = 4 * g.rows_alloc * 16;
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&full[s], 32 * K1A_TW + 1);
-      mbar_init(&empty[s], xs_bulk ? 2 : 1);  // the MMAs have read the stage (+ the bulk stores of the saved copy have)
+      mbar_init(&empty[s], (xs_bulk || XS == 3) ? 2 : 1);  // the MMAs have read the stage (+ the bulk stores of the saved copy have)
       mbar_init(&raw_full[s], 1);
       mbar_init(&raw_empty[s], 32 * K1A_TW);
     }
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
         const int row0 = (2 * i0 + (q >> 1)) * g.P + 2 * jc0 + (q & 1);
         t_raw[k] = (uint32_t)(((4 * kc * 8 + q) * P.HW + sc * 8) * 2);
         t_a[k] = (uint32_t)((kc * g.rows_alloc + row0) * 16);
-        t_x[k] = (uint32_t)((kc * P.Lxs.rows + P.Lxs.lead + row0) * 16);
+        if (XS == 1) t_x[k] = (uint32_t)((kc * P.Lxs.rows + P.Lxs.lead + row0) * 16);
         t_wrap[k] = P.W - jc0;  // position at which the image row wraps (W >= 8: at most once per task)
         nt = k + 1;
       }
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
     constexpr int MAXP = K1A_MAXPAD;
     uint32_t t_pad[MAXP];
     int npd = 0;
-    {
+    if (XS == 1) {
       const RowLayout L = P.Lxs;
       const int body1 = L.lead + L.Hi * L.Pp, ntail = L.rows - body1, npad = L.lead + ntail + L.Hi;
 #pragma unroll
@@ -360,9 +367,12 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
       mbar_wait(&empty[s], ((it / K1A_ASTAGES) & 1) ^ 1);
       unsigned char* As = stage_base + s * stage_bytes;
       unsigned char* xs_st = nullptr;  // this (frame, stage)'s 4 K-chunks of the saved copy
-      if (P.xs && !xs_bulk) {
+      unsigned char* xs_cp = nullptr;  // copy-out form: the saved copy leaves through the operand stage (below)
+      if (XS != 0 && XS != 3 && P.xs && !xs_bulk) {
         const int b = blockIdx.x + (it / P.nstages) * gridDim.x, st = it % P.nstages;
-        xs_st = reinterpret_cast<unsigned char*>(P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)P.Lxs.rows * 8);
+        unsigned char* slab = reinterpret_cast<unsigned char*>(P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)P.Lxs.rows * 8);
+        if (XS == 2) xs_cp = slab;
+        else xs_st = slab;
       }
       const unsigned char* raw = raw_base + r * raw_bytes;
 #pragma unroll
@@ -387,11 +397,11 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
             const int pos = 2 * j + hl;  // position within the task: spatial index sc*8 + pos
             const uint32_t delta = (uint32_t)(pos * 32) + (pos >= t_wrap[k] ? wrap_jump : 0u);
             *reinterpret_cast<uint4*>(As + t_a[k] + delta) = o;
-            if (xs_st) *reinterpret_cast<uint4*>(xs_st + t_x[k] + delta) = o;
+            if (XS == 1 && xs_st) *reinterpret_cast<uint4*>(xs_st + t_x[k] + delta) = o;
           }
         }
       }
-      if (xs_st && P.xs_pads) {
+      if (XS == 1 && xs_st && P.xs_pads) {
 #pragma unroll
         for (int k = 0; k < MAXP; ++k)
           if (k < npd) *reinterpret_cast<uint4*>(xs_st + t_pad[k]) = make_uint4(0, 0, 0, 0);
@@ -399,6 +409,56 @@ __global__ void __launch_bounds__(K1A_THREADS, 1) k1a_shuffle_convt_kernel(const
       fence_proxy_async();
       tc::mbar_arrive(&full[s]);
       tc::mbar_arrive(&raw_empty[r]);
+      if (xs_cp) {
+        // Saved copy, copy-out form: the operand stage IS the copy's row layout (halo rows and zero columns included), so
+        // once all four transposer warps have written it, the 128 threads stream it out with consecutive 16-byte rows per
+        // lane -- every store instruction fills 16 whole sectors.  (The direct form stores each 16-byte row from the thread
+        // that transposed it: 32 half-used sectors per instruction, every sector written twice -- the transposers' LSU
+        // time was k1a's bound in training.)  The MMAs read the stage meanwhile; it is rewritten two stages later, after
+        // this loop's next barrier.
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * K1A_TW) : "memory");
+        const int lead = P.Lxs.lead, nrows = P.Lxs.rows, nbody = nrows - lead;
+        constexpr int NT = 32 * K1A_TW, UB = 6;  // UB independent shared loads in flight per thread, then UB stores
+#pragma unroll 1
+        for (int kc = 0; kc < 4; ++kc) {
+          const unsigned char* srcp = As + (size_t)kc * g.rows_alloc * 16;
+          unsigned char* dstp = xs_cp + (size_t)kc * nrows * 16;
+          if (tid < lead) *reinterpret_cast<uint4*>(dstp + (size_t)tid * 16) = make_uint4(0, 0, 0, 0);  // lead <= 128 rows (host)
+          dstp += (size_t)lead * 16;
+#pragma unroll 1
+          for (int r0 = tid; r0 < nbody; r0 += UB * NT) {
+            uint4 v[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u)
+              if (r0 + u * NT < nbody) v[u] = *reinterpret_cast<const uint4*>(srcp + (size_t)(r0 + u * NT) * 16);
+#pragma unroll
+            for (int u = 0; u < UB; ++u)
+              if (r0 + u * NT < nbody) *reinterpret_cast<uint4*>(dstp + (size_t)(r0 + u * NT) * 16) = v[u];
+          }
+        }
+      }
+    }
+  } else if (XS == 3 && warp == K1A_TW + 6) {
+    // ================= store warp: finished operand stage -> saved copy, by TMA bulk stores =========================
+    if (lane == 0) {
+      const uint32_t lead_b = (uint32_t)P.Lxs.lead * 16, body_b = (uint32_t)(g.rows + g.P + 1) * 16;
+      for (int it = 0; it < total_it; ++it) {
+        const int s = it % K1A_ASTAGES, st = it % P.nstages;
+        mbar_wait(&full[s], (it / K1A_ASTAGES) & 1);
+        const int b = blockIdx.x + (it / P.nstages) * gridDim.x;
+        unsigned char* slab = reinterpret_cast<unsigned char*>(P.xs + ((size_t)b * P.nstages + st) * 4 * (size_t)P.Lxs.rows * 8);
+        const unsigned char* As = stage_base + s * stage_bytes;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          unsigned char* dst = slab + (size_t)kc * P.Lxs.rows * 16;
+          bulk_s2g(dst, zreg, lead_b);
+          bulk_s2g(dst + lead_b, As + (size_t)kc * g.rows_alloc * 16, body_b);
+        }
+        bulk_commit_group();
+        bulk_wait_group_read0();
+        tc::mbar_arrive(&empty[s]);
+      }
+      bulk_wait_group0();  // the copies are in global memory before the kernel ends
     }
   } else if (warp == K1A_TW) {
     // ================= MMA issuer =================
@@ -923,10 +983,17 @@ extern "C" int lpb_head_fwd_bf16_hinted(const void* features, int B, int C, int 
   pa.backoff = g_tuning[LPB_TUNE_WAIT_BACKOFF];
   pa.xs_bulk = g_tuning[LPB_TUNE_K1A_BULK_XS];
   pa.tile_inner = g_tuning[LPB_TUNE_MMA_TILE_INNER];
+  pa.xs_copy = (g_tuning[LPB_TUNE_K1A_XS_COPY] && !pa.row_transposer && !pa.xs_bulk) ? 1 : 0;
   pa.xs_pads = k1a_pads ? 1 : 0;
   pa.g = g1;
-  LPB_CUDA(cudaFuncSetAttribute(k1a_shuffle_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
-  k1a_shuffle_convt_kernel<<<B < sms ? B : sms, K1A_THREADS, s1, s>>>(pa);
+  {
+    // compile-time form of the saved copy (see the kernel): none / run-time forms / copy-out
+    if (pa.xs_copy && Lxs.lead > 32 * K1A_TW) pa.xs_copy = 0;
+    const int form = (!pa.xs || pa.row_transposer || pa.xs_bulk) ? (pa.xs || pa.row_transposer ? 1 : 0) : (g_tuning[LPB_TUNE_K1A_XS_COPY] == 2 ? 3 : (pa.xs_copy ? 2 : 1));
+    auto kern = form == 0 ? k1a_shuffle_convt_kernel<0> : (form == 1 ? k1a_shuffle_convt_kernel<1> : (form == 2 ? k1a_shuffle_convt_kernel<2> : k1a_shuffle_convt_kernel<3>));
+    LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
+    kern<<<B < sms ? B : sms, K1A_THREADS + (form == 3 ? 32 : 0), s1, s>>>(pa);
+  }
   if (g_tuning[LPB_TUNE_SOFTMAX_EPILOGUE_V2]) {
     // layer 2 on the banded kernel (head_rows_bf16.cu): same GEMM, leaner softmax epilogue
     ConvtRowsParams p2{};

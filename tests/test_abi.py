@@ -193,7 +193,7 @@ def test_round2_entry_points_validate_arguments_without_gpu():
         assert rc == -1, (rc, L.lpb_last_error())
     assert L.lpb_context_gather(C.c_void_p(16), 4, 24, 5, C.c_void_p(16), None) == -1  # items must be 16-byte multiples
     assert L.lpb_set_tuning(99, 1) == -1 and L.lpb_get_tuning(99) == -1
-    for k in range(15):
+    for k in range(16):
         assert 0 <= L.lpb_get_tuning(k) <= 8
 
 

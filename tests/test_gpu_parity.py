@@ -1103,7 +1103,7 @@ def test_kernel_variants_agree(lpb, dev):
         ((kp * gk).sum() * 1e-3 + (hm * hm).sum()).backward()
         return hm.detach().clone(), kp.detach().clone(), cf.detach().clone(), f.grad.float().clone(), list(head.upsampling_layers)[1].weight.grad.clone()
 
-    nkeys = 15
+    nkeys = 16
     saved = [lib.lpb_get_tuning(k) for k in range(nkeys)]
     cur = run()  # the defaults (some keys have more than two settings, e.g. 11 = 2)
     try:
