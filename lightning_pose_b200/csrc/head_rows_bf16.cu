@@ -476,7 +476,7 @@ int launch_convt_rows(ConvtRowsParams p, int sms, cudaStream_t s) {
     // decode hints come from the fused two-pass softmax only (same condition as the kernel's hint_on); every other route
     // marks them invalid
     const bool fused = p.mode == CONVT_ROWS_SOFTMAX && v2 &&
-                       !(p.partials && (g_tuning[LPB_TUNE_SOFTMAX_SPLIT] == 2 || (g_tuning[LPB_TUNE_SOFTMAX_SPLIT] == 1 && p.B < 2 * sms)));
+                       !(p.partials && (g_tuning[LPB_TUNE_SOFTMAX_SPLIT] == 2 || (g_tuning[LPB_TUNE_SOFTMAX_SPLIT] == 1 && p.B < sms)));
     if (!fused || 4 * p.L.Hi * p.L.Wi > 16384 || nbands * CR_TILES > CR_NMASK || !g_tuning[LPB_TUNE_DECODE_HINTS]) {
       LPB_CUDA(cudaMemsetAsync(p.hints, 0, sizeof(int4) * (size_t)p.B * p.cout, s));
       p.hints = nullptr;
@@ -485,10 +485,11 @@ int launch_convt_rows(ConvtRowsParams p, int sms, cudaStream_t s) {
   if (p.mode == CONVT_ROWS_MID) return run(convt_rows_kernel<CONVT_ROWS_MID, 0, false>, per_band);
   if (p.mode == CONVT_ROWS_PLANES) return k17 ? run(convt_rows_kernel<CONVT_ROWS_PLANES, 17, false>, per_band) : run(convt_rows_kernel<CONVT_ROWS_PLANES, 0, false>, per_band);
   // split softmax (statistics launch + normalising launch, both parallel over (frame, band)) when one CTA per frame would
-  // leave SMs idle; with >= one frame per resident CTA the single two-pass kernel is faster (768-frame step: 1.768 vs
-  // 1.802 ms), because a frame's second pass re-reads operands its first pass left in L2.  Key value 2 forces the split.
+  // leave SMs idle (fewer frames than SMs); otherwise the single two-pass kernel is faster, because a frame's second pass
+  // re-reads operands its first pass left in L2 (768-frame step 1.768 vs 1.802 ms; with the 256-frame labeled call fused
+  // as well: step 1.565 vs 1.583 ms, forward-only 0.611 vs 0.635 ms).  Key value 2 forces the split.
   const int split_key = g_tuning[LPB_TUNE_SOFTMAX_SPLIT];
-  if (v2 && p.partials && (split_key == 2 || (split_key == 1 && p.B < 2 * sms))) {
+  if (v2 && p.partials && (split_key == 2 || (split_key == 1 && p.B < sms))) {
     int rc = k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P0, 17, true>, per_band) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P0, 0, true>, per_band);
     if (rc != LPB_OK) return rc;
     return k17 ? run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P1, 17, true>, per_band) : run(convt_rows_kernel<CONVT_ROWS_SOFTMAX_P1, 0, true>, per_band);
