@@ -47,7 +47,7 @@ const char* lpb_build_arch(void);     /* "sm_100a" */
 #define LPB_TUNE_K1A_BULK_XS 4          /* 1: the saved operand copy leaves k1a by TMA bulk stores from the operand stage; 0 (default): producer stores */
 #define LPB_TUNE_DECODE_L2_HINTS 5      /* 1 (default): L2 evict_last / evict_first hints on the decode's two sweeps of a plane */
 #define LPB_TUNE_B3A_PREFETCH 6         /* 1 (default): b3a epilogue issues the next item's TMEM loads before storing the current one */
-#define LPB_TUNE_SOFTMAX_SPLIT 7         /* 1 (default): plane softmax as two launches parallel over (frame, band) when there are fewer frames than resident CTAs, else one per-frame two-pass kernel; 0: never split; 2: always */
+#define LPB_TUNE_SOFTMAX_SPLIT 7         /* 1 (default): plane softmax as two launches parallel over (frame, band) when there are fewer frames than SMs, else one per-frame two-pass kernel; 0: never split; 2: always */
 #define LPB_TUNE_DECODE_WARP_CTAS 8     /* > 0: resident CTAs per SM of the warp-per-plane decode are capped (fewer planes in flight than L2 holds); 0: no cap */
 #define LPB_TUNE_DECODE_REVERSE 9       /* 1: the decode walks the planes last-to-first (the producer's most recent writes are still in L2) */
 #define LPB_TUNE_B3A_TMA_STORE 10       /* 1 (default): b3a stages d features in shared memory and a TMA tensor store scatters them to NCHW; 0: direct 16-byte stores */
