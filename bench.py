@@ -155,14 +155,15 @@ BACKBONE_PARAMS = 23_508_032  # ResNet-50 trunk (94.4 MB of fp32 gr
 
 
 class HotPath:
-    # our own kernel launches per step, counted from the committed ncu launch list (profiles/r02_launches_train_step.csv);
-    # library kernels of torch (a dozen scalar element-wise ops, NCCL) are not counted
-    # per head call: preparation (packs + pads) + k1a + banded layer 2 (softmax statistics + normalising launch) + decode
-    # (warp kernel + queued CTA kernel) = 6;  labeled: + fused targets/MSE (2);  unlabeled: + remap + unsupervised losses (2)
-    LAUNCHES_FWD = 2 * 6 + 2 + 2
-    # unlabeled: unsup bwd, remap bwd, decode windows + dense fallback, then per head backward: preparation, plane dots,
-    # G2 front end, wgrad2, dgrad2, wgrad1, dgrad1 = 7;  labeled: targets/MSE bwd + the same 7
-    LAUNCHES_BWD = (4 + 7) + (1 + 7) + 1  # + the Adam step
+    # our own kernel launches per step, counted from the committed launch lists (profiles/r02_launches_train_step.csv,
+    # profiles/r02_kineto_step.json); library kernels of torch (a dozen scalar element-wise ops, NCCL) are not counted
+    # per head call: preparation (packs + pads) + k1a + banded layer 2 (one two-pass softmax kernel from 148 frames up) +
+    # decode (warp kernel + queued CTA kernel) = 5;  labeled: + fused targets/MSE + its final reduction (2);
+    # unlabeled: + remap + unsupervised losses (2)
+    LAUNCHES_FWD = 2 * 5 + 2 + 2
+    # unlabeled: unsup bwd, remap bwd, decode windows + dense fallback (4), then per head backward: preparation, plane dots,
+    # G2 front end, wgrad2, dgrad2, wgrad1, dgrad1 = 7, + the window patch pass (1);  labeled: targets/MSE bwd + the same 7
+    LAUNCHES_BWD = (4 + 7 + 1) + (1 + 7) + 1  # + the Adam step
 
     def __init__(self, prob, device, fwd_only: bool, world: int = 1, ddp_payload_floats: int = 0, two_streams: bool = True):
         from lightning_pose_b200 import ops
