@@ -40,6 +40,11 @@ def test_argument_validation_without_gpu():
 
     rc = _lib.lib.lpb_decode_fwd(None, 1, 8, 8, 2, 1000.0, None, None, None, None)
     assert rc == -1 and b"null pointer" in _lib.lib.lpb_last_error()
+    # the hinted forms validate like the plain ones (hints themselves are optional: NULL = plain route)
+    rc = _lib.lib.lpb_decode_fwd_hinted(None, 1, 8, 8, 2, 1000.0, None, None, None, None, None)
+    assert rc == -1 and b"null pointer" in _lib.lib.lpb_last_error()
+    rc = _lib.lib.lpb_head_fwd_bf16_hinted(None, 1, 384, 16, 16, None, None, 17, None, None, 0, 1, None, None, None, None, None)
+    assert rc == -1 and b"null pointer" in _lib.lib.lpb_last_error()
     rc = _lib.lib.lpb_decode_prepare(8, 8, 7)
     assert rc == -1 and b"bad shape" in _lib.lib.lpb_last_error()
     n = ctypes.c_size_t(0)
