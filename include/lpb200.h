@@ -53,7 +53,7 @@ const char* lpb_build_arch(void);     /* "sm_100a" */
 #define LPB_TUNE_B3A_TMA_STORE 10       /* 1 (default): b3a stages d features in shared memory and a TMA tensor store scatters them to NCHW; 0: direct 16-byte stores */
 #define LPB_TUNE_WGRAD_SWAP 11          /* layer-1 weight gradient: 1: A = features (M = 128 channels), B = gradient rows (N = 80); 2 (default): the same with the gradient rows staged twice, one row apart, side by side along N (N = 160: two shifts per MMA); 0: A = gradient rows */
 #define LPB_TUNE_G2_PATCH 12            /* 1 (default): decode windows enter the gradient rows in a patch pass (one warp per plane) after a look-up-free streaming pass; 0: look-ups fused into the streaming pass */
-#define LPB_TUNE_MMA_TILE_INNER 13      /* 1: k1a issues its MMAs tile-innermost (consecutive MMAs accumulate into different TMEM tiles); 0: tile-outermost */
+#define LPB_TUNE_MMA_TILE_INNER 13      /* 1 (default; measured neutral): k1a issues its MMAs tile-innermost (consecutive MMAs accumulate into different TMEM tiles); 0: tile-outermost */
 #define LPB_TUNE_DECODE_HINTS 14        /* 1: the fused two-pass softmax emits per-plane decode hints (arg max + largest value outside its 32x32 box) and the decode skips its plane sweeps when they allow; 0 (default): hints never produced (measured: what the decode saves, the issue-bound softmax epilogue pays) */
 #define LPB_TUNE_K1A_XS_COPY 15         /* k1a's saved operand copy: 2 (default): a dedicated extra warp sends each finished operand stage out with TMA bulk stores (the transposers store nothing); 1: streamed out of the finished stage by the transposer threads (whole sectors); 0: each transposer thread stores the rows it produced */
 #define LPB_TUNE_COUNT 16
